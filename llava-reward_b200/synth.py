@@ -1,0 +1,189 @@
+"""Deterministic synthetic weights and inputs for the reward-scoring path.
+
+There is no network in the build/bench environment, so weights are random-init of the
+named architecture (BASELINE.json `configs`). The generator is a counter-based integer
+hash followed by ONE fp32 multiply, so the same (name, seed) gives bit-identical values
+from torch on CPU (golden generation, oracle) and on CUDA (tests, bench) without moving
+16 GB of fp32 weights around.
+
+Tensor names follow the reference state_dict (``Phi3VForCausalLM`` +
+``CustomRewardModel`` heads, reference rw_model_general_preference.py:306-333,
+modeling_phi3_v.py:118-205,1332-1368) plus PEFT-style ``lora_A`` / ``lora_B`` entries.
+"""
+from __future__ import annotations
+
+import zlib
+from typing import Callable, Dict, Iterator, List, Optional, Tuple
+
+import torch
+
+from .config import RewardConfig, num_image_tokens
+
+_M32 = 0xFFFFFFFF
+_IH_STD = 65536.0 / (3.0 ** 0.5)  # std of the sum of four U{0..65535} (Irwin-Hall, n=4)
+
+
+def _fmix32(x: torch.Tensor) -> torch.Tensor:
+    """murmur3 finaliser on int64 lanes holding 32-bit values (only the low 32 bits matter)."""
+    x = x ^ (x >> 16)
+    x = (x * 0x85EBCA6B) & _M32
+    x = x ^ (x >> 13)
+    x = (x * 0xC2B2AE35) & _M32
+    x = x ^ (x >> 16)
+    return x
+
+
+def hash_normal(name: str, shape, std: float, seed: int, device="cpu", mean: float = 0.0,
+                dtype=torch.float32, chunk: int = 1 << 24) -> torch.Tensor:
+    """Pseudo-normal tensor: sum of four 16-bit uniforms, centred, times one fp32 scale."""
+    n = 1
+    for s in shape:
+        n *= int(s)
+    out = torch.empty(n, dtype=dtype, device=device)
+    key = (zlib.crc32(name.encode()) ^ (seed * 0x9E3779B1)) & _M32
+    scale = torch.tensor(std / _IH_STD, dtype=torch.float32, device=device)
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        idx = torch.arange(lo, hi, dtype=torch.int64, device=device)
+        a = _fmix32(((idx * 2) * 0x9E3779B1 + key) & _M32)
+        b = _fmix32(((idx * 2 + 1) * 0x9E3779B1 + key) & _M32)
+        s = (a & 0xFFFF) + (a >> 16) + (b & 0xFFFF) + (b >> 16) - 131070
+        v = s.to(torch.float32) * scale
+        if mean != 0.0:
+            v = v + mean
+        out[lo:hi] = v.to(dtype)
+    return out.view(*shape)
+
+
+def hash_randint(name: str, n: int, lo: int, hi: int, seed: int, device="cpu") -> torch.Tensor:
+    """Deterministic integers in [lo, hi)."""
+    key = (zlib.crc32(name.encode()) ^ (seed * 0x9E3779B1)) & _M32
+    idx = torch.arange(n, dtype=torch.int64, device=device)
+    h = _fmix32((idx * 0x9E3779B1 + key) & _M32)
+    return lo + h % (hi - lo)
+
+
+# --------------------------------------------------------------------------------------
+# parameter inventory
+# --------------------------------------------------------------------------------------
+CLIP_PREFIX = "model.vision_embed_tokens.img_processor.vision_model."
+
+
+def param_specs(cfg: RewardConfig) -> Iterator[Tuple[str, Tuple[int, ...], str]]:
+    """Yield (name, shape, kind) for every parameter the scoring path reads.
+
+    kind: 'w' = N(0, std), 'n' = norm weight 1 + N(0, std), all biases are 'w' as well so
+    that a dropped bias / separator / LoRA branch is visible to the parity tests
+    (default init leaves those at zero).
+    """
+    H, I, V = cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size
+    D, DI = cfg.clip_hidden, cfg.clip_intermediate
+    yield "model.embed_tokens.weight", (V, H), "w"
+    ve = "model.vision_embed_tokens."
+    yield ve + "glb_GN", (1, 1, 4 * D), "w"
+    yield ve + "sub_GN", (1, 1, 1, 4 * D), "w"
+    yield ve + "img_projection.0.weight", (H, 4 * D), "w"
+    yield ve + "img_projection.0.bias", (H,), "w"
+    yield ve + "img_projection.2.weight", (H, H), "w"
+    yield ve + "img_projection.2.bias", (H,), "w"
+    c = CLIP_PREFIX
+    yield c + "embeddings.class_embedding", (D,), "w"
+    yield c + "embeddings.patch_embedding.weight", (D, 3, cfg.patch, cfg.patch), "w"
+    yield c + "embeddings.position_embedding.weight", (cfg.clip_tokens, D), "w"
+    yield c + "pre_layrnorm.weight", (D,), "n"
+    yield c + "pre_layrnorm.bias", (D,), "w"
+    for i in range(cfg.clip_layers):
+        p = f"{c}encoder.layers.{i}."
+        for proj in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            yield p + f"self_attn.{proj}.weight", (D, D), "w"
+            yield p + f"self_attn.{proj}.bias", (D,), "w"
+        yield p + "layer_norm1.weight", (D,), "n"
+        yield p + "layer_norm1.bias", (D,), "w"
+        yield p + "mlp.fc1.weight", (DI, D), "w"
+        yield p + "mlp.fc1.bias", (DI,), "w"
+        yield p + "mlp.fc2.weight", (D, DI), "w"
+        yield p + "mlp.fc2.bias", (D,), "w"
+        yield p + "layer_norm2.weight", (D,), "n"
+        yield p + "layer_norm2.bias", (D,), "w"
+    r = cfg.lora_rank
+    for i in range(cfg.num_layers):
+        p = f"model.layers.{i}."
+        lin = (("self_attn.qkv_proj", 3 * H, H), ("self_attn.o_proj", H, H),
+               ("mlp.gate_up_proj", 2 * I, H), ("mlp.down_proj", H, I))
+        for nm, o, k in lin:
+            yield p + nm + ".weight", (o, k), "w"
+            if cfg.use_lora:
+                yield p + nm + ".lora_A.weight", (r, k), "w"
+                yield p + nm + ".lora_B.weight", (o, r), "w"
+        yield p + "input_layernorm.weight", (H,), "n"
+        yield p + "post_attention_layernorm.weight", (H,), "n"
+    yield "model.norm.weight", (H,), "n"
+    yield "value_head.weight", (cfg.vhd, H), "w"
+    if cfg.add_cross_attention:
+        yield "W_q.weight", (H, H), "w"
+        yield "W_k.weight", (H, H), "w"
+        yield "W_v.weight", (H, H), "w"
+        yield "ca_layernorm.weight", (H,), "n"
+
+
+class SynthProvider:
+    """Callable ``name -> tensor`` producing synthetic parameters on demand."""
+
+    def __init__(self, cfg: RewardConfig, seed: int = 1234, std: float = 0.02, device="cpu",
+                 dtype=torch.float32):
+        self.cfg, self.seed, self.std, self.device, self.dtype = cfg, seed, std, device, dtype
+        self.specs: Dict[str, Tuple[Tuple[int, ...], str]] = {n: (s, k) for n, s, k in param_specs(cfg)}
+
+    def names(self) -> List[str]:
+        return list(self.specs)
+
+    def __contains__(self, name: str) -> bool:
+        return name in self.specs
+
+    def __call__(self, name: str) -> torch.Tensor:
+        shape, kind = self.specs[name]
+        mean = 1.0 if kind == "n" else 0.0
+        return hash_normal(name, shape, self.std, self.seed, device=self.device, mean=mean, dtype=self.dtype)
+
+
+# --------------------------------------------------------------------------------------
+# synthetic inputs (the batch layout of reference reward_dataset.py:137-180 after squeeze(1))
+# --------------------------------------------------------------------------------------
+BOS, USER, NL, EOS, PAD = 1, 32010, 13, 32000, 32000
+
+
+def synth_batch(cfg: RewardConfig, batch: int, image_hw: Tuple[int, int], seq_len: Optional[int],
+                seed: int = 7, device="cpu", text_len_range: Tuple[int, int] = (40, 128),
+                tag: str = "c", image_hw_list=None):
+    """Build (input_ids, attention_mask, pixel_values, image_sizes) for `batch` samples.
+
+    Every sample is  [pad..., BOS, <|user|>, \\n, -1 x N_v, \\n, text..., EOS]  left-padded to
+    `seq_len` (None -> longest sample). Pixel values are N(0,1) in the real crop slots and zero
+    in the padded slots (what ``pad_to_max_num_crops_tensor`` produces,
+    reference processing_phi3_v.py:128-136).
+    """
+    ids_rows, lens = [], []
+    C = cfg.num_crops + 1
+    pix = torch.zeros(batch, C, 3, cfg.image_size, cfg.image_size, dtype=torch.float32, device=device)
+    sizes = torch.zeros(batch, 2, dtype=torch.int64)
+    tl = hash_randint(f"textlen.{tag}", batch, text_len_range[0], text_len_range[1], seed).tolist()
+    for b in range(batch):
+        h, w = image_hw_list[b] if image_hw_list is not None else image_hw
+        sizes[b, 0], sizes[b, 1] = h, w
+        nv = num_image_tokens(h, w)
+        ncrop = (h // 336) * (w // 336) + 1
+        pix[b, :ncrop] = hash_normal(f"pixels.{tag}.{b}", (ncrop, 3, cfg.image_size, cfg.image_size), 1.0, seed,
+                                     device=device)
+        text = hash_randint(f"text.{tag}.{b}", tl[b], 3, 31999, seed).tolist()
+        row = [BOS, USER, NL] + [-1] * nv + [NL] + text + [EOS]
+        ids_rows.append(row)
+        lens.append(len(row))
+    S = max(lens) if seq_len is None else seq_len
+    ids = torch.full((batch, S), PAD, dtype=torch.int64)
+    mask = torch.zeros((batch, S), dtype=torch.int64)
+    for b, row in enumerate(ids_rows):
+        if len(row) > S:
+            raise ValueError(f"sample {b} needs {len(row)} tokens > seq_len {S}")
+        ids[b, S - len(row):] = torch.tensor(row, dtype=torch.int64)
+        mask[b, S - len(row):] = 1
+    return ids.to(device), mask.to(device), pix, sizes.to(device)

@@ -1,0 +1,27 @@
+"""Helpers shared by the golden-vector tests."""
+import os
+
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_fixture(name):
+    path = os.path.join(GOLDEN_DIR, f"{name}.pt")
+    return torch.load(path, weights_only=False)
+
+
+def fixture_cfg(fx):
+    from llava_reward_b200.config import RewardConfig
+    return RewardConfig(**fx["cfg_overrides"])
+
+
+def fixture_batch(fx, entry, cfg, device="cpu"):
+    from llava_reward_b200.synth import synth_batch
+    hw = [tuple(x) for x in entry["image_hw"]]
+    return synth_batch(cfg, entry["batch"], hw[0], entry["seq_len"], seed=fx["seed_x"], tag=entry["tag"],
+                       image_hw_list=hw, device=device)
+
+
+def strided(t, stride, n=2048):
+    return t.detach().float().flatten()[::stride][:n].cpu()

@@ -1,0 +1,43 @@
+"""The oracle restatement must reproduce the reference's own outputs (fixtures made by
+tests/golden/make_golden.py, which executes /root/reference). fp32 CPU, tolerance 1e-4 on
+rewards (north_star: 1e-4 against the reference's fp32)."""
+import pytest
+import torch
+
+from golden_util import fixture_batch, fixture_cfg, load_fixture, strided
+from oracle import reward_oracle as O
+from llava_reward_b200.synth import SynthProvider
+
+TOL = 1e-4
+
+
+@pytest.mark.parametrize("case", ["slim_gpm", "slim_bt"])
+def test_oracle_matches_reference(case):
+    fx = load_fixture(case)
+    cfg = fixture_cfg(fx)
+    P = O.Params(SynthProvider(cfg, seed=fx["seed_w"]), dtype=torch.float32)
+    rewards = {}
+    for entry in fx["batches"]:
+        ids, mask, pix, sizes = fixture_batch(fx, entry, cfg)
+        assert ids.shape[1] == entry["S"]
+        taps = {}
+        with torch.no_grad():
+            r = O.custom_forward(P, cfg, ids, mask, pix, sizes, taps)
+        rewards[entry["tag"]] = r
+        assert r.shape == entry["reward"].shape
+        assert (r - entry["reward"]).abs().max().item() < TOL
+        ref_taps = entry["taps"]
+        mine = {"inputs_embeds": taps["inputs_embeds"], "hidden_0": taps["hidden_0"],
+                "last_hidden": taps["last_hidden"]}
+        for k, t in mine.items():
+            g = ref_taps[k]
+            assert list(t.shape) == g["shape"], k
+            # only valid (non-pad) rows are defined behaviour; pad rows are excluded via the mask
+            valid = mask.bool()[:, :, None].expand_as(t)
+            a = strided(torch.where(valid, t, torch.zeros_like(t)), g["stride"])
+            shape_mask = strided(valid.float(), g["stride"])
+            assert ((a - g["vals"] * shape_mask).abs().max().item()) < 2e-4, k
+        assert (taps["last_hidden"][:, -1, :64] - entry["last_hidden_eos"]).abs().max().item() < 2e-4
+    p = O.preference_compute(cfg, rewards["c"], rewards["r"])
+    assert (p - fx["prob"]).abs().max().item() < 1e-3
+    assert ((p > 0.5) == (fx["prob"] > 0.5)).all()
