@@ -1,0 +1,142 @@
+/*
+ * llava_reward_b200.h - C ABI of libllavareward.so (hand-written sm_100a CUDA).
+ *
+ * The reference (sjz5202/LLaVA-Reward) has no FFI/plugin layer of its own: its hot path is
+ * Python calling torch/cuBLAS/cuDNN/flash-attn. This header is therefore the
+ * boundary a maintainer binds with ctypes (INTEGRATION.md shows the stub) to replace, call site
+ * by call site, the library launches issued from
+ *   llava_reward/models/rw_model_general_preference.py:334-448   (custom_forward)
+ *   llava_reward/models/base_mllm/phi3_v/modeling_phi3_v.py      (Phi3VModel.forward and below)
+ *   llava_reward/models/base_mllm/phi3_v/processing_phi3_v.py    (Phi3VImageProcessor.preprocess)
+ *   eval/reward_adaptor_loader.py:174-181                        (preference_compute)
+ *
+ * Conventions: every entry takes raw DEVICE pointers, explicit sizes and leading dimensions
+ * (in elements), and a cudaStream_t passed as void* LAST. Nothing allocates, nothing keeps global
+ * state except a cached driver entry point; calls are re-entrant per stream. Return value: 0 = ok,
+ * negative = LR_ERR_*, positive = cudaError_t passthrough from the launch. bf16 tensors are
+ * row-major; "ld" = elements between consecutive rows. There is no CPU fallback: on a machine
+ * without an sm_100 device every compute entry returns an error.
+ */
+#ifndef LLAVA_REWARD_B200_H
+#define LLAVA_REWARD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LR_OK 0
+#define LR_ERR_BAD_ARG (-1)     /* null pointer, non-positive size, unsupported shape */
+#define LR_ERR_ALIGN (-2)       /* pointer / leading dimension not 16-byte aligned */
+#define LR_ERR_NO_DRIVER (-3)   /* cuTensorMapEncodeTiled not obtainable (no CUDA driver) */
+#define LR_ERR_UNSUPPORTED (-4) /* device is not sm_100 */
+
+/* GEMM epilogues (what follows the nn.Linear in the reference) */
+#define LR_EPI_NONE 0           /* C = bf16(acc)                                   W_q/W_k/W_v, lora_A */
+#define LR_EPI_BIAS 1           /* C = bf16(acc + bias)                            CLIP q|k|v, projector.2 */
+#define LR_EPI_BIAS_QUICKGELU 2 /* x=bf16(acc+bias); C = x*sigmoid(1.702x)         CLIP fc1 (modeling_phi3_v.py:71) */
+#define LR_EPI_BIAS_GELU 3      /* x=bf16(acc+bias); C = gelu_erf(x)               projector.0 + nn.GELU (:172-179) */
+#define LR_EPI_RESIDUAL 4       /* C = bf16(bf16(acc) + R)                         o_proj / down_proj (:1189,1194) */
+#define LR_EPI_BIAS_RESIDUAL 5  /* C = bf16(bf16(acc+bias) + R)                    CLIP out_proj / fc2 */
+#define LR_EPI_SWIGLU 6         /* W rows packed [gate128|up128] per 256; C[:,N/2] = up*silu(gate)  Phi3MLP (:566-572) */
+
+#define LR_GEMM_TCGEN05 0 /* tcgen05.mma + TMEM + TMA pipeline (product path) */
+#define LR_GEMM_SIMT 1    /* plain CUDA-core kernel, used only to cross-check the tcgen05 path in tests */
+
+int lr_version(void);
+/* 0 when the current CUDA device is compute capability 10.x, else LR_ERR_UNSUPPORTED / cudaError. */
+int lr_device_check(void);
+
+/* C[M, N'] = epilogue(A[M,K] . W[N,K]^T); A, W, C, R bf16; bias bf16 [N]; fp32 accumulation.
+ * N' = N/2 for LR_EPI_SWIGLU else N. K % 64 == 0, N % 128 == 0; M arbitrary (TMA zero-fills).
+ * LoRA is applied by K-extension: A = [x | x.A^T], W = [W0 | (alpha/r).B]  (peft lora.Linear.forward).
+ * Replaces: every nn.Linear / F.linear on the path (modeling_phi3_v.py:101-114,172-179,567-572,769,880;
+ * rw_model_general_preference.py:378-380; HF modeling_clip.py CLIPMLP/CLIPAttention). */
+int lr_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
+                 int epilogue, const void* bias, const void* R, int ldr, int impl, void* stream);
+
+/* y[i,:] = w * bf16(x[r,:] * rsqrt(mean(x[r,:]^2) + eps)),  r = row_index ? row_index[i] : i.
+ * Replaces Phi3RMSNorm.forward (modeling_phi3_v.py:386-391). cols % 8 == 0, cols <= 8192. */
+int lr_rmsnorm_bf16(const void* x, int ldx, const int* row_index, const void* w, void* y, int ldy, int rows,
+                    int cols, float eps, void* stream);
+
+/* y = LayerNorm(x) * w + b over the last dim (fp32 statistics, one rounding). Replaces nn.LayerNorm in
+ * HF CLIPEncoderLayer / pre_layrnorm (modeling_clip.py). cols % 8 == 0, cols <= 8192. */
+int lr_layernorm_bf16(const void* x, int ldx, const void* w, const void* b, void* y, int ldy, int rows, int cols,
+                      float eps, void* stream);
+
+/* Patch-embedding operand: pixels fp32 [*,3,336,336] (crop c read at slot crop_src[c]) ->
+ * A[n_crops*576, 640] bf16, column = ch*196 + ky*14 + kx (Conv2d weight order), columns 588..639 zero.
+ * Replaces the im2col inside cuDNN conv (modeling_clip.py CLIPVisionEmbeddings.forward). */
+int lr_clip_im2col(const float* pixels, const int* crop_src, void* A, int n_crops, void* stream);
+
+/* tokens[c*577+t,:] = LayerNorm( (t==0 ? class_emb : patch[c*576+t-1,:]) + pos_emb[t,:] ) : CLS concat,
+ * position add (bf16) and pre_layrnorm fused (modeling_clip.py CLIPVisionEmbeddings.forward + pre_layrnorm). */
+int lr_clip_embed_ln(const void* patch, const void* class_emb, const void* pos_emb, const void* ln_w,
+                     const void* ln_b, void* tokens, int n_crops, float eps, void* stream);
+
+/* Flash-style prefill attention, bf16 in/out, fp32 softmax. q/k/v point at column 0 of the first head inside a
+ * fused projection buffer with row stride ld_qkv; head h occupies columns [h*head_dim, (h+1)*head_dim).
+ * Sequence s owns rows [s*rows_per_seq, (s+1)*rows_per_seq); only rows [start, start+len) are valid
+ * (seq_start/seq_len may be NULL = whole slot). Invalid rows of o are zero-filled.
+ * head_dim 64 (CLIP, non-causal; replaces CLIPAttentionFA2, modeling_phi3_v.py:85-115) or
+ * 96 (Phi-3, causal varlen; replaces Phi3FlashAttention2._flash_attention_forward, :888-986). */
+int lr_attention_bf16(const void* q, const void* k, const void* v, void* o, int ld_qkv, int ld_o, int n_seq,
+                      int rows_per_seq, const int* seq_start, const int* seq_len, int n_heads, int head_dim,
+                      int causal, float scale, void* stream);
+
+/* In-place su/longrope rotary embedding on the q and k thirds of a fused qkv buffer [rows, 3*n_heads*head_dim]:
+ * x = bf16(bf16(x*cos) + bf16(rot_half(x)*sin)) with bf16 tables cos/sin[pos, head_dim/2].
+ * Replaces Phi3SuScaledRotaryEmbedding + apply_rotary_pos_emb (modeling_phi3_v.py:438-476, 529-553). */
+int lr_rope_su_bf16(void* qkv, int ld, const int* position_ids, const void* cos_tab, const void* sin_tab,
+                    int rows, int n_heads, int head_dim, void* stream);
+
+/* One pass over input_ids / attention_mask [B,S] (int64):
+ *   position_ids = cumsum(mask)-1, 1 where mask==0     (rw_model_general_preference.py:344-345)
+ *   img_ord[b,s] = ordinal of s among the image positions (-1e9 < id < 0) of row b, else -1 (modeling_phi3_v.py:228)
+ *   seq_start/seq_len = first valid column / number of valid columns; eos_row = b*S + last valid column (:420,439)
+ *   n_img[b] = number of image positions; flags[0] |= 1 if some mask row is not one contiguous run. */
+int lr_token_plan(const int64_t* input_ids, const int64_t* attention_mask, int B, int S, int* position_ids,
+                  int* img_ord, int* seq_start, int* seq_len, int* eos_row, int* n_img, int* flags, void* stream);
+
+/* per-sample plan record (int32 x 8) shared by lr_hd_gather_bf16 / lr_embed_scatter_bf16 / lr_skipca_* */
+#define LR_PLAN_STRIDE 8
+#define LR_PLAN_HCROP 0     /* image_sizes[b][0] / 336 */
+#define LR_PLAN_WCROP 1     /* image_sizes[b][1] / 336 */
+#define LR_PLAN_CROP_BASE 2 /* index of the sample's global crop in the compacted crop list */
+#define LR_PLAN_ROW_BASE 3  /* first row of the sample in the concatenated image-token matrix */
+#define LR_PLAN_NV 4        /* number of image tokens of the sample */
+
+/* HD feature transform: CLIP tokens [n_crops*577, 1024] (row 0 of each crop = CLS, skipped) ->
+ * rows [sum N_v, 4096] in 'sub_glb' order with sub_GN newlines and the glb_GN separator.
+ * Replaces hd_feature_transform / reshape_hd_patches_2x2merge / add_image_newline (modeling_phi3_v.py:254-362). */
+int lr_hd_gather_bf16(const void* clip_tokens, const int* plan, const void* sub_gn, const void* glb_gn, void* rows,
+                      int B, int max_nv, void* stream);
+
+/* hidden[b,s,:] = img_ord[b,s] >= 0 ? img_proj[row_base[b] + img_ord[b,s], :] : wte[clamp(id,0,V), :].
+ * Replaces wte + index_put (modeling_phi3_v.py:230-231, 247-249). */
+int lr_embed_scatter_bf16(const int64_t* input_ids, const int* img_ord, const int* plan, const void* wte,
+                          const void* img_proj, void* hidden, int ldh, int B, int S, int H, int V, void* stream);
+
+/* SkipCA, last-valid-token row only (the only row the reference consumes in eval, :420-421/439-444):
+ * scores[b,j] = bf16(bf16(q_b . K_bj) / sqrt(H)), j < N_v(b).  kv = [K | V] rows of the concatenated image tokens. */
+int lr_skipca_scores(const void* q, int ldq, const void* kv, int ldkv, const int* plan, float* scores, int B, int H,
+                     int max_nv, void* stream);
+
+/* reward[b,:] = value_head( ca_ln( x_b + sum_j softmax_j(scores_b over max_nv incl. zero-padded rows) V_bj ) ).
+ * scores == NULL skips the cross-attention (BT / no-SkipCA models: reward = value_head(x_b)).
+ * Replaces rw_model_general_preference.py:381-386 (softmax, bmm, residual, ca_layernorm) and :407-448. */
+int lr_skipca_head(const float* scores, const void* kv, int ldkv, const int* plan, const void* x, int ldx,
+                   const void* ca_ln_w, const void* value_head_w, void* reward, int B, int H, int max_nv, int vhd,
+                   float eps, void* stream);
+
+/* prob[i] = sigmoid((c0*r1 - c1*r0)/tau) (GPM, vhd==2) or sigmoid((c - r)/tau), bf16 arithmetic like the
+ * reference, fp32 output. Replaces preference_compute (eval/reward_adaptor_loader.py:174-181). */
+int lr_preference(const void* chosen, const void* reject, float* prob, int n, int vhd, int is_gpm, float tau,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLAVA_REWARD_B200_H */

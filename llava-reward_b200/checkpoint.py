@@ -1,0 +1,86 @@
+"""Checkpoint ingestion: HF Phi-3.5-vision safetensors + the reference's `save_model_lora` directory layout
+(reference llava_reward/utils/deepspeed.py:333-417: pytorch_model.bin with value_head / W_q / W_k / W_v /
+ca_layernorm / img_projection keys, lora/adapter_model.{bin,safetensors}, reward_config.yaml) -> a
+``name -> tensor`` provider with the reference state_dict names that `pack_weights` consumes.
+"""
+from __future__ import annotations
+
+import glob
+import json
+import os
+from typing import Callable, Dict, Optional, Tuple
+
+import torch
+
+from .config import RewardConfig
+
+
+def _load_file(path: str) -> Dict[str, torch.Tensor]:
+    if path.endswith(".safetensors"):
+        from safetensors.torch import load_file
+        return load_file(path)
+    return torch.load(path, map_location="cpu", weights_only=True)
+
+
+def checkpoint_provider(cfg: RewardConfig, pretrain_dir: str, pm_path: Optional[str],
+                        ft_projector: bool = False) -> Tuple[RewardConfig, Callable[[str], torch.Tensor]]:
+    if not os.path.isdir(pretrain_dir):
+        raise FileNotFoundError(f"args.pretrain={pretrain_dir!r} is not a local directory (no network access: "
+                                "hub ids cannot be resolved) - use 'synthetic' for random-init weights")
+    with open(os.path.join(pretrain_dir, "config.json")) as f:
+        hf = json.load(f)
+    rs = hf.get("rope_scaling") or {}
+    cfg.vocab_size = hf.get("vocab_size", cfg.vocab_size)
+    cfg.hidden_size = hf.get("hidden_size", cfg.hidden_size)
+    cfg.intermediate_size = hf.get("intermediate_size", cfg.intermediate_size)
+    cfg.num_layers = hf.get("num_hidden_layers", cfg.num_layers)
+    cfg.num_heads = hf.get("num_attention_heads", cfg.num_heads)
+    cfg.rms_eps = hf.get("rms_norm_eps", cfg.rms_eps)
+    cfg.rope_theta = hf.get("rope_theta", cfg.rope_theta)
+    cfg.max_position_embeddings = hf.get("max_position_embeddings", cfg.max_position_embeddings)
+    cfg.original_max_position_embeddings = hf.get("original_max_position_embeddings",
+                                                   cfg.original_max_position_embeddings)
+    if rs:
+        cfg.short_factor, cfg.long_factor = list(rs["short_factor"]), list(rs["long_factor"])
+    tensors: Dict[str, torch.Tensor] = {}
+    files = sorted(glob.glob(os.path.join(pretrain_dir, "*.safetensors"))) or \
+        sorted(glob.glob(os.path.join(pretrain_dir, "pytorch_model*.bin")))
+    if not files:
+        raise FileNotFoundError(f"no *.safetensors / pytorch_model*.bin under {pretrain_dir}")
+    for fpath in files:
+        tensors.update(_load_file(fpath))
+    tensors = {k.replace("model.vision_embed_tokens.wte.", "model.embed_tokens."): v for k, v in tensors.items()}
+    cfg.use_lora = False
+    if pm_path:
+        # LoRA adapter saved by PEFT: keys 'base_model.model.<module>.lora_A.weight' (maybe with '.default')
+        for cand in ("adapter_model.safetensors", "adapter_model.bin"):
+            p = os.path.join(pm_path, "lora", cand)
+            if os.path.exists(p):
+                for k, v in _load_file(p).items():
+                    k = k.replace("base_model.model.", "", 1).replace(".default", "")
+                    tensors[k] = v
+                cfg.use_lora = True
+                acfg = os.path.join(pm_path, "lora", "adapter_config.json")
+                if os.path.exists(acfg):
+                    with open(acfg) as f:
+                        a = json.load(f)
+                    cfg.lora_rank, cfg.lora_alpha = int(a.get("r", cfg.lora_rank)), float(a.get("lora_alpha", cfg.lora_alpha))
+                break
+        heads = os.path.join(pm_path, "pytorch_model.bin")
+        if os.path.exists(heads):
+            sd = torch.load(heads, map_location="cpu", weights_only=True)
+            # key selection mirrors reference eval/reward_adaptor_loader.py:46-60
+            for k, v in sd.items():
+                leaf = k.split(".")[-1]
+                for mod in ("value_head", "W_q", "W_k", "W_v", "ca_layernorm"):
+                    if mod in k:
+                        tensors[f"{mod}.{leaf}"] = v
+                if ft_projector and "img_projection" in k:
+                    tensors["model.vision_embed_tokens.img_projection." + ".".join(k.split(".")[-2:])] = v
+
+    def get(name: str) -> torch.Tensor:
+        if name not in tensors:
+            raise KeyError(f"checkpoint is missing parameter {name!r}")
+        return tensors[name]
+
+    return cfg, get

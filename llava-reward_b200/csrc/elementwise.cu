@@ -1,0 +1,220 @@
+// Index / gather kernels around the GEMMs: token plan (positions, image ordinals, EOS rows), su-RoPE,
+// HD feature transform gather, embedding gather + image-row scatter. All HBM-bound, 16-byte accesses.
+#include "common.cuh"
+
+namespace lr {
+
+// ---------------------------------------------------------------- token plan: one CTA (256 threads) per sample
+__global__ void __launch_bounds__(256)
+token_plan_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mask, int S, int* __restrict__ pos,
+                  int* __restrict__ img_ord, int* __restrict__ seq_start, int* __restrict__ seq_len,
+                  int* __restrict__ eos_row, int* __restrict__ n_img, int* __restrict__ flags) {
+  __shared__ int wsum_m[8], wsum_i[8];
+  __shared__ int s_first, s_last;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    s_first = S;
+    s_last = -1;
+  }
+  __syncthreads();
+  int run_m = 0, run_i = 0;  // running totals before this tile (identical in all threads)
+  int my_first = S, my_last = -1;
+  for (int s0 = 0; s0 < S; s0 += 256) {
+    const int s = s0 + tid;
+    const bool in = s < S;
+    const int64_t id = in ? ids[size_t(b) * S + s] : 0;
+    const bool m = in && mask[size_t(b) * S + s] != 0;
+    const bool im = in && id < 0 && id > -1000000000LL;
+    const unsigned bm = __ballot_sync(0xffffffffu, m), bi = __ballot_sync(0xffffffffu, im);
+    const unsigned lt = (1u << lane) - 1u;
+    if (lane == 0) {
+      wsum_m[warp] = __popc(bm);
+      wsum_i[warp] = __popc(bi);
+    }
+    __syncthreads();
+    int pre_m = 0, pre_i = 0, tot_m = 0, tot_i = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) {
+        pre_m += wsum_m[w];
+        pre_i += wsum_i[w];
+      }
+      tot_m += wsum_m[w];
+      tot_i += wsum_i[w];
+    }
+    if (in) {
+      const int incl = run_m + pre_m + __popc(bm & lt) + (m ? 1 : 0);
+      pos[size_t(b) * S + s] = m ? incl - 1 : 1;
+      img_ord[size_t(b) * S + s] = im ? run_i + pre_i + __popc(bi & lt) : -1;
+      if (m) {
+        my_first = min(my_first, s);
+        my_last = max(my_last, s);
+      }
+    }
+    run_m += tot_m;
+    run_i += tot_i;
+    __syncthreads();
+  }
+  if (my_last >= 0) {
+    atomicMin(&s_first, my_first);
+    atomicMax(&s_last, my_last);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const int first = run_m ? s_first : 0;
+    const int last = run_m ? s_last : S - 1;  // all-zero mask row: argmax(flip)=0 -> S-1, as the reference
+    seq_start[b] = first;
+    seq_len[b] = run_m;
+    eos_row[b] = b * S + last;
+    n_img[b] = run_i;
+    if (run_m && last - first + 1 != run_m) atomicOr(flags, 1);
+  }
+}
+
+// ---------------------------------------------------------------- su-RoPE, in place on q|k of a fused qkv row
+// work item = (which in {q,k}, head, 8-wide chunk of the first half); 8 x (x1, x2) pairs per item.
+__global__ void __launch_bounds__(192)
+rope_su_kernel(bf16* __restrict__ qkv, int ld, const int* __restrict__ position_ids, const bf16* __restrict__ cos_tab,
+               const bf16* __restrict__ sin_tab, int n_heads, int head_dim) {
+  const int row = blockIdx.x;
+  const int half = head_dim >> 1, cph = half >> 3;  // chunks per half-head
+  const int items = 2 * n_heads * cph;
+  const int p = position_ids[row];
+  bf16* base = qkv + size_t(row) * ld;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int c = it % cph, hh = it / cph;  // hh in [0, 2*n_heads): q heads then k heads (contiguous columns)
+    bf16* x1p = base + hh * head_dim + c * 8;
+    bf16* x2p = x1p + half;
+    float x1[8], x2[8], cs[8], sn[8], o1[8], o2[8];
+    {
+      uint4 u = *reinterpret_cast<const uint4*>(x1p);
+      float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      x1[0] = a.x, x1[1] = a.y, x1[2] = b.x, x1[3] = b.y, x1[4] = cc.x, x1[5] = cc.y, x1[6] = d.x, x1[7] = d.y;
+      u = *reinterpret_cast<const uint4*>(x2p);
+      a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      x2[0] = a.x, x2[1] = a.y, x2[2] = b.x, x2[3] = b.y, x2[4] = cc.x, x2[5] = cc.y, x2[6] = d.x, x2[7] = d.y;
+      u = ldg128(cos_tab + size_t(p) * half + c * 8);
+      a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      cs[0] = a.x, cs[1] = a.y, cs[2] = b.x, cs[3] = b.y, cs[4] = cc.x, cs[5] = cc.y, cs[6] = d.x, cs[7] = d.y;
+      u = ldg128(sin_tab + size_t(p) * half + c * 8);
+      a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      sn[0] = a.x, sn[1] = a.y, sn[2] = b.x, sn[3] = b.y, sn[4] = cc.x, sn[5] = cc.y, sn[6] = d.x, sn[7] = d.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // q_embed = (q * cos) + (rotate_half(q) * sin), every product and the sum rounded to bf16
+      o1[j] = bf16_round(x1[j] * cs[j]) + bf16_round(-x2[j] * sn[j]);
+      o2[j] = bf16_round(x2[j] * cs[j]) + bf16_round(x1[j] * sn[j]);
+    }
+    uint4 w1, w2;
+    w1.x = pack_bf16x2(o1[0], o1[1]), w1.y = pack_bf16x2(o1[2], o1[3]);
+    w1.z = pack_bf16x2(o1[4], o1[5]), w1.w = pack_bf16x2(o1[6], o1[7]);
+    w2.x = pack_bf16x2(o2[0], o2[1]), w2.y = pack_bf16x2(o2[2], o2[3]);
+    w2.z = pack_bf16x2(o2[4], o2[5]), w2.w = pack_bf16x2(o2[6], o2[7]);
+    *reinterpret_cast<uint4*>(x1p) = w1;
+    *reinterpret_cast<uint4*>(x2p) = w2;
+  }
+}
+
+// ---------------------------------------------------------------- HD feature transform gather
+// grid (max_nv, B), 256 threads: output row r of sample b = 4 x 1024 bf16 (2x2 merged tokens) or a separator.
+__global__ void __launch_bounds__(256)
+hd_gather_kernel(const bf16* __restrict__ clip, const int* __restrict__ plan, const bf16* __restrict__ sub_gn,
+                 const bf16* __restrict__ glb_gn, bf16* __restrict__ rows) {
+  constexpr int D = 1024, T = 577;
+  const int b = blockIdx.y, r = blockIdx.x;
+  const int* pl = plan + b * LR_PLAN_STRIDE;
+  const int hc = pl[LR_PLAN_HCROP], wc = pl[LR_PLAN_WCROP], crop_base = pl[LR_PLAN_CROP_BASE];
+  const int row_base = pl[LR_PLAN_ROW_BASE], nv = pl[LR_PLAN_NV];
+  if (r >= nv) return;
+  const int sub_w = wc * 12 + 1, n_sub = hc * 12 * sub_w;
+  int crop = -1, py = 0, px = 0;
+  const bf16* special = nullptr;
+  if (r < n_sub) {
+    const int y = r / sub_w, x = r % sub_w;
+    if (x == wc * 12) special = sub_gn;
+    else crop = 1 + (y / 12) * wc + x / 12, py = y % 12, px = x % 12;
+  } else if (r == n_sub) {
+    special = glb_gn;
+  } else {
+    const int r2 = r - n_sub - 1, y = r2 / 13, x = r2 % 13;
+    if (x == 12) special = sub_gn;
+    else crop = 0, py = y, px = x;
+  }
+  bf16* out = rows + size_t(row_base + r) * (4 * D);
+  for (int i = threadIdx.x; i < 4 * D / 8; i += blockDim.x) {
+    const int qd = i / (D / 8), c = (i % (D / 8)) * 8;  // quadrant (dy,dx) = (qd>>1, qd&1)
+    const bf16* src;
+    if (special) src = special + qd * D + c;
+    else src = clip + (size_t(crop_base + crop) * T + 1 + (2 * py + (qd >> 1)) * 24 + 2 * px + (qd & 1)) * D + c;
+    stg128(out + qd * D + c, ldg128(src));
+  }
+}
+
+// ---------------------------------------------------------------- embedding gather + image-row scatter
+__global__ void __launch_bounds__(128)
+embed_scatter_kernel(const int64_t* __restrict__ ids, const int* __restrict__ img_ord, const int* __restrict__ plan,
+                     const bf16* __restrict__ wte, const bf16* __restrict__ img_proj, bf16* __restrict__ hidden,
+                     int ldh, int S, int H, int V) {
+  const size_t tok = blockIdx.x;
+  const int b = int(tok / S);
+  const int ord = img_ord[tok];
+  const bf16* src;
+  if (ord >= 0) {
+    src = img_proj + size_t(plan[b * LR_PLAN_STRIDE + LR_PLAN_ROW_BASE] + ord) * H;
+  } else {
+    int64_t id = ids[tok];
+    id = id < 0 ? 0 : (id > V - 1 ? V - 1 : id);
+    src = wte + size_t(id) * H;
+  }
+  bf16* dst = hidden + tok * ldh;
+  for (int c = threadIdx.x * 8; c < H; c += blockDim.x * 8) stg128(dst + c, ldg128(src + c));
+}
+
+}  // namespace lr
+
+using namespace lr;
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int lr_token_plan(const int64_t* input_ids, const int64_t* attention_mask, int B, int S,
+                             int* position_ids, int* img_ord, int* seq_start, int* seq_len, int* eos_row, int* n_img,
+                             int* flags, void* stream) {
+  LR_CHECK_ARG(input_ids && attention_mask && position_ids && img_ord && seq_start && seq_len && eos_row && n_img &&
+               flags && B > 0 && S > 0);
+  token_plan_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      input_ids, attention_mask, S, position_ids, img_ord, seq_start, seq_len, eos_row, n_img, flags);
+  return lr_launch_status();
+}
+
+extern "C" int lr_rope_su_bf16(void* qkv, int ld, const int* position_ids, const void* cos_tab, const void* sin_tab,
+                               int rows, int n_heads, int head_dim, void* stream) {
+  LR_CHECK_ARG(qkv && position_ids && cos_tab && sin_tab && rows > 0 && n_heads > 0 && head_dim > 0 &&
+               head_dim % 16 == 0);
+  if ((ld % 8) || !aligned16(qkv) || !aligned16(cos_tab) || !aligned16(sin_tab)) return LR_ERR_ALIGN;
+  rope_su_kernel<<<rows, 192, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<bf16*>(qkv), ld, position_ids, reinterpret_cast<const bf16*>(cos_tab),
+      reinterpret_cast<const bf16*>(sin_tab), n_heads, head_dim);
+  return lr_launch_status();
+}
+
+extern "C" int lr_hd_gather_bf16(const void* clip_tokens, const int* plan, const void* sub_gn, const void* glb_gn,
+                                 void* rows, int B, int max_nv, void* stream) {
+  LR_CHECK_ARG(clip_tokens && plan && sub_gn && glb_gn && rows && B > 0 && max_nv > 0);
+  if (!aligned16(clip_tokens) || !aligned16(sub_gn) || !aligned16(glb_gn) || !aligned16(rows)) return LR_ERR_ALIGN;
+  hd_gather_kernel<<<dim3(max_nv, B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(clip_tokens), plan, reinterpret_cast<const bf16*>(sub_gn),
+      reinterpret_cast<const bf16*>(glb_gn), reinterpret_cast<bf16*>(rows));
+  return lr_launch_status();
+}
+
+extern "C" int lr_embed_scatter_bf16(const int64_t* input_ids, const int* img_ord, const int* plan, const void* wte,
+                                     const void* img_proj, void* hidden, int ldh, int B, int S, int H, int V,
+                                     void* stream) {
+  LR_CHECK_ARG(input_ids && img_ord && plan && wte && img_proj && hidden && B > 0 && S > 0 && H > 0 && H % 8 == 0 &&
+               V > 0);
+  if ((ldh % 8) || !aligned16(wte) || !aligned16(img_proj) || !aligned16(hidden)) return LR_ERR_ALIGN;
+  embed_scatter_kernel<<<B * S, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      input_ids, img_ord, plan, reinterpret_cast<const bf16*>(wte), reinterpret_cast<const bf16*>(img_proj),
+      reinterpret_cast<bf16*>(hidden), ldh, S, H, V);
+  return lr_launch_status();
+}

@@ -1,0 +1,191 @@
+// Reward head: SkipCA on the last-valid-token row, residual + RMSNorm, value head, preference probability.
+// The reference computes W_q/W_k/W_v, the S x N_v score matrix and the value head for all S rows and then
+// gathers one row per sample (rw_model_general_preference.py:376-386, 407-448); only that row is computed here.
+#include "common.cuh"
+
+namespace lr {
+
+// scores[b, j] = bf16( bf16(q_b . K_bj) / sqrt(H) ) for j < N_v(b), 0 for N_v(b) <= j < max_nv
+// (rows the reference zero-pads: K row = 0 -> score 0). grid (ceil(max_nv/8), B), one warp per K row.
+__global__ void __launch_bounds__(256)
+skipca_scores_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ kv, int ldkv,
+                     const int* __restrict__ plan, float* __restrict__ scores, int H, int max_nv, float inv_sqrt_d) {
+  extern __shared__ __align__(16) uint8_t sc_smem[];
+  bf16* sq = reinterpret_cast<bf16*>(sc_smem);
+  const int b = blockIdx.y;
+  const int row_base = plan[b * LR_PLAN_STRIDE + LR_PLAN_ROW_BASE], nv = plan[b * LR_PLAN_STRIDE + LR_PLAN_NV];
+  for (int c = threadIdx.x * 8; c < H; c += blockDim.x * 8) stg128(sq + c, ldg128(q + size_t(b) * ldq + c));
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + warp;
+  if (j >= max_nv) return;
+  float acc = 0.f;
+  if (j < nv) {
+    const bf16* kr = kv + size_t(row_base + j) * ldkv;
+    for (int c = lane * 8; c < H; c += 256) {
+      const uint4 a = *reinterpret_cast<const uint4*>(sq + c), k4 = ldg128(kr + c);
+      float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+      float2 k0 = unpack_bf16x2(k4.x), k1 = unpack_bf16x2(k4.y), k2 = unpack_bf16x2(k4.z), k3 = unpack_bf16x2(k4.w);
+      acc += a0.x * k0.x + a0.y * k0.y + a1.x * k1.x + a1.y * k1.y + a2.x * k2.x + a2.y * k2.y + a3.x * k3.x +
+             a3.y * k3.y;
+    }
+    acc = warp_sum(acc);
+  }
+  if (lane == 0) scores[size_t(b) * max_nv + j] = (j < nv) ? bf16_round(bf16_round(acc) * inv_sqrt_d) : 0.f;
+}
+
+// One CTA (768 threads) per sample: softmax over max_nv scores, out = P V, y = x + out, RMSNorm, value head.
+constexpr int kHeadThreads = 768;
+constexpr int kHeadMaxNv = 4096;
+
+__global__ void __launch_bounds__(kHeadThreads)
+skipca_head_kernel(const float* __restrict__ scores, const bf16* __restrict__ kv, int ldkv,
+                   const int* __restrict__ plan, const bf16* __restrict__ x, int ldx, const bf16* __restrict__ ln_w,
+                   const bf16* __restrict__ vh_w, bf16* __restrict__ reward, int H, int max_nv, int vhd, float eps) {
+  __shared__ float red[32];
+  __shared__ float prob[kHeadMaxNv];
+  extern __shared__ __align__(16) uint8_t hd_smem[];
+  float* part = reinterpret_cast<float*>(hd_smem);  // [2][H] partial PV sums, later the normalised row
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int cpr = H >> 3;              // 16-byte chunks per row (384 for H=3072)
+  const int grp = tid / cpr;           // 0 or 1 (threads >= 2*cpr idle in the PV loop)
+  const int ch = tid % cpr;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (scores) {
+    const int row_base = plan[b * LR_PLAN_STRIDE + LR_PLAN_ROW_BASE], nv = plan[b * LR_PLAN_STRIDE + LR_PLAN_NV];
+    const float* sc = scores + size_t(b) * max_nv;
+    float mx = -INFINITY;
+    for (int j = tid; j < max_nv; j += kHeadThreads) mx = fmaxf(mx, sc[j]);
+    mx = block_max(mx, red);
+    float sum = 0.f;
+    for (int j = tid; j < max_nv; j += kHeadThreads) {
+      const float e = __expf(sc[j] - mx);
+      prob[j] = e;
+      sum += e;
+    }
+    sum = block_sum(sum, red);
+    const float inv = 1.f / sum;
+    for (int j = tid; j < max_nv; j += kHeadThreads) prob[j] = bf16_round(prob[j] * inv);  // softmax output is bf16
+    __syncthreads();
+    if (grp < 2) {
+      const bf16* vbase = kv + size_t(row_base) * ldkv + H + ch * 8;  // V = second half of the [K|V] row
+      int j = grp;
+      for (; j + 6 < nv; j += 8) {  // 4 rows in flight per thread
+        uint4 u[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) u[t] = ldg128(vbase + size_t(j + 2 * t) * ldkv);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float p = prob[j + 2 * t];
+          float2 f0 = unpack_bf16x2(u[t].x), f1 = unpack_bf16x2(u[t].y), f2 = unpack_bf16x2(u[t].z),
+                 f3 = unpack_bf16x2(u[t].w);
+          acc[0] += p * f0.x, acc[1] += p * f0.y, acc[2] += p * f1.x, acc[3] += p * f1.y;
+          acc[4] += p * f2.x, acc[5] += p * f2.y, acc[6] += p * f3.x, acc[7] += p * f3.y;
+        }
+      }
+      for (; j < nv; j += 2) {
+        const uint4 u = ldg128(vbase + size_t(j) * ldkv);
+        const float p = prob[j];
+        float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+        acc[0] += p * f0.x, acc[1] += p * f0.y, acc[2] += p * f1.x, acc[3] += p * f1.y;
+        acc[4] += p * f2.x, acc[5] += p * f2.y, acc[6] += p * f3.x, acc[7] += p * f3.y;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) part[grp * H + ch * 8 + e] = acc[e];
+    }
+    __syncthreads();
+  }
+  // y = bf16(x + bf16(attn_out)); RMSNorm; value head. Threads of group 0 own 8 columns each.
+  float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float ss = 0.f;
+  if (grp == 0) {
+    const uint4 u = ldg128(x + size_t(b) * ldx + ch * 8);
+    float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+    y[0] = f0.x, y[1] = f0.y, y[2] = f1.x, y[3] = f1.y, y[4] = f2.x, y[5] = f2.y, y[6] = f3.x, y[7] = f3.y;
+    if (scores) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float o = bf16_round(part[ch * 8 + e] + part[H + ch * 8 + e]);
+        y[e] = bf16_round(y[e] + o);
+        ss += y[e] * y[e];
+      }
+    }
+  }
+  if (scores) {
+    ss = block_sum(ss, red);
+    const float rstd = rsqrtf(ss / float(H) + eps);
+    if (grp == 0) {
+      const uint4 u = ldg128(ln_w + ch * 8);
+      float2 g0 = unpack_bf16x2(u.x), g1 = unpack_bf16x2(u.y), g2 = unpack_bf16x2(u.z), g3 = unpack_bf16x2(u.w);
+      const float g[8] = {g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, g3.x, g3.y};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = bf16_round(g[e] * bf16_round(y[e] * rstd));
+    }
+  }
+  for (int d = 0; d < vhd; ++d) {
+    float dot = 0.f;
+    if (grp == 0) {
+      const uint4 u = ldg128(vh_w + size_t(d) * H + ch * 8);
+      float2 w0 = unpack_bf16x2(u.x), w1 = unpack_bf16x2(u.y), w2 = unpack_bf16x2(u.z), w3 = unpack_bf16x2(u.w);
+      dot = y[0] * w0.x + y[1] * w0.y + y[2] * w1.x + y[3] * w1.y + y[4] * w2.x + y[5] * w2.y + y[6] * w3.x +
+            y[7] * w3.y;
+    }
+    dot = block_sum(dot, red);
+    if (tid == 0) reward[size_t(b) * vhd + d] = __float2bfloat16_rn(dot);
+  }
+}
+
+// bf16 arithmetic, one rounding per torch op of preference_compute
+__global__ void preference_kernel(const bf16* __restrict__ c, const bf16* __restrict__ r, float* __restrict__ prob,
+                                  int n, int vhd, int is_gpm, float tau) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float z;
+  if (is_gpm && vhd == 2) {
+    const float c0 = __bfloat162float(c[2 * i]), c1 = __bfloat162float(c[2 * i + 1]);
+    const float r0 = __bfloat162float(r[2 * i]), r1 = __bfloat162float(r[2 * i + 1]);
+    z = bf16_round(bf16_round(c0 * r1) - bf16_round(c1 * r0));
+  } else {
+    z = bf16_round(__bfloat162float(c[size_t(i) * vhd]) - __bfloat162float(r[size_t(i) * vhd]));
+  }
+  z = bf16_round(z / tau);
+  prob[i] = bf16_round(1.f / (1.f + expf(-z)));
+}
+
+}  // namespace lr
+
+using namespace lr;
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int lr_skipca_scores(const void* q, int ldq, const void* kv, int ldkv, const int* plan, float* scores,
+                                int B, int H, int max_nv, void* stream) {
+  LR_CHECK_ARG(q && kv && plan && scores && B > 0 && H > 0 && H % 256 == 0 && max_nv > 0);
+  if ((ldq % 8) || (ldkv % 8) || !aligned16(q) || !aligned16(kv)) return LR_ERR_ALIGN;
+  skipca_scores_kernel<<<dim3((max_nv + 7) / 8, B), 256, H * 2, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(q), ldq, reinterpret_cast<const bf16*>(kv), ldkv, plan, scores, H, max_nv,
+      1.0f / sqrtf(float(H)));
+  return lr_launch_status();
+}
+
+extern "C" int lr_skipca_head(const float* scores, const void* kv, int ldkv, const int* plan, const void* x, int ldx,
+                              const void* ca_ln_w, const void* value_head_w, void* reward, int B, int H, int max_nv,
+                              int vhd, float eps, void* stream) {
+  LR_CHECK_ARG(x && value_head_w && reward && B > 0 && H > 0 && H % 8 == 0 && (H / 8) * 2 <= kHeadThreads &&
+               vhd > 0);
+  if (scores) LR_CHECK_ARG(kv && plan && ca_ln_w && max_nv > 0 && max_nv <= kHeadMaxNv);
+  if ((ldx % 8) || !aligned16(x) || !aligned16(value_head_w) || (scores && ((ldkv % 8) || !aligned16(kv))))
+    return LR_ERR_ALIGN;
+  skipca_head_kernel<<<B, kHeadThreads, 2 * H * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+      scores, reinterpret_cast<const bf16*>(kv), ldkv, plan, reinterpret_cast<const bf16*>(x), ldx,
+      reinterpret_cast<const bf16*>(ca_ln_w), reinterpret_cast<const bf16*>(value_head_w),
+      reinterpret_cast<bf16*>(reward), H, max_nv, vhd, eps);
+  return lr_launch_status();
+}
+
+extern "C" int lr_preference(const void* chosen, const void* reject, float* prob, int n, int vhd, int is_gpm,
+                             float tau, void* stream) {
+  LR_CHECK_ARG(chosen && reject && prob && n > 0 && vhd > 0 && tau != 0.f);
+  preference_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(chosen), reinterpret_cast<const bf16*>(reject), prob, n, vhd, is_gpm, tau);
+  return lr_launch_status();
+}

@@ -1,0 +1,225 @@
+"""RewardEngine: the scoring forward (reference `CustomRewardModel.custom_forward`, phi3v branch,
+llava_reward/models/rw_model_general_preference.py:334-448) as a fixed sequence of C-ABI kernel launches.
+
+Host side is plumbing only: buffer allocation (torch.empty), one tiny D2H read of per-sample counts at
+the top of the call (the reference performs ~70 hidden syncs per forward), pointer passing.
+Every FLOP and every byte moved on the device is done by libllavareward.so.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import ops
+from .config import RewardConfig, num_image_tokens
+from .weights import PackedWeights
+
+
+class RewardEngine:
+    def __init__(self, cfg: RewardConfig, weights: PackedWeights, device="cuda", gemm_impl: int = L.GEMM_TCGEN05):
+        L.load()
+        self.cfg, self.w, self.device, self.gemm_impl = cfg, weights, torch.device(device), gemm_impl
+        self._bufs: Dict[Tuple[str, Tuple[int, ...], torch.dtype], torch.Tensor] = {}
+        self._rope: Dict[Tuple[int, bool], Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.launches = 0        # kernels launched by the last forward (for bench `gpu_launches`)
+        self.taps: Optional[dict] = None  # set to {} to capture intermediates (tests)
+
+    # ------------------------------------------------------------------ helpers
+    def buf(self, name: str, shape, dtype=torch.bfloat16) -> torch.Tensor:
+        key = (name, tuple(shape), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            # drop older shapes of the same logical buffer
+            for k in [k for k in self._bufs if k[0] == name]:
+                del self._bufs[k]
+            t = torch.empty(*shape, dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t
+
+    def rope_tables(self, n_pos: int, long: bool):
+        """cos/sin [n_pos, head_dim/2] bf16, computed like Phi3SuScaledRotaryEmbedding.forward
+        (modeling_phi3_v.py:446-476): fp32 angles, * scaling factor, cast to bf16."""
+        key = (n_pos, long)
+        if key not in self._rope:
+            cfg = self.cfg
+            fac = cfg.long_factor if long else cfg.short_factor
+            ext = torch.tensor(fac, dtype=torch.float32, device=self.device)
+            expo = torch.arange(0, cfg.head_dim, 2, dtype=torch.int64, device=self.device).float() / cfg.head_dim
+            inv_freq = 1.0 / (ext * cfg.rope_theta ** expo)
+            ang = torch.arange(n_pos, dtype=torch.int64, device=self.device).float()[:, None] * inv_freq[None, :]
+            s = cfg.rope_scaling_factor
+            self._rope = {key: ((ang.cos() * s).to(torch.bfloat16).contiguous(),
+                                (ang.sin() * s).to(torch.bfloat16).contiguous())}
+        return self._rope[key]
+
+    def _gemm(self, A, W, C, M, N, K, epi=L.EPI_NONE, bias=None, R=None):
+        ops.gemm(A, W, C, M, N, K, epi, bias, R, impl=self.gemm_impl)
+        self.launches += 1
+
+    def _tap(self, name, t):
+        if self.taps is not None:
+            self.taps[name] = t.clone()
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, pixel_values: torch.Tensor,
+                image_sizes) -> torch.Tensor:
+        cfg, w, dev = self.cfg, self.w, self.device
+        bf = torch.bfloat16
+        self.launches = 0
+        B, S = input_ids.shape
+        H, I, r = cfg.hidden_size, cfg.intermediate_size, (cfg.lora_rank if cfg.use_lora else 0)
+        ids = input_ids.to(dev, torch.int64).contiguous()
+        mask = attention_mask.to(dev, torch.int64).contiguous()
+        pix = pixel_values.to(dev, torch.float32).contiguous()
+        if pix.dim() != 5 or tuple(pix.shape[2:]) != (3, cfg.image_size, cfg.image_size):
+            raise AssertionError("pixel_values must be [B, crops, 3, 336, 336]")  # modeling_phi3_v.py:236
+        n_slots = pix.shape[1]
+
+        # 1. token plan on device, then ONE small D2H read
+        M = B * S
+        pos = self.buf("pos", (M,), torch.int32)
+        img_ord = self.buf("img_ord", (M,), torch.int32)
+        meta = self.buf("meta", (4 * B + 1,), torch.int32)  # seq_start | seq_len | eos_row | n_img | flags
+        seq_start, seq_len, eos_row, n_img, flags = meta[:B], meta[B:2 * B], meta[2 * B:3 * B], meta[3 * B:4 * B], meta[4 * B:]
+        flags.zero_()
+        ops.token_plan(ids, mask, B, S, pos, img_ord, seq_start, seq_len, eos_row, n_img, flags)
+        self.launches += 1
+        meta_h = meta.cpu().numpy()
+        sizes_h = image_sizes.cpu().numpy() if torch.is_tensor(image_sizes) else np.asarray(image_sizes)
+        sizes_h = sizes_h.reshape(B, 2).astype(np.int64)
+        if meta_h[4 * B] & 1:
+            raise ValueError("attention_mask rows must be one contiguous run of ones (left/right padding)")
+        plan_h = np.zeros((B, L.PLAN_STRIDE), dtype=np.int32)
+        crop_src, crop_base, row_base = [], 0, 0
+        for b in range(B):
+            hc, wc = int(sizes_h[b, 0]) // 336, int(sizes_h[b, 1]) // 336
+            ncrop = hc * wc + 1
+            nv = num_image_tokens(int(sizes_h[b, 0]), int(sizes_h[b, 1]))
+            if ncrop > n_slots:
+                raise ValueError(f"image_sizes[{b}] needs {ncrop} crops but pixel_values has {n_slots} slots")
+            if int(meta_h[3 * B + b]) != nv:
+                # the reference fails in index_put with a shape mismatch (modeling_phi3_v.py:247-249)
+                raise ValueError(f"sample {b}: {int(meta_h[3 * B + b])} image placeholder tokens but image_sizes "
+                                 f"implies {nv}")
+            plan_h[b, :5] = (hc, wc, crop_base, row_base, nv)
+            crop_src.extend(range(b * n_slots, b * n_slots + ncrop))
+            crop_base += ncrop
+            row_base += nv
+        n_crops, sum_nv = crop_base, row_base
+        max_nv = int(plan_h[:, L.PLAN_NV].max())
+        max_len = int(meta_h[B:2 * B].max())
+        host = torch.from_numpy(np.concatenate([plan_h.reshape(-1), np.asarray(crop_src, dtype=np.int32)]))
+        dev_plan = self.buf("plan", (host.numel(),), torch.int32)
+        dev_plan.copy_(host.pin_memory() if dev.type == "cuda" else host, non_blocking=True)
+        plan = dev_plan[: B * L.PLAN_STRIDE]
+        crop_idx = dev_plan[B * L.PLAN_STRIDE:]
+
+        # 2. CLIP tower on the real crops only
+        D, DI, T = cfg.clip_hidden, cfg.clip_intermediate, cfg.clip_tokens
+        Mv = n_crops * T
+        a0 = self.buf("clip_a0", (n_crops * (T - 1), 640))
+        ops.clip_im2col(pix, crop_idx, a0, n_crops)
+        patch = self.buf("clip_patch", (n_crops * (T - 1), D))
+        self._gemm(a0, w.clip["patch_w"], patch, n_crops * (T - 1), D, 640)
+        x = self.buf("clip_x", (Mv, D))
+        ops.clip_embed_ln(patch, w.clip["cls"], w.clip["pos"], w.clip["pre_w"], w.clip["pre_b"], x, n_crops, cfg.clip_eps)
+        self.launches += 2
+        self._tap("clip_embed", x)
+        hn = self.buf("clip_hn", (Mv, D))
+        qkv = self.buf("clip_qkv", (Mv, 3 * D))
+        ao = self.buf("clip_ao", (Mv, D))
+        ff = self.buf("clip_ff", (Mv, DI))
+        scale = cfg.clip_head_dim ** -0.5
+        for li, lw in enumerate(w.clip_layers):
+            ops.layernorm(x, lw["ln1_w"], lw["ln1_b"], hn, Mv, D, cfg.clip_eps)
+            self._gemm(hn, lw["qkv_w"], qkv, Mv, 3 * D, D, L.EPI_BIAS, lw["qkv_b"])
+            ops.attention(qkv, qkv[:, D:], qkv[:, 2 * D:], ao, 3 * D, D, n_crops, T, None, None, cfg.clip_heads,
+                          cfg.clip_head_dim, False, scale)
+            self._gemm(ao, lw["out_w"], x, Mv, D, D, L.EPI_BIAS_RESIDUAL, lw["out_b"], x)
+            ops.layernorm(x, lw["ln2_w"], lw["ln2_b"], hn, Mv, D, cfg.clip_eps)
+            self._gemm(hn, lw["fc1_w"], ff, Mv, DI, D, L.EPI_BIAS_QUICKGELU, lw["fc1_b"])
+            self._gemm(ff, lw["fc2_w"], x, Mv, D, DI, L.EPI_BIAS_RESIDUAL, lw["fc2_b"], x)
+            self.launches += 3
+            if li == 0:
+                self._tap("clip_layer0", x)
+        self._tap("clip_out", x)
+
+        # 3. HD transform gather + projector
+        rows = self.buf("hd_rows", (sum_nv, 4 * D))
+        ops.hd_gather(x, plan, w.proj["sub_gn"], w.proj["glb_gn"], rows, B, max_nv)
+        p1 = self.buf("proj1", (sum_nv, H))
+        self._gemm(rows, w.proj["p0_w"], p1, sum_nv, H, 4 * D, L.EPI_BIAS_GELU, w.proj["p0_b"])
+        img = self.buf("img_proj", (sum_nv, H))
+        self._gemm(p1, w.proj["p2_w"], img, sum_nv, H, H, L.EPI_BIAS, w.proj["p2_b"])
+        self._tap("img_proj", img)
+
+        # 4. embeddings
+        hid = self.buf("hidden", (M, H))
+        ops.embed_scatter(ids, img_ord, plan, w.embed, img, hid, B, S, H, cfg.vocab_size)
+        self.launches += 2
+        self._tap("inputs_embeds", hid)
+
+        # 5. decoder
+        xn = self.buf("dec_xn", (M, H + r))
+        dqkv = self.buf("dec_qkv", (M, 3 * H))
+        dao = self.buf("dec_ao", (M, H + r))
+        gg = self.buf("dec_g", (M, I + r))
+        cos_tab, sin_tab = self.rope_tables(max(S, 2), max_len > cfg.original_max_position_embeddings)
+        att_scale = 1.0 / math.sqrt(cfg.head_dim)
+        nh, hd = cfg.num_heads, cfg.head_dim
+        for li, lw in enumerate(w.layers):
+            ops.rmsnorm(hid, lw["in_ln"], xn, M, H, cfg.rms_eps)
+            if r:
+                self._gemm(xn, lw["qkv_a"], xn[:, H:], M, r, H)
+            self._gemm(xn, lw["qkv_w"], dqkv, M, 3 * H, H + r)
+            ops.rope_su(dqkv, pos, cos_tab, sin_tab, M, nh, hd)
+            ops.attention(dqkv, dqkv[:, H:], dqkv[:, 2 * H:], dao, 3 * H, H + r, B, S, seq_start, seq_len, nh, hd,
+                          True, att_scale)
+            if r:
+                self._gemm(dao, lw["o_a"], dao[:, H:], M, r, H)
+            self._gemm(dao, lw["o_w"], hid, M, H, H + r, L.EPI_RESIDUAL, None, hid)
+            ops.rmsnorm(hid, lw["post_ln"], xn, M, H, cfg.rms_eps)
+            if r:
+                self._gemm(xn, lw["gu_a"], xn[:, H:], M, r, H)
+            self._gemm(xn, lw["gu_w"], gg, M, 2 * I, H + r, L.EPI_SWIGLU)
+            if r:
+                self._gemm(gg, lw["dn_a"], gg[:, I:], M, r, I)
+            self._gemm(gg, lw["dn_w"], hid, M, H, I + r, L.EPI_RESIDUAL, None, hid)
+            self.launches += 4
+            if self.taps is not None:
+                self._tap(f"hidden_{li}", hid)
+
+        # 6. reward head on the last valid token of each sample
+        xe = self.buf("x_eos", (max(B, 1), H))
+        ops.rmsnorm(hid, w.head["norm"], xe, B, H, cfg.rms_eps, row_index=eos_row)
+        self._tap("last_hidden_eos", xe)
+        vhd = cfg.vhd
+        reward = torch.empty(B, vhd, dtype=bf, device=dev)
+        if cfg.add_cross_attention:
+            q = self.buf("ca_q", (B, H))
+            self._gemm(xe, w.head["wq"], q, B, H, H)
+            kv = self.buf("ca_kv", (sum_nv, 2 * H))
+            self._gemm(img, w.head["wkv"], kv, sum_nv, 2 * H, H)
+            scores = self.buf("ca_scores", (B, max_nv), torch.float32)
+            ops.skipca_scores(q, kv, plan, scores, B, H, max_nv)
+            ops.skipca_head(scores, kv, plan, xe, w.head["ca_ln"], w.head["vh"], reward, B, H, max_nv, vhd, cfg.rms_eps)
+            self.launches += 3
+        else:
+            ops.skipca_head(None, None, None, xe, None, w.head["vh"], reward, B, H, 0, vhd, cfg.rms_eps)
+            self.launches += 2
+        return reward
+
+    @torch.no_grad()
+    def preference(self, chosen: torch.Tensor, reject: torch.Tensor) -> torch.Tensor:
+        """fp32 device tensor of P(chosen > reject) (preference_compute without the .cpu().numpy())."""
+        cfg = self.cfg
+        n = chosen.shape[0]
+        prob = torch.empty(n, dtype=torch.float32, device=self.device)
+        ops.preference(chosen.to(torch.bfloat16).contiguous(), reject.to(torch.bfloat16).contiguous(), prob, n,
+                       chosen.shape[1], cfg.is_general_preference, cfg.general_preference_tau)
+        return prob

@@ -1,0 +1,92 @@
+"""Model object with the reference's scoring surface (`custom_forward`, `.to()`, `.eval()`).
+
+Mirrors `CustomRewardModel` (reference llava_reward/models/rw_model_general_preference.py:303-448) for
+model_type 'phi3v'. It is NOT an nn.Module wrapper around torch layers: `.to('cuda')` packs the
+parameters into kernel layouts and `custom_forward` runs `RewardEngine.forward`.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+
+from . import _lib as L
+from .config import RewardConfig
+from .engine import RewardEngine
+from .weights import pack_weights
+
+
+class B200RewardModel:
+    model_type = "phi3v"
+
+    def __init__(self, cfg: RewardConfig, provider: Callable[[str], torch.Tensor]):
+        self.config = cfg
+        self._provider = provider
+        self.engine: Optional[RewardEngine] = None
+        self.training = False
+        # attributes the reference's custom_forward honours (rw_model_general_preference.py:327-333)
+        self.mean_hidden_state = None
+        self.layer_id = 32
+        self.vision_layer_id = -1
+        self.value_head_dim = cfg.vhd
+        self.add_cross_attention = cfg.add_cross_attention
+        self.is_general_preference = cfg.is_general_preference
+        self.device = torch.device("cpu")
+        self.dtype = torch.bfloat16
+
+    # --- nn.Module-like plumbing used by the reference's callers (eval/simple_inference.py:17-18)
+    def to(self, device=None, *args, **kwargs):
+        device = torch.device(device if device is not None else "cuda")
+        if device.type != "cuda":
+            raise RuntimeError("llava-reward-b200 runs on sm_100a CUDA devices only; there is no CPU fallback")
+        L.load()
+        L.check(L.load().lr_device_check(), "lr_device_check")
+        with torch.cuda.device(device):
+            weights = pack_weights(self.config, self._provider, device=device)
+            self.engine = RewardEngine(self.config, weights, device=device)
+        self.device = device
+        return self
+
+    def cuda(self, device=None):
+        return self.to("cuda" if device is None else device)
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError("the B200 path implements the scoring forward only (no backward)")
+        return self.eval()
+
+    def parameters(self):
+        return iter(())
+
+    # --- the hot path
+    def custom_forward(self, input_ids: torch.LongTensor = None, attention_mask: Optional[torch.Tensor] = None,
+                       pixel_values: Optional[torch.FloatTensor] = None, image_sizes: Optional[torch.LongTensor] = None,
+                       return_output=False, inputs_batch=None):
+        """-> (reward [B, vhd] (GPM) or [B, 1] (BT), bf16 on device, None).
+        Same signature/positional order as the reference (rw_model_general_preference.py:334-342)."""
+        if self.engine is None:
+            raise RuntimeError("call .to('cuda') before custom_forward (weights are packed on the device)")
+        if inputs_batch is not None:
+            raise NotImplementedError("inputs_batch is the qwen/llava calling convention; this build covers phi3v")
+        if return_output:
+            raise NotImplementedError("return_output=True (HF BaseModelOutputWithPast) is not produced by the fused path")
+        if self.mean_hidden_state:
+            raise NotImplementedError("mean_hidden_state pooling is off in all shipped reference configs")
+        if self.layer_id != self.config.num_layers and self.layer_id != 32:
+            raise NotImplementedError("layer_id other than the last layer")
+        if input_ids is None or attention_mask is None:
+            raise ValueError("input_ids and attention_mask are required")
+        if pixel_values is None or image_sizes is None:
+            # the reference path is image-only by construction (UnboundLocalError at modeling_phi3_v.py:252)
+            raise ValueError("pixel_values and image_sizes are required (the scoring path is image-only)")
+        if self.training:
+            raise NotImplementedError("training-mode gather (values[:, -1]) is not part of the scoring path")
+        with torch.cuda.device(self.device):
+            reward = self.engine.forward(input_ids, attention_mask, pixel_values, image_sizes)
+        return reward, None
+
+    __call__ = custom_forward

@@ -1,0 +1,98 @@
+"""Tensor-level wrappers over the C ABI (pointer extraction + shape checks only; no math happens here)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("llava-reward-b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+def gemm(A: torch.Tensor, W: torch.Tensor, C: torch.Tensor, M: int, N: int, K: int, epilogue: int = L.EPI_NONE,
+         bias: Optional[torch.Tensor] = None, R: Optional[torch.Tensor] = None, impl: int = L.GEMM_TCGEN05,
+         lda: Optional[int] = None, ldw: Optional[int] = None, ldc: Optional[int] = None, ldr: Optional[int] = None):
+    """C[M,N'] = epi(A[M,K] W[N,K]^T). A/W/C/R may be column-sliced views: leading dims default to stride(0)."""
+    _need_cuda(A, W, C, bias, R)
+    L.call("lr_gemm_bf16", _ptr(A), lda or A.stride(0), _ptr(W), ldw or W.stride(0), _ptr(C), ldc or C.stride(0),
+           M, N, K, epilogue, _ptr(bias), _ptr(R), (ldr or (R.stride(0) if R is not None else 0)), impl, _stream())
+
+
+def rmsnorm(x, w, y, rows, cols, eps, row_index=None):
+    _need_cuda(x, w, y, row_index)
+    L.call("lr_rmsnorm_bf16", _ptr(x), x.stride(0), _ptr(row_index), _ptr(w), _ptr(y), y.stride(0), rows, cols, eps,
+           _stream())
+
+
+def layernorm(x, w, b, y, rows, cols, eps):
+    _need_cuda(x, w, b, y)
+    L.call("lr_layernorm_bf16", _ptr(x), x.stride(0), _ptr(w), _ptr(b), _ptr(y), y.stride(0), rows, cols, eps, _stream())
+
+
+def clip_im2col(pixels, crop_src, A, n_crops):
+    _need_cuda(pixels, crop_src, A)
+    L.call("lr_clip_im2col", _ptr(pixels), _ptr(crop_src), _ptr(A), n_crops, _stream())
+
+
+def clip_embed_ln(patch, cls, pos, w, b, tokens, n_crops, eps):
+    _need_cuda(patch, cls, pos, w, b, tokens)
+    L.call("lr_clip_embed_ln", _ptr(patch), _ptr(cls), _ptr(pos), _ptr(w), _ptr(b), _ptr(tokens), n_crops, eps, _stream())
+
+
+def attention(q, k, v, o, ld_qkv, ld_o, n_seq, rows_per_seq, seq_start, seq_len, n_heads, head_dim, causal, scale):
+    _need_cuda(q, k, v, o, seq_start, seq_len)
+    L.call("lr_attention_bf16", _ptr(q), _ptr(k), _ptr(v), _ptr(o), ld_qkv, ld_o, n_seq, rows_per_seq, _ptr(seq_start),
+           _ptr(seq_len), n_heads, head_dim, int(causal), scale, _stream())
+
+
+def rope_su(qkv, position_ids, cos_tab, sin_tab, rows, n_heads, head_dim):
+    _need_cuda(qkv, position_ids, cos_tab, sin_tab)
+    L.call("lr_rope_su_bf16", _ptr(qkv), qkv.stride(0), _ptr(position_ids), _ptr(cos_tab), _ptr(sin_tab), rows, n_heads,
+           head_dim, _stream())
+
+
+def token_plan(ids, mask, B, S, pos, img_ord, seq_start, seq_len, eos_row, n_img, flags):
+    _need_cuda(ids, mask, pos, img_ord, seq_start, seq_len, eos_row, n_img, flags)
+    L.call("lr_token_plan", _ptr(ids), _ptr(mask), B, S, _ptr(pos), _ptr(img_ord), _ptr(seq_start), _ptr(seq_len),
+           _ptr(eos_row), _ptr(n_img), _ptr(flags), _stream())
+
+
+def hd_gather(clip_tokens, plan, sub_gn, glb_gn, rows, B, max_nv):
+    _need_cuda(clip_tokens, plan, sub_gn, glb_gn, rows)
+    L.call("lr_hd_gather_bf16", _ptr(clip_tokens), _ptr(plan), _ptr(sub_gn), _ptr(glb_gn), _ptr(rows), B, max_nv, _stream())
+
+
+def embed_scatter(ids, img_ord, plan, wte, img_proj, hidden, B, S, H, V):
+    _need_cuda(ids, img_ord, plan, wte, img_proj, hidden)
+    L.call("lr_embed_scatter_bf16", _ptr(ids), _ptr(img_ord), _ptr(plan), _ptr(wte), _ptr(img_proj), _ptr(hidden),
+           hidden.stride(0), B, S, H, V, _stream())
+
+
+def skipca_scores(q, kv, plan, scores, B, H, max_nv):
+    _need_cuda(q, kv, plan, scores)
+    L.call("lr_skipca_scores", _ptr(q), q.stride(0), _ptr(kv), kv.stride(0), _ptr(plan), _ptr(scores), B, H, max_nv,
+           _stream())
+
+
+def skipca_head(scores, kv, plan, x, ca_ln_w, vh_w, reward, B, H, max_nv, vhd, eps):
+    _need_cuda(scores, kv, plan, x, ca_ln_w, vh_w, reward)
+    L.call("lr_skipca_head", _ptr(scores), _ptr(kv), (kv.stride(0) if kv is not None else 0), _ptr(plan), _ptr(x),
+           x.stride(0), _ptr(ca_ln_w), _ptr(vh_w), _ptr(reward), B, H, max_nv, vhd, eps, _stream())
+
+
+def preference(chosen, reject, prob, n, vhd, is_gpm, tau):
+    _need_cuda(chosen, reject, prob)
+    L.call("lr_preference", _ptr(chosen), _ptr(reject), _ptr(prob), n, vhd, int(is_gpm), float(tau), _stream())

@@ -1,0 +1,88 @@
+"""Drop-in for the reference's scoring API (reference eval/reward_adaptor_loader.py:24-181):
+`load_reward_adaptor`, `inference_process_phi3v`, `preference_compute` with the same signatures,
+argument meaning and error behaviour, backed by the B200 engine.
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable
+
+import numpy as np
+import torch
+import yaml
+
+from .checkpoint import checkpoint_provider
+from .config import RewardConfig
+from .model import B200RewardModel
+from .synth import SynthProvider
+
+
+def load_reward_adaptor(args, model_type, reward_config_path, load_tokenizer=False):
+    """Same contract as reference eval/reward_adaptor_loader.py:24-156: reads the 4 yaml keys into `args`
+    (mutating it), builds the reward model for `args.pretrain` + `args.pm_path`, returns (args, model) or
+    (args, model, processor, tokenizer). The model is returned un-placed; the caller does `.to('cuda').eval()`.
+
+    `args.pretrain` is either a local directory holding the Phi-3.5-vision HF checkpoint
+    (config.json + *.safetensors) or ``synthetic[:seed]`` for random-init weights of the named architecture
+    (the only option without network access)."""
+    with open(reward_config_path) as f:
+        reward_cfg = yaml.safe_load(f)
+    args.is_general_preference = reward_cfg['is_general_preference']
+    args.add_cross_attention = reward_cfg['add_cross_attention']
+    args.value_head_dim = reward_cfg['value_head_dim']
+    args.general_preference_tau = reward_cfg['general_preference_tau']
+    if model_type != 'phi3v':
+        raise NotImplementedError(f"model_type={model_type!r}: this build covers the phi3v backbone "
+                                  "(qwen / llava are the next rows of SURVEY.md 8f)")
+    overrides = dict(getattr(args, "config_overrides", None) or {})
+    pretrain = str(args.pretrain)
+    synthetic = pretrain.startswith("synthetic")
+    cfg = RewardConfig(is_general_preference=bool(args.is_general_preference),
+                       add_cross_attention=bool(args.add_cross_attention),
+                       value_head_dim=int(args.value_head_dim),
+                       general_preference_tau=float(args.general_preference_tau), **overrides)
+    if synthetic:
+        seed = int(pretrain.split(":", 1)[1]) if ":" in pretrain else 1234
+        provider: Callable[[str], torch.Tensor] = SynthProvider(cfg, seed=seed)
+    else:
+        cfg, provider = checkpoint_provider(cfg, pretrain, getattr(args, "pm_path", None),
+                                            ft_projector=bool(getattr(args, "ft_projector", False)))
+    model = B200RewardModel(cfg, provider)
+    if load_tokenizer:
+        from .processing import load_processor
+        processor, tokenizer = load_processor(pretrain, cfg, cache_dir=getattr(args, "cache_dir", None),
+                                              use_fast=not getattr(args, "disable_fast_tokenizer", False))
+        tokenizer.truncation_side = "right"
+        return args, model, processor, tokenizer
+    return args, model
+
+
+def inference_process_phi3v(args, processor, tokenizer, img_dir_list, caption, device='cuda'):
+    """Same contract as reference eval/reward_adaptor_loader.py:158-173: one BatchFeature-like dict per image
+    with input_ids / attention_mask / pixel_values / image_sizes on `device`."""
+    from PIL import Image
+    img_list = [Image.open(d).convert("RGB") for d in img_dir_list]
+    prompt_messages = {'role': 'user', 'content': f'<|image_1|>\n{caption}'}
+    prompt = tokenizer.apply_chat_template([prompt_messages], tokenize=False, add_generation_prompt=True)[:-22] \
+        + tokenizer.eos_token
+    img_inputs = []
+    for img in img_list:
+        img_input = processor(text=prompt, images=[img], return_tensors="pt", padding=True, truncation=True)
+        for k in img_input:
+            img_input[k] = img_input[k].to(device)
+        img_inputs.append(img_input)
+    return img_inputs
+
+
+def preference_compute(args, chosen_rewards, reject_rewards):
+    """Same contract as reference eval/reward_adaptor_loader.py:174-181 -> np.float32 [B] (synchronises)."""
+    from . import ops
+    if not (torch.is_tensor(chosen_rewards) and chosen_rewards.is_cuda):
+        raise RuntimeError("preference_compute expects the CUDA reward tensors returned by custom_forward")
+    n, vhd = chosen_rewards.shape
+    prob = torch.empty(n, dtype=torch.float32, device=chosen_rewards.device)
+    with torch.cuda.device(chosen_rewards.device):
+        ops.preference(chosen_rewards.to(torch.bfloat16).contiguous(), reject_rewards.to(torch.bfloat16).contiguous(),
+                       prob, n, vhd, bool(args.is_general_preference) and int(args.value_head_dim) == 2,
+                       float(args.general_preference_tau))
+    return prob.cpu().numpy()

@@ -1,0 +1,110 @@
+"""Pack reference-named parameters into the device layouts the kernels consume.
+
+Input: a provider ``name -> tensor`` using the reference's state_dict names
+(``Phi3VForCausalLM`` + reward heads + PEFT ``lora_A/lora_B``; see synth.param_specs) - a real
+checkpoint loaded by `load_reward_adaptor` yields the same names.
+Output: bf16 CUDA tensors
+  * CLIP q/k/v fused into one [3072,1024] weight (the reference issues 3 GEMMs, modeling_phi3_v.py:101-103)
+  * patch-embedding conv weight flattened to [1024, 640] (588 + zero pad so K is a multiple of 64)
+  * LoRA folded by K-extension: W_ext = [W | (alpha/r) B]  ([out, in + r]); lora_A kept as its own [r, in] GEMM
+  * gate_up_proj rows interleaved in blocks of 128 ([gate_b | up_b]) so silu(gate)*up is a GEMM epilogue
+  * W_k and W_v stacked into one [2H, H] weight
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List
+
+import torch
+
+from .config import RewardConfig
+from .synth import CLIP_PREFIX
+
+VE = "model.vision_embed_tokens."
+
+
+class PackedWeights:
+    def __init__(self):
+        self.clip: Dict[str, torch.Tensor] = {}
+        self.clip_layers: List[Dict[str, torch.Tensor]] = []
+        self.proj: Dict[str, torch.Tensor] = {}
+        self.layers: List[Dict[str, torch.Tensor]] = []
+        self.head: Dict[str, torch.Tensor] = {}
+        self.embed: torch.Tensor = None
+
+    def nbytes(self) -> int:
+        tot = 0
+        for d in [self.clip, self.proj, self.head, *self.clip_layers, *self.layers]:
+            tot += sum(t.numel() * t.element_size() for t in d.values())
+        return tot + self.embed.numel() * self.embed.element_size()
+
+
+def pack_weights(cfg: RewardConfig, get: Callable[[str], torch.Tensor], device="cuda") -> PackedWeights:
+    bf = torch.bfloat16
+
+    def g(name):
+        return get(name).to(device=device, dtype=bf).contiguous()
+
+    pw = PackedWeights()
+    c = CLIP_PREFIX
+    D = cfg.clip_hidden
+    pe = g(c + "embeddings.patch_embedding.weight").reshape(D, -1)  # [1024, 588], (ch, ky, kx) order
+    patch_w = torch.zeros(D, 640, dtype=bf, device=device)
+    patch_w[:, : pe.shape[1]] = pe
+    pw.clip = {
+        "patch_w": patch_w,
+        "cls": g(c + "embeddings.class_embedding"),
+        "pos": g(c + "embeddings.position_embedding.weight"),
+        "pre_w": g(c + "pre_layrnorm.weight"),
+        "pre_b": g(c + "pre_layrnorm.bias"),
+    }
+    for i in range(cfg.clip_layers):
+        p = f"{c}encoder.layers.{i}."
+        a = p + "self_attn."
+        pw.clip_layers.append({
+            "ln1_w": g(p + "layer_norm1.weight"), "ln1_b": g(p + "layer_norm1.bias"),
+            "qkv_w": torch.cat([g(a + "q_proj.weight"), g(a + "k_proj.weight"), g(a + "v_proj.weight")], 0).contiguous(),
+            "qkv_b": torch.cat([g(a + "q_proj.bias"), g(a + "k_proj.bias"), g(a + "v_proj.bias")], 0).contiguous(),
+            "out_w": g(a + "out_proj.weight"), "out_b": g(a + "out_proj.bias"),
+            "ln2_w": g(p + "layer_norm2.weight"), "ln2_b": g(p + "layer_norm2.bias"),
+            "fc1_w": g(p + "mlp.fc1.weight"), "fc1_b": g(p + "mlp.fc1.bias"),
+            "fc2_w": g(p + "mlp.fc2.weight"), "fc2_b": g(p + "mlp.fc2.bias"),
+        })
+    pw.proj = {
+        "p0_w": g(VE + "img_projection.0.weight"), "p0_b": g(VE + "img_projection.0.bias"),
+        "p2_w": g(VE + "img_projection.2.weight"), "p2_b": g(VE + "img_projection.2.bias"),
+        "sub_gn": g(VE + "sub_GN").reshape(-1), "glb_gn": g(VE + "glb_GN").reshape(-1),
+    }
+    pw.embed = g("model.embed_tokens.weight")
+    H, I, r = cfg.hidden_size, cfg.intermediate_size, cfg.lora_rank
+    assert I % 128 == 0
+    nb = I // 128
+    perm = torch.arange(2 * I, device=device).view(2, nb, 128).permute(1, 0, 2).reshape(-1)  # [gate_b | up_b] blocks
+
+    def ext(name):
+        W = g(name + ".weight")
+        if not cfg.use_lora:
+            return W, None
+        A = g(name + ".lora_A.weight")
+        B = (get(name + ".lora_B.weight").to(device=device, dtype=torch.float32) * cfg.lora_scale).to(bf)
+        return torch.cat([W, B], dim=1).contiguous(), A
+
+    for i in range(cfg.num_layers):
+        p = f"model.layers.{i}."
+        qkv_w, qkv_a = ext(p + "self_attn.qkv_proj")
+        o_w, o_a = ext(p + "self_attn.o_proj")
+        gu_w, gu_a = ext(p + "mlp.gate_up_proj")
+        gu_w = gu_w[perm].contiguous()
+        dn_w, dn_a = ext(p + "mlp.down_proj")
+        d = {"in_ln": g(p + "input_layernorm.weight"), "post_ln": g(p + "post_attention_layernorm.weight"),
+             "qkv_w": qkv_w, "o_w": o_w, "gu_w": gu_w, "dn_w": dn_w}
+        if cfg.use_lora:
+            d.update({"qkv_a": qkv_a, "o_a": o_a, "gu_a": gu_a, "dn_a": dn_a})
+        pw.layers.append(d)
+    pw.head = {"norm": g("model.norm.weight"), "vh": g("value_head.weight")}
+    if cfg.add_cross_attention:
+        pw.head.update({
+            "wq": g("W_q.weight"),
+            "wkv": torch.cat([g("W_k.weight"), g("W_v.weight")], 0).contiguous(),
+            "ca_ln": g("ca_layernorm.weight"),
+        })
+    return pw

@@ -1,0 +1,177 @@
+"""End-to-end parity of the CUDA engine (through the reference-shaped API) against
+ (a) the reference's own fp32 outputs stored in tests/golden/*.pt (made by tests/golden/make_golden.py),
+ (b) the oracle restatement run in bf16 on the same GPU (= the reference's GPU arithmetic, eager attention).
+Tolerance (north_star): per-sample rewards within 2e-2 absolute in bf16; identical preference decisions."""
+import os
+import types
+
+import pytest
+import torch
+import yaml
+
+pytestmark = pytest.mark.gpu
+
+from golden_util import GOLDEN_DIR, fixture_batch, fixture_cfg, load_fixture  # noqa: E402
+from llava_reward_b200 import _lib as L  # noqa: E402
+from llava_reward_b200.reward_adaptor_loader import load_reward_adaptor, preference_compute  # noqa: E402
+from llava_reward_b200.synth import SynthProvider  # noqa: E402
+from oracle import reward_oracle as O  # noqa: E402
+
+REWARD_TOL = 2e-2
+_models = {}
+
+
+def build_model(fx, tmp_path_factory):
+    key = fx["case"]
+    if key not in _models:
+        cfg = fixture_cfg(fx)
+        d = tmp_path_factory.mktemp(key)
+        ypath = os.path.join(d, "reward_config.yaml")
+        with open(ypath, "w") as f:
+            yaml.safe_dump({"is_general_preference": cfg.is_general_preference,
+                            "add_cross_attention": cfg.add_cross_attention,
+                            "value_head_dim": cfg.value_head_dim,
+                            "general_preference_tau": cfg.general_preference_tau}, f)
+        args = types.SimpleNamespace(pretrain=f"synthetic:{fx['seed_w']}", pm_path=None, cache_dir=None,
+                                     ft_projector=False, disable_fast_tokenizer=False,
+                                     config_overrides={k: v for k, v in fx["cfg_overrides"].items()
+                                                       if k in ("num_layers", "clip_layers", "use_lora")})
+        args, model = load_reward_adaptor(args, "phi3v", ypath)
+        _models[key] = (args, model.to("cuda").eval(), cfg)
+    return _models[key]
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize("case", ["slim_gpm", "slim_bt"])
+def test_slim_vs_reference_golden(case, tmp_path_factory):
+    fx = load_fixture(case)
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    rewards = {}
+    for entry in fx["batches"]:
+        ids, mask, pix, sizes = fixture_batch(fx, entry, cfg, device="cuda")
+        r, _ = model.custom_forward(ids, mask, pix, sizes)
+        assert r.dtype == torch.bfloat16 and r.is_cuda and tuple(r.shape) == tuple(entry["reward"].shape)
+        err = (r.float().cpu() - entry["reward"]).abs().max().item()
+        assert err < REWARD_TOL, f"{case}/{entry['tag']}: reward err {err:.4g} vs reference fp32"
+        rewards[entry["tag"]] = r
+    prob = preference_compute(args, rewards["c"], rewards["r"])
+    assert prob.dtype.name == "float32" and prob.shape == (fx["prob"].shape[0],)
+    ref = fx["prob"].numpy()
+    decided = abs(ref - 0.5) > 0.05  # pairs whose reference margin is above bf16 noise
+    assert ((prob > 0.5) == (ref > 0.5))[decided].all()
+
+
+@pytest.mark.parametrize("case", ["slim_gpm", "slim_bt"])
+def test_slim_stages_vs_oracle_bf16(case, tmp_path_factory):
+    """Stage-by-stage against the oracle in bf16 on the GPU (relative L2 error per stage)."""
+    fx = load_fixture(case)
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    entry = fx["batches"][0]
+    ids, mask, pix, sizes = fixture_batch(fx, entry, cfg, device="cuda")
+    P = O.Params(SynthProvider(cfg, seed=fx["seed_w"], device="cuda"), dtype=torch.bfloat16, device="cuda")
+    taps_o = {}
+    with torch.no_grad():
+        r_o = O.custom_forward(P, cfg, ids, mask, pix, sizes, taps_o)
+    model.engine.taps = {}
+    r_e, _ = model.custom_forward(ids, mask, pix, sizes)
+    taps_e, model.engine.taps = model.engine.taps, None
+    B, S = ids.shape
+    valid = mask.bool()
+    # CLIP: the engine runs only the real crops, compacted; the oracle runs all 17 slots like the reference
+    n_slots = pix.shape[1]
+    real = []
+    for b in range(B):
+        nc = (int(sizes[b, 0]) // 336) * (int(sizes[b, 1]) // 336) + 1
+        real += [b * n_slots + i for i in range(nc)]
+    real = torch.tensor(real, device="cuda")
+    T = cfg.clip_tokens
+    errs = {
+        "clip_embed": rel_err(taps_e["clip_embed"].view(-1, T, 1024), taps_o["clip_embed"][real]),
+        "clip_layer0": rel_err(taps_e["clip_layer0"].view(-1, T, 1024), taps_o["clip_layer0"][real]),
+        "clip_out": rel_err(taps_e["clip_out"].view(-1, T, 1024)[:, 1:], taps_o["clip_features"].flatten(0, 1)[real]),
+        "img_proj": rel_err(taps_e["img_proj"], taps_o["img_proj"]),
+        "inputs_embeds": rel_err(taps_e["inputs_embeds"].view(B, S, -1)[valid], taps_o["inputs_embeds"][valid]),
+    }
+    for i in range(cfg.num_layers):
+        errs[f"hidden_{i}"] = rel_err(taps_e[f"hidden_{i}"].view(B, S, -1)[valid], taps_o[f"hidden_{i}"][valid])
+    errs["last_hidden_eos"] = rel_err(taps_e["last_hidden_eos"], taps_o["last_hidden"][:, -1])
+    print({k: round(v, 5) for k, v in errs.items()})
+    for k, v in errs.items():
+        assert v < 3e-2, (k, v)
+    assert (r_e.float() - r_o.float()).abs().max().item() < REWARD_TOL
+
+
+def test_batch_composition_quirk(tmp_path_factory):
+    """SkipCA softmax includes the zero-padded vision rows of the longest image in the batch
+    (SURVEY.md 3.1): scoring sample 0 alone or next to a larger image follows the oracle in both cases."""
+    fx = load_fixture("slim_gpm")
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    entry = fx["batches"][0]
+    ids, mask, pix, sizes = fixture_batch(fx, entry, cfg, device="cuda")
+    r_batched, _ = model.custom_forward(ids, mask, pix, sizes)
+    first = int(mask[0].nonzero()[0])
+    r_alone, _ = model.custom_forward(ids[:1, first:], mask[:1, first:], pix[:1], sizes[:1])
+    P = O.Params(SynthProvider(cfg, seed=fx["seed_w"], device="cuda"), dtype=torch.float32, device="cuda")
+    with torch.no_grad():
+        o_b = O.custom_forward(P, cfg, ids, mask, pix, sizes)
+        o_a = O.custom_forward(P, cfg, ids[:1, first:], mask[:1, first:], pix[:1], sizes[:1])
+    assert (r_batched[0].float() - o_b[0]).abs().max().item() < REWARD_TOL
+    assert (r_alone[0].float() - o_a[0]).abs().max().item() < REWARD_TOL
+
+
+def test_tcgen05_and_simt_engines_agree(tmp_path_factory):
+    fx = load_fixture("slim_gpm")
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    ids, mask, pix, sizes = fixture_batch(fx, fx["batches"][0], cfg, device="cuda")
+    r1, _ = model.custom_forward(ids, mask, pix, sizes)
+    model.engine.gemm_impl = L.GEMM_SIMT
+    try:
+        r2, _ = model.custom_forward(ids, mask, pix, sizes)
+    finally:
+        model.engine.gemm_impl = L.GEMM_TCGEN05
+    assert (r1.float() - r2.float()).abs().max().item() < 1e-2
+
+
+def test_input_validation(tmp_path_factory):
+    fx = load_fixture("slim_gpm")
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    ids, mask, pix, sizes = fixture_batch(fx, fx["batches"][0], cfg, device="cuda")
+    with pytest.raises(ValueError):
+        model.custom_forward(ids, mask, None, None)
+    bad = sizes.clone()
+    bad[0, 0] = 672
+    with pytest.raises(ValueError):
+        model.custom_forward(ids, mask, pix, bad)
+    with pytest.raises(AssertionError):
+        model.custom_forward(ids, mask, pix[:, :, :, :100], sizes)
+
+
+@pytest.mark.parametrize("case", ["full_bt", "full_gpm"])
+def test_full_depth_vs_reference_golden(case, tmp_path_factory):
+    """BASELINE.json configs[0] / configs[1] shapes at full depth (24-layer CLIP, 32-layer decoder):
+    bf16 engine vs the reference's fp32 CPU rewards."""
+    if not os.path.exists(os.path.join(GOLDEN_DIR, f"{case}.pt")):
+        pytest.skip("fixture not generated")
+    for k in list(_models):
+        del _models[k]
+    torch.cuda.empty_cache()
+    fx = load_fixture(case)
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    rewards = {}
+    for entry in fx["batches"]:
+        ids, mask, pix, sizes = fixture_batch(fx, entry, cfg, device="cuda")
+        r, _ = model.custom_forward(ids, mask, pix, sizes)
+        err = (r.float().cpu() - entry["reward"]).abs().max().item()
+        print(f"{case}/{entry['tag']}: engine {r.float().flatten().tolist()} ref {entry['reward'].flatten().tolist()}")
+        assert err < 5e-2, f"{case}/{entry['tag']}: reward err {err:.4g} vs reference fp32 (32 layers of bf16)"
+        rewards[entry["tag"]] = r
+    prob = preference_compute(args, rewards["c"], rewards["r"])
+    ref = fx["prob"].numpy()
+    decided = abs(ref - 0.5) > 0.1
+    assert ((prob > 0.5) == (ref > 0.5))[decided].all()
+    _models.pop(case, None)
+    torch.cuda.empty_cache()
