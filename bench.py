@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Benchmark of the reward-scoring hot path (BASELINE.json metric: text-image pairs scored / s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = score one batch of 32 synthetic pairs of BASELINE.json configs[1]
+(Phi-3.5-vision + SkipCA + LoRA r128 + GPM, image (1008,1344) -> 13 crops, N_v=1921, S=2048, bf16):
+2 x custom_forward(32 samples) + preference_compute. Weak scaling: every rank scores its own 32 pairs per step,
+results are all-gathered (NCCL) inside the timed region.
+
+  value : pairs/s with the step's inputs already resident in HBM (CUDA events, max over ranks)
+  e2e   : pairs/s through the reference-shaped API with HOST (pinned) inputs: H2D of ids/mask/pixels and the
+          D2H of the probabilities are inside the timed region
+  roofline     : dominant kernel = the tcgen05 gate_up GEMM of the decoder, timed live with CUDA events
+  cpu_baseline : the oracle port (fp32, eager attention, all host cores) on a bounded sample, rank 0 only
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PAIRS_PER_STEP = 32
+IMAGE_HW = (1008, 1344)
+SEQ_LEN = 2048
+TFLOP_PER_PAIR = 42.99       # 21.495 TFLOP/sample at this shape (algorithmic, unmerged LoRA)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"bf16_sustained": d.get("bf16_tflops_sustained", 1391.8), "bf16_burst": d.get("bf16_tflops", 1653.1),
+                "hbm_gbs": d.get("hbm_gbs", 6553.6), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), default=None)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores, bounded sample
+# --------------------------------------------------------------------------------------------------
+def cpu_sample_seconds(threads: int):
+    """Seconds per sample of the full-depth config-1-shaped workload on `threads` host cores, from three
+    reduced-depth runs of the oracle ((clip,dec) layers = (1,1),(2,1),(1,2)) extrapolated linearly to (23,32)."""
+    import torch
+    from llava_reward_b200.config import RewardConfig
+    from llava_reward_b200.synth import SynthProvider, synth_batch
+    from oracle import reward_oracle as O
+
+    torch.set_num_threads(threads)
+    times = {}
+    for depth in ((1, 1), (2, 1), (1, 2)):
+        cfg = RewardConfig(clip_layers=depth[0], num_layers=depth[1])
+        P = O.Params(SynthProvider(cfg, seed=1234), dtype=torch.float32)
+        ids, mask, pix, sizes = synth_batch(cfg, 1, IMAGE_HW, SEQ_LEN, seed=7, tag="c")
+        for n in SynthProvider(cfg).names():
+            P(n)  # materialise weights outside the timed region
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            O.custom_forward(P, cfg, ids, mask, pix[:, :13], sizes)  # 13 real crops (padded slots skipped)
+            times[depth] = time.perf_counter() - t0
+        del P
+    d_clip = max(times[(2, 1)] - times[(1, 1)], 0.0)
+    d_dec = max(times[(1, 2)] - times[(1, 1)], 0.0)
+    fixed = max(times[(1, 1)] - d_clip - d_dec, 0.0)
+    return fixed + 23 * d_clip + 32 * d_dec, times
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per_sample = []
+    for _ in range(max(1, min(a.warmup, 1))):
+        cpu_sample_seconds(threads)
+    for _ in range(max(1, min(a.steps, 3))):
+        s, _ = cpu_sample_seconds(threads)
+        per_sample.append(s)
+    sec = sum(per_sample) / len(per_sample)
+    value = 1.0 / (2.0 * sec)
+    sample = ("1 sample (13 crops, N_v=1921, S=2048, fp32, eager attention) through the oracle port at "
+              "(CLIP,decoder) depths (1,1),(2,1),(1,2), extrapolated linearly to (23,32) layers; "
+              f"{len(per_sample)} repetition(s)")
+    line = {"impl": "reference", "metric": "text-image pairs scored/sec", "value": value, "unit": "pairs/s",
+            "n_gpus": a.gpus, "steps": len(per_sample), "warmup": 1, "ms_per_step": sec * 2 * PAIRS_PER_STEP * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a.gpus),
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": "BASELINE.json configs[1]: Phi-3.5-vision + SkipCA + LoRA r128 + GPM(vhd=2,tau=0.1) pair scoring, "
+                        "32 pairs/step/GPU, image (1008,1344)->13 crops, N_v=1921, S=2048, random-init weights",
+            "pairs_per_step_per_gpu": PAIRS_PER_STEP, "seq_len": SEQ_LEN, "image_hw": list(IMAGE_HW),
+            "parallelism": f"dp{n_gpus} (pairs sharded round-robin, full bf16 replica per GPU)",
+            "l2_policy": "inputs larger than L2 (1.47 GB of pixels + >1 GB activations per step)"}
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", type=int, default=None, help="debug only: reduce decoder/CLIP depth (INVALID as a bench)")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import yaml
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from llava_reward_b200 import _lib as L
+    from llava_reward_b200.reward_adaptor_loader import load_reward_adaptor
+    from llava_reward_b200.synth import synth_batch
+
+    ypath = f"/tmp/llava_reward_b200_bench_{rank}.yaml"
+    with open(ypath, "w") as f:
+        yaml.safe_dump({"is_general_preference": True, "add_cross_attention": True, "value_head_dim": 2,
+                        "general_preference_tau": 0.1}, f)
+    over = {} if a.layers is None else {"num_layers": a.layers, "clip_layers": min(a.layers, 23)}
+    args = types.SimpleNamespace(pretrain="synthetic:1234", pm_path=None, cache_dir=None, ft_projector=False,
+                                 config_overrides=over)
+    args, model = load_reward_adaptor(args, "phi3v", ypath)
+    model = model.to(dev).eval()
+    eng = model.engine
+    cfg = model.config
+
+    # synthetic pairs of this rank, built once in pinned host memory
+    host = {}
+    for tag in ("c", "r"):
+        ids, mask, pix, sizes = synth_batch(cfg, PAIRS_PER_STEP, IMAGE_HW, SEQ_LEN, seed=7 + rank, tag=tag, device=dev)
+        host[tag] = tuple(t.cpu().pin_memory() for t in (ids, mask, pix, sizes))
+    resident = {tag: tuple(t.to(dev) for t in host[tag][:3]) + (host[tag][3],) for tag in host}
+    h2d = sum(t.numel() * t.element_size() for tag in host for t in host[tag][:3])
+    d2h = PAIRS_PER_STEP * 4 * world
+
+    gather_buf = torch.empty(world * PAIRS_PER_STEP, dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step(from_host: bool):
+        rs = {}
+        for tag in ("c", "r"):
+            if from_host:
+                ids, mask, pix = (t.to(dev, non_blocking=True) for t in host[tag][:3])
+                sizes = host[tag][3]
+            else:
+                ids, mask, pix, sizes = resident[tag]
+            rs[tag], _ = model.custom_forward(ids, mask, pix, sizes)
+        prob = eng.preference(rs["c"], rs["r"])
+        if world > 1:
+            dist.all_gather_into_tensor(gather_buf, prob)
+            prob = gather_buf
+        if from_host:
+            return prob.cpu()
+        return prob
+
+    def timed(from_host: bool, steps: int):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(from_host)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return ms.item()
+
+    for _ in range(max(a.warmup, 3)):
+        step(False)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    L.reset_launch_count()
+    eng.profile = {"gate_up": []}
+    ms_dev = timed(False, a.steps)
+    launches = L.launch_count()
+    prof = eng.profile
+    eng.profile = None
+    clocks = sampler.stop() if sampler else None
+    step(True)  # warm the pinned path
+    ms_e2e = timed(True, a.steps)
+
+    if rank == 0:
+        peaks = load_peaks()
+        pairs = PAIRS_PER_STEP * world * a.steps
+        value = pairs / (ms_dev / 1e3)
+        e2e_value = pairs / (ms_e2e / 1e3)
+        # dominant kernel: decoder gate_up GEMM (tcgen05, SWIGLU epilogue), 32 launches per forward
+        M = PAIRS_PER_STEP * SEQ_LEN
+        K = cfg.hidden_size + (cfg.lora_rank if cfg.use_lora else 0)
+        flops = 2.0 * M * (2 * cfg.intermediate_size) * K
+        durs = [s.elapsed_time(e) for s, e in prof["gate_up"]]
+        ach = flops / (sum(durs) / len(durs) * 1e-3) / 1e12 if durs else None
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_gate_up_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        line = {
+            "metric": "text-image pairs scored/sec", "value": value, "unit": "pairs/s", "n_gpus": world,
+            "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_dev / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(world), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<256,SWIGLU> (decoder gate_up_proj + LoRA-B)",
+                         "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": (ach / peaks["bf16_sustained"]) if ach else None, "traffic": traffic,
+                         "launches_timed": len(durs), "flops_per_launch": flops, "peak_source": peaks["source"]},
+            "step_roofline": {"tflop_per_pair": TFLOP_PER_PAIR,
+                              "achieved_tflops_per_gpu": value / world * TFLOP_PER_PAIR,
+                              "frac_of_sustained": value / world * TFLOP_PER_PAIR / peaks["bf16_sustained"],
+                              "frac_of_burst": value / world * TFLOP_PER_PAIR / peaks["bf16_burst"]},
+        }
+        if a.layers is not None:
+            line["INVALID"] = "reduced depth debug run"
+        if world == 1 and not a.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sec, times = cpu_sample_seconds(threads)
+            line["cpu_baseline"] = {
+                "value": 1.0 / (2.0 * sec), "unit": "pairs/s", "cores": threads, "kind": "port",
+                "sample": "1 sample (13 crops, N_v=1921, S=2048, fp32, eager attention) through the oracle port at "
+                          "(CLIP,decoder) depths (1,1),(2,1),(1,2), extrapolated linearly to (23,32) layers",
+                "seconds_per_sample_extrapolated": sec,
+                "raw_seconds": {f"{k[0]},{k[1]}": v for k, v in times.items()}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -70,5 +70,20 @@ def check(status: int, what: str):
         raise RuntimeError(f"{what}: CUDA error {status}")
 
 
+_launches = 0
+
+
+def reset_launch_count():
+    global _launches
+    _launches = 0
+
+
+def launch_count() -> int:
+    """Kernels launched through this binding since the last reset (every compute entry = one launch)."""
+    return _launches
+
+
 def call(name: str, *args):
+    global _launches
     check(getattr(load(), name)(*args), name)
+    _launches += 1

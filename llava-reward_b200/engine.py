@@ -27,6 +27,7 @@ class RewardEngine:
         self._rope: Dict[Tuple[int, bool], Tuple[torch.Tensor, torch.Tensor]] = {}
         self.launches = 0        # kernels launched by the last forward (for bench `gpu_launches`)
         self.taps: Optional[dict] = None  # set to {} to capture intermediates (tests)
+        self.profile: Optional[dict] = None  # {"gate_up": []} -> CUDA-event pairs around that GEMM (bench roofline)
 
     # ------------------------------------------------------------------ helpers
     def buf(self, name: str, shape, dtype=torch.bfloat16) -> torch.Tensor:
@@ -186,7 +187,13 @@ class RewardEngine:
             ops.rmsnorm(hid, lw["post_ln"], xn, M, H, cfg.rms_eps)
             if r:
                 self._gemm(xn, lw["gu_a"], xn[:, H:], M, r, H)
+            if self.profile is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             self._gemm(xn, lw["gu_w"], gg, M, 2 * I, H + r, L.EPI_SWIGLU)
+            if self.profile is not None:
+                ev[1].record()
+                self.profile["gate_up"].append(ev)
             if r:
                 self._gemm(gg, lw["dn_a"], gg[:, I:], M, r, I)
             self._gemm(gg, lw["dn_w"], hid, M, H, I + r, L.EPI_RESIDUAL, None, hid)
