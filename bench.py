@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 PAIRS_PER_STEP = 32
 IMAGE_HW = (1008, 1344)
 SEQ_LEN = 2048
+TEXT_LEN_RANGE = (35, 123)   # + 5 special tokens + 1921 image tokens -> valid length in [1961, 2048]
 TFLOP_PER_PAIR = 42.99       # 21.495 TFLOP/sample at this shape (algorithmic, unmerged LoRA)
 
 
@@ -93,7 +94,7 @@ def cpu_sample_seconds(threads: int):
     for depth in ((1, 1), (2, 1), (1, 2)):
         cfg = RewardConfig(clip_layers=depth[0], num_layers=depth[1])
         P = O.Params(SynthProvider(cfg, seed=1234), dtype=torch.float32)
-        ids, mask, pix, sizes = synth_batch(cfg, 1, IMAGE_HW, SEQ_LEN, seed=7, tag="c")
+        ids, mask, pix, sizes = synth_batch(cfg, 1, IMAGE_HW, SEQ_LEN, seed=7, tag="c", text_len_range=TEXT_LEN_RANGE)
         for n in SynthProvider(cfg).names():
             P(n)  # materialise weights outside the timed region
         with torch.no_grad():
@@ -150,6 +151,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-run", action="store_true", help="for ncu: 1 warm-up step, 1 device-timed step, nothing else")
     ap.add_argument("--layers", type=int, default=None, help="debug only: reduce decoder/CLIP depth (INVALID as a bench)")
     a = ap.parse_args()
     if a.impl == "reference":
@@ -187,7 +189,8 @@ def main():
     # synthetic pairs of this rank, built once in pinned host memory
     host = {}
     for tag in ("c", "r"):
-        ids, mask, pix, sizes = synth_batch(cfg, PAIRS_PER_STEP, IMAGE_HW, SEQ_LEN, seed=7 + rank, tag=tag, device=dev)
+        ids, mask, pix, sizes = synth_batch(cfg, PAIRS_PER_STEP, IMAGE_HW, SEQ_LEN, seed=7 + rank, tag=tag, device=dev,
+                                            text_len_range=TEXT_LEN_RANGE)
         host[tag] = tuple(t.cpu().pin_memory() for t in (ids, mask, pix, sizes))
     resident = {tag: tuple(t.to(dev) for t in host[tag][:3]) + (host[tag][3],) for tag in host}
     h2d = sum(t.numel() * t.element_size() for tag in host for t in host[tag][:3])
@@ -228,6 +231,11 @@ def main():
             dist.barrier()
         return ms.item()
 
+    if a.profile_run:
+        step(False)
+        torch.cuda.synchronize()
+        print("PROFILE-RUN ms", timed(False, 1), "launches/step", None, flush=True)
+        return
     for _ in range(max(a.warmup, 3)):
         step(False)
     sampler = ClockSampler(local) if rank == 0 else None

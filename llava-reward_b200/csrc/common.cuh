@@ -71,11 +71,17 @@ __device__ __forceinline__ void stg128(void* p, uint4 v) { *reinterpret_cast<uin
 // ---- GEMM epilogue math shared by the tcgen05 and SIMT kernels -------------------------------
 // All variants first round the fp32 accumulator (+bias) to bf16, because the reference
 // materialises the nn.Linear output in bf16 before the activation / residual add.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid(z) = 0.5 + 0.5 tanh(z/2): one MUFU op instead of ex2 + rcp (the epilogues are MUFU/issue bound)
 __device__ __forceinline__ float epi_quick_gelu(float x) {  // x * sigmoid(1.702 x)
-  return x / (1.f + __expf(-1.702f * x));
+  return x * fmaf(0.5f, tanh_approx(0.851f * x), 0.5f);
 }
 __device__ __forceinline__ float epi_gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float epi_silu(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float epi_silu(float x) { return x * fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
 
 template <int EPI>
 __device__ __forceinline__ float epi_apply(float acc, float bias, float res) {

@@ -2,12 +2,14 @@
 //
 //   A [M,K] row-major (K-major), W [N,K] row-major (K-major, the nn.Linear layout), fp32 accumulate in TMEM.
 //
-// One persistent CTA per SM, 256 threads, warp-specialised:
-//   warp 0  : TMA producer   (cp.async.bulk.tensor 2D, 128B swizzle, kStages-deep smem ring)
-//   warp 1  : MMA issuer     (one lane issues tcgen05.mma 128 x BN x 16, commits to mbarriers)
-//   warp 2  : TMEM allocator (2 accumulator buffers of BN fp32 columns -> MMA of tile i+1 overlaps
-//                             the epilogue of tile i)
-//   warps 4-7: epilogue      (tcgen05.ld 32 lanes x 32 columns -> bias/activation/residual -> bf16 -> global)
+// One persistent CTA per SM, 384 threads, warp-specialised:
+//   warp 0   : TMA producer   (cp.async.bulk.tensor 2D, 128B swizzle, kStages-deep smem ring)
+//   warp 1   : MMA issuer     (one lane issues tcgen05.mma 128 x BN x 16, commits to mbarriers)
+//   warp 2   : TMEM allocator (2 accumulator buffers of BN fp32 columns -> the MMAs of tile i+1 overlap
+//                              the epilogue of tile i)
+//   warps 4-11: epilogue      (two warps per TMEM lane quarter, each owning half of the tile's columns:
+//                              tcgen05.ld 32 lanes x 32 columns -> bias/activation/residual -> bf16 ->
+//                              128B-swizzled smem staging tile [32 rows x 64 cols] -> TMA store)
 //
 // Tile order: m fastest inside groups of kGroupM m-tiles, so the CTAs running concurrently share a handful
 // of weight tiles and a 16 x 128-row slab of A in L2 (A is read from HBM once, W stays L2 resident).
@@ -21,7 +23,9 @@ namespace lr {
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kGroupM = 16;
-constexpr int kGemmThreads = 256;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 128 + kEpiWarps * 32;
+constexpr int kStagingBytes = 32 * 128;  // one [32 rows x 64 bf16] tile per epilogue warp
 
 template <int BN>
 struct GemmCfg {
@@ -30,7 +34,8 @@ struct GemmCfg {
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
   static constexpr int kStages = (BN == 256) ? 4 : 6;
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kEpiWarps * kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
@@ -43,18 +48,24 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int&
   n_blk = r / gm;
 }
 
+__device__ __forceinline__ void unpack8_bf16(const uint4& u, float* f) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x, f[1] = a.y, f[2] = b.x, f[3] = b.y, f[4] = c.x, f[5] = c.y, f[6] = d.x, f[7] = d.y;
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                    bf16* __restrict__ C, int ldc, int M, int N, int K, const bf16* __restrict__ bias,
-                    const bf16* __restrict__ R, int ldr) {
+                    const __grid_constant__ CUtensorMap tma_c, int M, int N, int K,
+                    const bf16* __restrict__ bias, const bf16* __restrict__ R, int ldr) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kStageBytesA;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* smem_c = smem + kStages * Cfg::kStageBytes;  // 1024-aligned: every stage size is a multiple of 1024
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + kEpiWarps * kStagingBytes);
   uint64_t* full_bar = bars;                 // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kStages;      // [kStages]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * kStages;  // [2]        MMA -> epilogue
@@ -70,6 +81,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_c);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -78,7 +90,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], kEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -150,74 +162,80 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     __syncwarp();
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int ew = warp - 4;
+    const int q = warp & 3;      // TMEM lane quarter this warp may access (hardware rule: warp_id % 4)
+    const int half = ew >> 2;    // which half of the tile's output columns
+    constexpr int kOutN = (EPI == LR_EPI_SWIGLU) ? BN / 2 : BN;
+    constexpr int kChunks = kOutN / 2 / 64;  // 64-column chunks per warp
+    static_assert(kChunks >= 1, "tile too narrow for 8 epilogue warps");
+    uint8_t* stg = smem_c + ew * kStagingBytes;
+    uint8_t* my_row = stg + lane * 128;
     int as = 0;
     uint32_t aphase = 0;
-    constexpr int kOutN = (EPI == LR_EPI_SWIGLU) ? BN / 2 : BN;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
       tile_coords(tile, num_m, num_n, m_blk, n_blk);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const int row = m_blk * kBM + q * 32 + lane;
+      const int row0 = m_blk * kBM + q * 32;
+      const int row = row0 + lane;
       const bool row_ok = row < M;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
-      bf16* crow = C + size_t(row) * ldc + size_t(n_blk) * kOutN;
-      const bf16* rrow = epi_has_res(EPI) ? (R + size_t(row) * ldr + size_t(n_blk) * kOutN) : nullptr;
 #pragma unroll 1
-      for (int c = 0; c < kOutN / 32; ++c) {
-        uint32_t acc[32];
-        tmem_ld_32x32(taddr + c * 32, acc);
-        float v[32];
-        if constexpr (EPI == LR_EPI_SWIGLU) {
-          uint32_t up[32];
-          tmem_ld_32x32(taddr + BN / 2 + c * 32, up);
-          tmem_ld_wait();
+      for (int c = 0; c < kChunks; ++c) {
+        const int col_t = half * (kOutN / 2) + c * 64;  // first output column of this chunk inside the tile
+        const int col_g = n_blk * kOutN + col_t;        // ... in C
+        uint32_t packed[32];                            // 64 bf16 outputs of this thread's row
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = epi_swiglu(__uint_as_float(acc[j]), __uint_as_float(up[j]));
-        } else {
-          tmem_ld_wait();
-          float bv[32], rv[32];
-          if constexpr (epi_has_bias(EPI)) {
-            const uint4* bp = reinterpret_cast<const uint4*>(bias + size_t(n_blk) * BN + c * 32);
+        for (int hh = 0; hh < 2; ++hh) {                // two 32-column sub-chunks
+          uint32_t acc[32];
+          float v[32];
+          tmem_ld_32x32(taddr + col_t + hh * 32, acc);
+          if constexpr (EPI == LR_EPI_SWIGLU) {
+            uint32_t up[32];
+            tmem_ld_32x32(taddr + BN / 2 + col_t + hh * 32, up);
+            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 u = __ldg(bp + j);
-              float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-              bv[j * 8 + 0] = f0.x, bv[j * 8 + 1] = f0.y, bv[j * 8 + 2] = f1.x, bv[j * 8 + 3] = f1.y;
-              bv[j * 8 + 4] = f2.x, bv[j * 8 + 5] = f2.y, bv[j * 8 + 6] = f3.x, bv[j * 8 + 7] = f3.y;
+            for (int j = 0; j < 32; ++j) v[j] = epi_swiglu(__uint_as_float(acc[j]), __uint_as_float(up[j]));
+          } else {
+            float bv[32], rv[32];
+            if constexpr (epi_has_bias(EPI)) {
+              const uint4* bp = reinterpret_cast<const uint4*>(bias + col_g + hh * 32);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) unpack8_bf16(__ldg(bp + j), bv + j * 8);
             }
-          }
-          if constexpr (epi_has_res(EPI)) {
-            if (row_ok) {
-              const uint4* rp = reinterpret_cast<const uint4*>(rrow + c * 32);
+            if constexpr (epi_has_res(EPI)) {
+              if (row_ok) {
+                const uint4* rp = reinterpret_cast<const uint4*>(R + size_t(row) * ldr + col_g + hh * 32);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 u = rp[j];
-                float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-                rv[j * 8 + 0] = f0.x, rv[j * 8 + 1] = f0.y, rv[j * 8 + 2] = f1.x, rv[j * 8 + 3] = f1.y;
-                rv[j * 8 + 4] = f2.x, rv[j * 8 + 5] = f2.y, rv[j * 8 + 6] = f3.x, rv[j * 8 + 7] = f3.y;
+                for (int j = 0; j < 4; ++j) unpack8_bf16(rp[j], rv + j * 8);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) rv[j] = 0.f;
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) rv[j] = 0.f;
             }
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = epi_apply<EPI>(__uint_as_float(acc[j]), epi_has_bias(EPI) ? bv[j] : 0.f,
+                                    epi_has_res(EPI) ? rv[j] : 0.f);
           }
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = epi_apply<EPI>(__uint_as_float(acc[j]), epi_has_bias(EPI) ? bv[j] : 0.f, epi_has_res(EPI) ? rv[j] : 0.f);
+          for (int j = 0; j < 16; ++j) packed[hh * 16 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
         }
-        if (row_ok) {
-          uint4* cp = reinterpret_cast<uint4*>(crow + c * 32);
+        // staging tile is free once the previous TMA store has finished reading it
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 u;
-            u.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]);
-            u.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
-            u.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]);
-            u.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
-            cp[j] = u;
-          }
+        for (int j = 0; j < 8; ++j) {  // 8 x 16 B, chunk position XOR (row & 7) = the 128B TMA swizzle
+          *reinterpret_cast<uint4*>(my_row + ((j ^ (lane & 7)) << 4)) =
+              make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tma_c, stg, col_g, row0);
+          tma_store_commit();
         }
       }
       tc_fence_before();
@@ -228,6 +246,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         aphase ^= 1;
       }
     }
+    if (lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -260,6 +279,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // 2D bf16 tensor [rows, cols] with row pitch ld elements; box = [64 cols, box_rows], 128B swizzle.
 static int make_tmap(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows) {
+  if (rows <= 0 || cols <= 0) return LR_ERR_BAD_ARG;
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return LR_ERR_NO_DRIVER;
   cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
@@ -286,10 +306,12 @@ template <int BN, int EPI>
 static int launch_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
                        const void* bias, const void* R, int ldr, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc;
   int st = make_tmap(&ta, A, M, K, lda, kBM);
   if (st != LR_OK) return st;
   st = make_tmap(&tb, W, N, K, ldw, BN);
+  if (st != LR_OK) return st;
+  st = make_tmap(&tc, C, M, EPI == LR_EPI_SWIGLU ? N / 2 : N, ldc, 32);
   if (st != LR_OK) return st;
   auto kern = gemm_tcgen05_kernel<BN, EPI>;
   static bool attr_done = false;
@@ -300,8 +322,7 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, void* C, 
   }
   const int num_tiles = ((M + kBM - 1) / kBM) * (N / BN);
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, reinterpret_cast<bf16*>(C), ldc, M, N, K,
-                                                        reinterpret_cast<const bf16*>(bias),
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, M, N, K, reinterpret_cast<const bf16*>(bias),
                                                         reinterpret_cast<const bf16*>(R), ldr);
   return lr_launch_status();
 }

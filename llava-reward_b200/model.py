@@ -41,6 +41,8 @@ class B200RewardModel:
             raise RuntimeError("llava-reward-b200 runs on sm_100a CUDA devices only; there is no CPU fallback")
         L.load()
         L.check(L.load().lr_device_check(), "lr_device_check")
+        if hasattr(self._provider, "device"):
+            self._provider.device = device  # synthetic weights are generated directly on the GPU
         with torch.cuda.device(device):
             weights = pack_weights(self.config, self._provider, device=device)
             self.engine = RewardEngine(self.config, weights, device=device)
