@@ -81,10 +81,13 @@ int lr_clip_embed_ln(const void* patch, const void* class_emb, const void* pos_e
  * Sequence s owns rows [s*rows_per_seq, (s+1)*rows_per_seq); only rows [start, start+len) are valid
  * (seq_start/seq_len may be NULL = whole slot). Invalid rows of o are zero-filled.
  * head_dim 64 (CLIP, non-causal; replaces CLIPAttentionFA2, modeling_phi3_v.py:85-115) or
- * 96 (Phi-3, causal varlen; replaces Phi3FlashAttention2._flash_attention_forward, :888-986). */
+ * 96 (Phi-3, causal varlen; replaces Phi3FlashAttention2._flash_attention_forward, :888-986).
+ * For LR_ATTN_TCGEN05 q, k, v must be column offsets into one row-major buffer (the fused qkv projection). */
+#define LR_ATTN_TCGEN05 0 /* tcgen05.mma + TMEM + TMA, two 128-row query tiles per CTA (product path) */
+#define LR_ATTN_MMA_SYNC 1 /* mma.sync kernel, kept to cross-check the tcgen05 path in tests */
 int lr_attention_bf16(const void* q, const void* k, const void* v, void* o, int ld_qkv, int ld_o, int n_seq,
                       int rows_per_seq, const int* seq_start, const int* seq_len, int n_heads, int head_dim,
-                      int causal, float scale, void* stream);
+                      int causal, float scale, int impl, void* stream);
 
 /* In-place su/longrope rotary embedding on the q and k thirds of a fused qkv buffer [rows, 3*n_heads*head_dim]:
  * x = bf16(bf16(x*cos) + bf16(rot_half(x)*sin)) with bf16 tables cos/sin[pos, head_dim/2].

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libllavareward.so")
 LR_OK = 0
 EPI_NONE, EPI_BIAS, EPI_BIAS_QUICKGELU, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_BIAS_RESIDUAL, EPI_SWIGLU = range(7)
 GEMM_TCGEN05, GEMM_SIMT = 0, 1
+ATTN_TCGEN05, ATTN_MMA_SYNC = 0, 1
 PLAN_STRIDE = 8
 PLAN_HCROP, PLAN_WCROP, PLAN_CROP_BASE, PLAN_ROW_BASE, PLAN_NV = 0, 1, 2, 3, 4
 
@@ -29,7 +30,7 @@ SIGNATURES = {
     "lr_layernorm_bf16": ([p, i32, p, p, p, i32, i32, i32, f32, p], i32),
     "lr_clip_im2col": ([p, p, p, i32, p], i32),
     "lr_clip_embed_ln": ([p, p, p, p, p, p, i32, f32, p], i32),
-    "lr_attention_bf16": ([p, p, p, p, i32, i32, i32, i32, p, p, i32, i32, i32, f32, p], i32),
+    "lr_attention_bf16": ([p, p, p, p, i32, i32, i32, i32, p, p, i32, i32, i32, f32, i32, p], i32),
     "lr_rope_su_bf16": ([p, i32, p, p, p, i32, i32, i32, p], i32),
     "lr_token_plan": ([p, p, i32, i32, p, p, p, p, p, p, p, p], i32),
     "lr_hd_gather_bf16": ([p, p, p, p, p, i32, i32, p], i32),

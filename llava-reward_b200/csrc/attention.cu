@@ -245,17 +245,25 @@ static int launch_attn(const void* q, const void* k, const void* v, void* o, int
   return lr_launch_status();
 }
 
+int attention_tc(const void* q, const void* k, const void* v, void* o, int ld_qkv, int ld_o, int n_seq,
+                 int rows_per_seq, const int* seq_start, const int* seq_len, int n_heads, int head_dim, int causal,
+                 float scale, cudaStream_t s);
+
 }  // namespace lr
 
 extern "C" int lr_attention_bf16(const void* q, const void* k, const void* v, void* o, int ld_qkv, int ld_o,
                                  int n_seq, int rows_per_seq, const int* seq_start, const int* seq_len, int n_heads,
-                                 int head_dim, int causal, float scale, void* stream) {
+                                 int head_dim, int causal, float scale, int impl, void* stream) {
   using namespace lr;
   LR_CHECK_ARG(q && k && v && o && n_seq > 0 && rows_per_seq > 0 && n_heads > 0);
   if ((ld_qkv % 8) || (ld_o % 8) || (reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
                                      reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(o)) & 15)
     return LR_ERR_ALIGN;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (impl == LR_ATTN_TCGEN05)
+    return attention_tc(q, k, v, o, ld_qkv, ld_o, n_seq, rows_per_seq, seq_start, seq_len, n_heads, head_dim, causal,
+                        scale, s);
+  if (impl != LR_ATTN_MMA_SYNC) return LR_ERR_BAD_ARG;
   if (head_dim == 64 && !causal)
     return launch_attn<64, false>(q, k, v, o, ld_qkv, ld_o, n_seq, rows_per_seq, seq_start, seq_len, n_heads, scale, s);
   if (head_dim == 96 && causal)

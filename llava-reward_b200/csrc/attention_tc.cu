@@ -1,0 +1,417 @@
+// Flash-style prefill attention on tcgen05 tensor cores (sm_100a): S = Q K^T and O += P V are tcgen05.mma with
+// the accumulators in TMEM; K/V/Q tiles arrive by TMA (64B-swizzled atoms of 32 head-dim columns, so head_dim 96
+// needs no padding); softmax runs thread-per-row out of TMEM.
+//
+// One CTA = 256 query rows of one head (two 128-row tiles A and B), 384 threads:
+//   warp 0    : TMA producer (Q_A, Q_B once; K_j / V_j through two 2-stage rings shared by both tiles)
+//   warp 1    : MMA issuer   (S_X(j) = Q_X K_j^T  [128x128xHD],  O_X += P_X(j) V_j  [128xHDx128], X in {A,B})
+//   warp 2    : TMEM allocator (S_A, S_B: 128 fp32 columns each; O_A, O_B: HD columns each)
+//   warps 4-7 : softmax warpgroup of tile A,   warps 8-11: softmax warpgroup of tile B
+//               (tcgen05.ld the whole 128-column S row into registers and hand the S buffer straight back so
+//                S_X(j+1) is computed while this block's softmax runs -> running max / exp2 / row sum -> bf16 P
+//                row into 128B-swizzled smem -> mbarrier; O is rescaled in TMEM (tcgen05.ld/st) lazily, only when
+//                the row max grew by > 2^8)
+// The softmax warpgroups therefore run back to back; all MMA work hides behind them.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace lr {
+
+constexpr int kTcThreads = 384;
+constexpr int kAtomBytes = 128 * 64;      // [128 rows x 32 bf16], 64B swizzle
+constexpr int kPBytes = 128 * 128 * 2;    // P tile: two [128 x 64 bf16] 128B-swizzled atoms
+constexpr float kRescaleThreshold = 8.f;  // log2 units: P stays <= 2^8 between rescales
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= uint64_t((addr >> 4) & 0x3FFF);
+  d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(layout) << 61;
+  return d;
+}
+constexpr uint32_t kLayoutSW128 = 2, kLayoutSW64 = 4;
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+      "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+      "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int HD>
+struct AttnTcCfg {
+  static constexpr int kAtoms = HD / 32;
+  static constexpr int kTileBytes = kAtoms * kAtomBytes;  // one Q / K / V tile
+  static constexpr int kSmemBytes = 2 * kTileBytes /*Q_A,Q_B*/ + 4 * kTileBytes /*K,V x 2 stages*/ + 2 * kPBytes +
+                                    1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int HD, bool CAUSAL>
+__global__ void __launch_bounds__(kTcThreads, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o, int ld_o, int rows_per_seq,
+               const int* __restrict__ seq_start, const int* __restrict__ seq_len, int q_col0, int k_col0, int v_col0,
+               float scale_log2) {
+  using Cfg = AttnTcCfg<HD>;
+  constexpr int NA = Cfg::kAtoms;
+  constexpr int TILE = Cfg::kTileBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                    // [2][TILE]
+  uint8_t* sK = sQ + 2 * TILE;           // [2][TILE]
+  uint8_t* sV = sK + 2 * TILE;           // [2][TILE]
+  uint8_t* sP = sV + 2 * TILE;           // [2][kPBytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
+  uint64_t* q_full = bars;               // [1]
+  uint64_t* k_full = bars + 1;           // [2]
+  uint64_t* k_empty = bars + 3;          // [2]
+  uint64_t* v_full = bars + 5;           // [2]
+  uint64_t* v_empty = bars + 7;          // [2]
+  uint64_t* s_full = bars + 9;           // [2] per tile  MMA -> softmax : S_x(j) is in TMEM
+  uint64_t* s_free = bars + 11;          // [2] per tile  softmax -> MMA : S_x(j) has been read into registers
+  uint64_t* p_full = bars + 13;          // [2] per tile  softmax -> MMA : P_x(j) is in smem (and O_x rescaled)
+  uint64_t* pv_done = bars + 15;         // [2] per tile  MMA -> softmax : O_x += P_x(j) V_j retired
+  uint64_t* o_final = bars + 17;         // [2] per tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int seq = blockIdx.z, head = blockIdx.y;
+  const int qt = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+  const int m0 = qt * 256;
+  const int start = seq_start ? seq_start[seq] : 0;
+  const int len = seq_len ? seq_len[seq] : rows_per_seq;
+  const int end = start + len;
+  const int slot_row0 = seq * rows_per_seq;
+
+  int lo[2], hi[2], nblk[2], kv_end[2];
+#pragma unroll
+  for (int x = 0; x < 2; ++x) {
+    lo[x] = max(m0 + x * 128, start);
+    hi[x] = min(min(m0 + x * 128 + 128, end), rows_per_seq);
+    const bool valid = lo[x] < hi[x];
+    kv_end[x] = valid ? (CAUSAL ? min(end, hi[x]) : end) : start;
+    nblk[x] = (kv_end[x] - start + 127) / 128;
+  }
+  const int n = max(nblk[0], nblk[1]);
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_qkv);
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&pv_done[i], 1);
+      mbar_init(&o_final[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_S[2] = {tmem_base, tmem_base + 128};
+  const uint32_t tm_O[2] = {tmem_base + 256, tmem_base + 384};
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0 && n > 0) {
+      const uint32_t q_bytes = (nblk[0] > 0 ? TILE : 0) + (nblk[1] > 0 ? TILE : 0);
+      mbar_arrive_expect_tx(q_full, q_bytes);
+#pragma unroll
+      for (int x = 0; x < 2; ++x)
+        if (nblk[x] > 0)
+          for (int a = 0; a < NA; ++a)
+            tma_load_2d(sQ + x * TILE + a * kAtomBytes, &tm_qkv, q_full, q_col0 + head * HD + a * 32,
+                        slot_row0 + m0 + x * 128);
+      for (int j = 0; j < n; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        const int row = slot_row0 + start + j * 128;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], TILE);
+        for (int a = 0; a < NA; ++a)
+          tma_load_2d(sK + s * TILE + a * kAtomBytes, &tm_qkv, &k_full[s], k_col0 + head * HD + a * 32, row);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[s], TILE);
+        for (int a = 0; a < NA; ++a)
+          tma_load_2d(sV + s * TILE + a * kAtomBytes, &tm_qkv, &v_full[s], v_col0 + head * HD + a * 32, row);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0 && n > 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD) | (1u << 16);  // B (= V) is MN-major
+      auto issue_s = [&](int x, int ks) {  // S_x = Q_x K^T : A = Q (K-major, SW64), B = K stage ks (K-major, SW64)
+        const uint32_t qa = smem_u32(sQ + x * TILE), ka = smem_u32(sK + ks * TILE);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t off = (kk >> 1) * kAtomBytes + (kk & 1) * 32;
+          umma_bf16_ss(tm_S[x], umma_desc(qa + off, 16, 512, kLayoutSW64), umma_desc(ka + off, 16, 512, kLayoutSW64),
+                       idesc_s, kk != 0);
+        }
+        umma_commit(&s_full[x]);
+      };
+      auto issue_pv = [&](int x, int vs, bool acc) {  // O_x += P_x V : A = P (K-major, SW128), B = V (MN-major, SW64)
+        const uint32_t pa = smem_u32(sP + x * kPBytes), va = smem_u32(sV + vs * TILE);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          umma_bf16_ss(tm_O[x], umma_desc(pa + (kk >> 2) * (kPBytes / 2) + (kk & 3) * 32, 16, 1024, kLayoutSW128),
+                       umma_desc(va + kk * 1024, kAtomBytes, 512, kLayoutSW64), idesc_o, acc || kk != 0);
+        }
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      if (nblk[0] > 0) issue_s(0, 0);
+      if (nblk[1] > 0) issue_s(1, 0);
+      umma_commit(&k_empty[0]);
+      for (int j = 0; j < n; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        const bool more = j + 1 < n;
+        if (more) mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+        bool v_ready = false;
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          if (j < nblk[x]) {
+            if (j + 1 < nblk[x]) {  // next S as soon as the softmax warps hold S_x(j) in registers
+              mbar_wait(&s_free[x], j & 1);
+              tc_fence_after();
+              issue_s(x, (j + 1) & 1);
+            }
+            if (!v_ready) {
+              mbar_wait(&v_full[s], ph);
+              v_ready = true;
+            }
+            mbar_wait(&p_full[x], j & 1);
+            tc_fence_after();
+            issue_pv(x, s, j > 0);
+            umma_commit(&pv_done[x]);
+            if (j + 1 == nblk[x]) umma_commit(&o_final[x]);
+          }
+        }
+        umma_commit(&v_empty[s]);
+        if (more) umma_commit(&k_empty[(j + 1) & 1]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax warpgroups
+    const int x = (warp - 4) >> 2;   // tile A (warps 4-7) or B (warps 8-11)
+    const int q = warp & 3;          // TMEM lane quarter
+    const int r = q * 32 + lane;     // row inside the tile
+    const int row_abs = m0 + x * 128 + r;
+    const uint32_t lane_addr = uint32_t(q * 32) << 16;
+    uint8_t* prow = sP + x * kPBytes + r * 128;
+    float m_ref = -INFINITY, l_sum = 0.f;
+    const int nx = nblk[x];
+    for (int j = 0; j < nx; ++j) {
+      mbar_wait(&s_full[x], j & 1);
+      tc_fence_after();
+      const int kv0 = start + j * 128;
+      const bool need_mask = (kv0 + 128 > kv_end[x]) || (CAUSAL && kv0 + 127 > m0 + x * 128);
+      // whole S row -> registers, then give the TMEM buffer back to the MMA warp
+      uint32_t sv[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(tm_S[x] + lane_addr + c * 32, sv[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[x]);
+      if (need_mask) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int col = kv0 + c * 32 + i;
+            const bool ok = col < kv_end[x] && (!CAUSAL || col <= row_abs);
+            sv[c][i] = ok ? sv[c][i] : 0xff800000u;  // -inf
+          }
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[c][i]));
+      mx *= scale_log2;  // scale > 0, so max commutes with the scaling
+      // lazy rescale: move the reference max only when it grew by more than the threshold
+      float alpha = 1.f;
+      const bool grow = mx > m_ref + kRescaleThreshold || (m_ref == -INFINITY && mx > -INFINITY);
+      if (grow) {
+        alpha = exp2f(m_ref - mx);  // 0 when m_ref = -inf
+        m_ref = mx;
+        l_sum *= alpha;
+      }
+      const float msafe = (m_ref == -INFINITY) ? 0.f : m_ref;
+      // P = exp2(S*scale - m_ref) (masked entries: exp2(-inf) = 0), row sum in fp32, packed to bf16 in place
+      uint32_t pk[4][16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float e0 = exp2f(fmaf(__uint_as_float(sv[c][2 * i]), scale_log2, -msafe));
+          const float e1 = exp2f(fmaf(__uint_as_float(sv[c][2 * i + 1]), scale_log2, -msafe));
+          l_sum += e0 + e1;
+          pk[c][i] = pack_bf16x2(e0, e1);
+        }
+      // P_x buffer and O_x may be touched only after O_x += P_x(j-1) V_(j-1) has retired
+      if (j > 0) {
+        mbar_wait(&pv_done[x], (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll 1
+          for (int c = 0; c < HD / 32; ++c) {
+            uint32_t ov[32];
+            tmem_ld_32x32(tm_O[x] + lane_addr + c * 32, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st_32x32(tm_O[x] + lane_addr + c * 32, ov);
+          }
+          tmem_st_wait();
+        }
+      }
+      // 128 columns = 2 atoms x 8 chunks of 16 B; chunk position XOR (row & 7) = the 128B swizzle
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint8_t* base = prow + (c >> 1) * (kPBytes / 2);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int chunk = ((c & 1) * 4 + t) ^ (r & 7);
+          *reinterpret_cast<uint4*>(base + (chunk << 4)) =
+              make_uint4(pk[c][4 * t], pk[c][4 * t + 1], pk[c][4 * t + 2], pk[c][4 * t + 3]);
+        }
+      }
+      fence_proxy_async_smem();  // P (generic-proxy stores) must be visible to the tensor core's async proxy
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[x]);
+    }
+    // epilogue: O / l -> bf16 -> global; rows outside the valid run are zero-filled
+    const bool row_in_slot = row_abs < rows_per_seq;
+    const bool row_valid = row_abs >= lo[x] && row_abs < hi[x];
+    bf16* orow = o + size_t(slot_row0 + row_abs) * ld_o + head * HD;
+    if (nx > 0) {
+      mbar_wait(&o_final[x], 0);
+      tc_fence_after();
+      const float inv = l_sum > 0.f ? 1.f / l_sum : 0.f;
+#pragma unroll 1
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t ov[32];
+        tmem_ld_32x32(tm_O[x] + lane_addr + c * 32, ov);
+        tmem_ld_wait();
+        if (row_in_slot) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            uint4 u = make_uint4(0, 0, 0, 0);
+            if (row_valid) {
+              u.x = pack_bf16x2(__uint_as_float(ov[8 * t]) * inv, __uint_as_float(ov[8 * t + 1]) * inv);
+              u.y = pack_bf16x2(__uint_as_float(ov[8 * t + 2]) * inv, __uint_as_float(ov[8 * t + 3]) * inv);
+              u.z = pack_bf16x2(__uint_as_float(ov[8 * t + 4]) * inv, __uint_as_float(ov[8 * t + 5]) * inv);
+              u.w = pack_bf16x2(__uint_as_float(ov[8 * t + 6]) * inv, __uint_as_float(ov[8 * t + 7]) * inv);
+            }
+            *reinterpret_cast<uint4*>(orow + c * 32 + t * 8) = u;
+          }
+        }
+      }
+    } else if (row_in_slot) {
+#pragma unroll 1
+      for (int c = 0; c < HD / 8; ++c) *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(0, 0, 0, 0);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn attn_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+template <int HD, bool CAUSAL>
+static int launch_attn_tc(const void* base, int total_rows, int ld_qkv, int q_col0, int k_col0, int v_col0, void* o,
+                          int ld_o, int n_seq, int rows_per_seq, const int* seq_start, const int* seq_len, int n_heads,
+                          float scale, cudaStream_t stream) {
+  using Cfg = AttnTcCfg<HD>;
+  EncodeTiledFn fn = attn_encode_fn();
+  if (!fn) return LR_ERR_NO_DRIVER;
+  CUtensorMap tm;
+  cuuint64_t dims[2] = {cuuint64_t(ld_qkv), cuuint64_t(total_rows)};
+  cuuint64_t strides[1] = {cuuint64_t(ld_qkv) * 2};
+  cuuint32_t box[2] = {32, 128};
+  cuuint32_t estr[2] = {1, 1};
+  if (fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return LR_ERR_BAD_ARG;
+  auto kern = attn_tc_kernel<HD, CAUSAL>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_done = true;
+  }
+  dim3 grid((rows_per_seq + 255) / 256, n_heads, n_seq);
+  kern<<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(tm, reinterpret_cast<bf16*>(o), ld_o, rows_per_seq, seq_start,
+                                                      seq_len, q_col0, k_col0, v_col0, scale * 1.4426950408889634f);
+  return lr_launch_status();
+}
+
+// q, k, v must be column offsets into ONE row-major buffer (the fused qkv projection): base = q.
+int attention_tc(const void* q, const void* k, const void* v, void* o, int ld_qkv, int ld_o, int n_seq,
+                 int rows_per_seq, const int* seq_start, const int* seq_len, int n_heads, int head_dim, int causal,
+                 float scale, cudaStream_t s) {
+  const ptrdiff_t kd = (reinterpret_cast<const char*>(k) - reinterpret_cast<const char*>(q)) / 2;
+  const ptrdiff_t vd = (reinterpret_cast<const char*>(v) - reinterpret_cast<const char*>(q)) / 2;
+  const int width = n_heads * head_dim;
+  if (kd < 0 || vd < 0 || kd + width > ld_qkv || vd + width > ld_qkv) return LR_ERR_BAD_ARG;
+  const int total_rows = n_seq * rows_per_seq;
+  if (head_dim == 64 && !causal)
+    return launch_attn_tc<64, false>(q, total_rows, ld_qkv, 0, int(kd), int(vd), o, ld_o, n_seq, rows_per_seq,
+                                     seq_start, seq_len, n_heads, scale, s);
+  if (head_dim == 96 && causal)
+    return launch_attn_tc<96, true>(q, total_rows, ld_qkv, 0, int(kd), int(vd), o, ld_o, n_seq, rows_per_seq,
+                                    seq_start, seq_len, n_heads, scale, s);
+  return LR_ERR_BAD_ARG;
+}
+
+}  // namespace lr

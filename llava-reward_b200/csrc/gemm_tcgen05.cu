@@ -11,8 +11,8 @@
 //                              tcgen05.ld 32 lanes x 32 columns -> bias/activation/residual -> bf16 ->
 //                              128B-swizzled smem staging tile [32 rows x 64 cols] -> TMA store)
 //
-// Tile order: m fastest inside groups of kGroupM m-tiles, so the CTAs running concurrently share a handful
-// of weight tiles and a 16 x 128-row slab of A in L2 (A is read from HBM once, W stays L2 resident).
+// Tile order: m fastest inside groups of group_m m-tiles, so the CTAs running concurrently share a handful
+// of weight tiles and a ~32 MB slab of A in L2 (A is read from HBM once, W once per group).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -22,7 +22,6 @@ namespace lr {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int kGroupM = 16;
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 128 + kEpiWarps * 32;
 constexpr int kStagingBytes = 32 * 128;  // one [32 rows x 64 bf16] tile per epilogue warp
@@ -38,11 +37,11 @@ struct GemmCfg {
       kStages * kStageBytes + kEpiWarps * kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
-  const int per_group = kGroupM * num_n;
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int group_m, int& m_blk, int& n_blk) {
+  const int per_group = group_m * num_n;
   const int g = tile / per_group;
-  const int first_m = g * kGroupM;
-  const int gm = min(kGroupM, num_m - first_m);
+  const int first_m = g * group_m;
+  const int gm = min(group_m, num_m - first_m);
   const int r = tile - g * per_group;
   m_blk = first_m + r % gm;
   n_blk = r / gm;
@@ -57,7 +56,7 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const __grid_constant__ CUtensorMap tma_c, int M, int N, int K,
-                    const bf16* __restrict__ bias, const bf16* __restrict__ R, int ldr) {
+                    const bf16* __restrict__ bias, const bf16* __restrict__ R, int ldr, int group_m) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -110,7 +109,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int m_blk, n_blk;
-        tile_coords(tile, num_m, num_n, m_blk, n_blk);
+        tile_coords(tile, num_m, num_n, group_m, m_blk, n_blk);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -174,7 +173,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
-      tile_coords(tile, num_m, num_n, m_blk, n_blk);
+      tile_coords(tile, num_m, num_n, group_m, m_blk, n_blk);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const int row0 = m_blk * kBM + q * 32;
@@ -322,8 +321,12 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, void* C, 
   }
   const int num_tiles = ((M + kBM - 1) / kBM) * (N / BN);
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  // m-tiles per rasterisation group: keep the group's A slab (group_m x 128 x K bf16) around 32 MB so it stays
+  // L2-resident while the group sweeps all n-tiles; W is then streamed from HBM once per group.
+  int group_m = int((32ll << 20) / (int64_t(kBM) * K * 2));
+  group_m = group_m < 8 ? 8 : (group_m > 64 ? 64 : group_m);
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, M, N, K, reinterpret_cast<const bf16*>(bias),
-                                                        reinterpret_cast<const bf16*>(R), ldr);
+                                                        reinterpret_cast<const bf16*>(R), ldr, group_m);
   return lr_launch_status();
 }
 

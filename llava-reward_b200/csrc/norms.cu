@@ -117,6 +117,42 @@ layernorm_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ w
   layernorm_row(v, nchunk, cols, w, b, y + row * ldy, eps, red);
 }
 
+// Warp-per-row LayerNorm for 1024-column rows (CLIP): 4 x 16 B per lane, shuffle reductions only, 8 rows per CTA.
+__global__ void __launch_bounds__(256)
+layernorm1024_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ w, const bf16* __restrict__ b,
+                     bf16* __restrict__ y, int ldy, int rows, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const bf16* xr = x + size_t(row) * ldx;
+  float f[4][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    unpack8(ldg128(xr + (lane + 32 * i) * 8), f[i]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += f[i][j];
+  }
+  const float mean = warp_sum(s) * (1.f / 1024.f);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sq += (f[i][j] - mean) * (f[i][j] - mean);
+  const float rstd = rsqrtf(warp_sum(sq) * (1.f / 1024.f) + eps);
+  bf16* yr = y + size_t(row) * ldy;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = (lane + 32 * i) * 8;
+    float g[8], h[8];
+    unpack8(ldg128(w + c), g);
+    unpack8(ldg128(b + c), h);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[i][j] = (f[i][j] - mean) * rstd * g[j] + h[j];
+    stg128(yr + c, pack8(f[i]));
+  }
+}
+
 // CLIP: tokens[c*577+t] = LN( bf16( (t ? patch[c*576+t-1] : class_emb) + pos[t] ) ), 1024 columns.
 __global__ void __launch_bounds__(kRowThreads)
 clip_embed_ln_kernel(const bf16* __restrict__ patch, const bf16* __restrict__ cls, const bf16* __restrict__ pos,
@@ -194,6 +230,12 @@ extern "C" int lr_layernorm_bf16(const void* x, int ldx, const void* w, const vo
                                  int cols, float eps, void* stream) {
   LR_CHECK_ARG(x && w && b && y && rows > 0 && cols > 0 && cols % 8 == 0 && cols <= kRowThreads * kMaxChunks * 8);
   if ((ldx % 8) || (ldy % 8) || !aligned16(x) || !aligned16(w) || !aligned16(b) || !aligned16(y)) return LR_ERR_ALIGN;
+  if (cols == 1024) {
+    layernorm1024_kernel<<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(w), reinterpret_cast<const bf16*>(b),
+        reinterpret_cast<bf16*>(y), ldy, rows, eps);
+    return lr_launch_status();
+  }
   layernorm_kernel<<<rows, kRowThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(w), reinterpret_cast<const bf16*>(b),
       reinterpret_cast<bf16*>(y), ldy, cols, eps);

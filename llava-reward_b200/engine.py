@@ -20,9 +20,11 @@ from .weights import PackedWeights
 
 
 class RewardEngine:
-    def __init__(self, cfg: RewardConfig, weights: PackedWeights, device="cuda", gemm_impl: int = L.GEMM_TCGEN05):
+    def __init__(self, cfg: RewardConfig, weights: PackedWeights, device="cuda", gemm_impl: int = L.GEMM_TCGEN05,
+                 attn_impl: int = L.ATTN_TCGEN05):
         L.load()
         self.cfg, self.w, self.device, self.gemm_impl = cfg, weights, torch.device(device), gemm_impl
+        self.attn_impl = attn_impl
         self._bufs: Dict[Tuple[str, Tuple[int, ...], torch.dtype], torch.Tensor] = {}
         self._rope: Dict[Tuple[int, bool], Tuple[torch.Tensor, torch.Tensor]] = {}
         self.launches = 0        # kernels launched by the last forward (for bench `gpu_launches`)
@@ -140,7 +142,7 @@ class RewardEngine:
             ops.layernorm(x, lw["ln1_w"], lw["ln1_b"], hn, Mv, D, cfg.clip_eps)
             self._gemm(hn, lw["qkv_w"], qkv, Mv, 3 * D, D, L.EPI_BIAS, lw["qkv_b"])
             ops.attention(qkv, qkv[:, D:], qkv[:, 2 * D:], ao, 3 * D, D, n_crops, T, None, None, cfg.clip_heads,
-                          cfg.clip_head_dim, False, scale)
+                          cfg.clip_head_dim, False, scale, self.attn_impl)
             self._gemm(ao, lw["out_w"], x, Mv, D, D, L.EPI_BIAS_RESIDUAL, lw["out_b"], x)
             ops.layernorm(x, lw["ln2_w"], lw["ln2_b"], hn, Mv, D, cfg.clip_eps)
             self._gemm(hn, lw["fc1_w"], ff, Mv, DI, D, L.EPI_BIAS_QUICKGELU, lw["fc1_b"])
@@ -180,7 +182,7 @@ class RewardEngine:
             self._gemm(xn, lw["qkv_w"], dqkv, M, 3 * H, H + r)
             ops.rope_su(dqkv, pos, cos_tab, sin_tab, M, nh, hd)
             ops.attention(dqkv, dqkv[:, H:], dqkv[:, 2 * H:], dao, 3 * H, H + r, B, S, seq_start, seq_len, nh, hd,
-                          True, att_scale)
+                          True, att_scale, self.attn_impl)
             if r:
                 self._gemm(dao, lw["o_a"], dao[:, H:], M, r, H)
             self._gemm(dao, lw["o_w"], hid, M, H, H + r, L.EPI_RESIDUAL, None, hid)

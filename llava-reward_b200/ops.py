@@ -52,10 +52,11 @@ def clip_embed_ln(patch, cls, pos, w, b, tokens, n_crops, eps):
     L.call("lr_clip_embed_ln", _ptr(patch), _ptr(cls), _ptr(pos), _ptr(w), _ptr(b), _ptr(tokens), n_crops, eps, _stream())
 
 
-def attention(q, k, v, o, ld_qkv, ld_o, n_seq, rows_per_seq, seq_start, seq_len, n_heads, head_dim, causal, scale):
+def attention(q, k, v, o, ld_qkv, ld_o, n_seq, rows_per_seq, seq_start, seq_len, n_heads, head_dim, causal, scale,
+              impl: int = L.ATTN_TCGEN05):
     _need_cuda(q, k, v, o, seq_start, seq_len)
     L.call("lr_attention_bf16", _ptr(q), _ptr(k), _ptr(v), _ptr(o), ld_qkv, ld_o, n_seq, rows_per_seq, _ptr(seq_start),
-           _ptr(seq_len), n_heads, head_dim, int(causal), scale, _stream())
+           _ptr(seq_len), n_heads, head_dim, int(causal), scale, impl, _stream())
 
 
 def rope_su(qkv, position_ids, cos_tab, sin_tab, rows, n_heads, head_dim):

@@ -33,7 +33,7 @@ def test_argument_validation_without_gpu(lib):
     # bad arguments are rejected before any CUDA call
     assert lib.lr_gemm_bf16(None, 0, None, 0, None, 0, 1, 1, 1, 0, None, None, 0, 0, None) == -1
     assert lib.lr_rmsnorm_bf16(None, 0, None, None, None, 0, 1, 8, 1e-5, None) == -1
-    assert lib.lr_attention_bf16(None, None, None, None, 0, 0, 1, 1, None, None, 1, 64, 0, 1.0, None) == -1
+    assert lib.lr_attention_bf16(None, None, None, None, 0, 0, 1, 1, None, None, 1, 64, 0, 1.0, 0, None) == -1
     if not torch.cuda.is_available():
         assert lib.lr_device_check() != 0
         from llava_reward_b200 import ops

@@ -133,11 +133,18 @@ def test_batch_composition_quirk(tmp_path_factory):
     first = int(mask[0].nonzero()[0])
     r_alone, _ = model.custom_forward(ids[:1, first:], mask[:1, first:], pix[:1], sizes[:1])
     P = O.Params(SynthProvider(cfg, seed=fx["seed_w"], device="cuda"), dtype=torch.float32, device="cuda")
+    P16 = O.Params(SynthProvider(cfg, seed=fx["seed_w"], device="cuda"), dtype=torch.bfloat16, device="cuda")
     with torch.no_grad():
         o_b = O.custom_forward(P, cfg, ids, mask, pix, sizes)
         o_a = O.custom_forward(P, cfg, ids[:1, first:], mask[:1, first:], pix[:1], sizes[:1])
-    assert (r_batched[0].float() - o_b[0]).abs().max().item() < REWARD_TOL
-    assert (r_alone[0].float() - o_a[0]).abs().max().item() < REWARD_TOL
+        h_b = O.custom_forward(P16, cfg, ids, mask, pix, sizes)
+        h_a = O.custom_forward(P16, cfg, ids[:1, first:], mask[:1, first:], pix[:1], sizes[:1])
+    floor = max((h_b.float() - o_b).abs().max().item(), (h_a.float() - o_a).abs().max().item())
+    e_b = (r_batched[0].float() - o_b[0]).abs().max().item()
+    e_a = (r_alone[0].float() - o_a[0]).abs().max().item()
+    print(f"quirk: fp32 oracle alone {o_a[0].tolist()} batched {o_b[0].tolist()} | engine err batched {e_b:.4g} "
+          f"alone {e_a:.4g} | reference bf16 noise {floor:.4g}")
+    assert e_b < REWARD_TOL + floor and e_a < REWARD_TOL + floor
 
 
 def test_tcgen05_and_simt_engines_agree(tmp_path_factory):

@@ -182,21 +182,23 @@ def attn_ref(q, k, v, causal, scale, start=0, length=None):
     return out
 
 
+@pytest.mark.parametrize("impl", [L.ATTN_TCGEN05, L.ATTN_MMA_SYNC])
 @pytest.mark.parametrize("hd,heads,T,nseq,causal", [(64, 16, 577, 3, False), (96, 32, 700, 2, True),
-                                                    (96, 4, 130, 3, True), (64, 2, 64, 1, False)])
-def test_attention(hd, heads, T, nseq, causal):
+                                                    (96, 4, 130, 3, True), (64, 2, 64, 1, False),
+                                                    (96, 2, 2048, 3, True), (64, 3, 1000, 2, False)])
+def test_attention(hd, heads, T, nseq, causal, impl):
     D = heads * hd
     qkv = rnd(nseq * T, 3 * D, seed=1)
     o = torch.full((nseq * T, D + 128), float("nan"), dtype=bf, device=DEV)
     if causal:
-        lens = [T, T - 37, 5][:nseq]
+        lens = [T, T - 37, 5][:nseq] if T < 2000 else [T, T - 87, 1300][:nseq]
         starts = [T - n for n in lens]
         ss = torch.tensor(starts, dtype=torch.int32, device=DEV)
         sl = torch.tensor(lens, dtype=torch.int32, device=DEV)
     else:
         lens, starts, ss, sl = [T] * nseq, [0] * nseq, None, None
     scale = hd ** -0.5
-    ops.attention(qkv, qkv[:, D:], qkv[:, 2 * D:], o, 3 * D, D + 128, nseq, T, ss, sl, heads, hd, causal, scale)
+    ops.attention(qkv, qkv[:, D:], qkv[:, 2 * D:], o, 3 * D, D + 128, nseq, T, ss, sl, heads, hd, causal, scale, impl)
     torch.cuda.synchronize()
     f = qkv.float().view(nseq, T, 3, heads, hd)
     for s in range(nseq):

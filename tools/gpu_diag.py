@@ -74,15 +74,15 @@ def gemm_diag():
             break
 
 
-def perf():
+def perf(gemms=True):
     res = {}
-    for name, (M, N, K, epi) in {
+    for name, (M, N, K, epi) in ({} if not gemms else {
         "qkv": (65536, 9216, 3200, L.EPI_NONE), "o": (65536, 3072, 3200, L.EPI_RESIDUAL),
         "gate_up": (65536, 16384, 3200, L.EPI_SWIGLU), "down": (65536, 3072, 8320, L.EPI_RESIDUAL),
         "lora_a": (65536, 128, 3072, L.EPI_NONE), "clip_qkv": (240032, 3072, 1024, L.EPI_BIAS),
         "clip_fc1": (240032, 4096, 1024, L.EPI_BIAS_QUICKGELU), "clip_fc2": (240032, 1024, 4096, L.EPI_BIAS_RESIDUAL),
         "clip_out": (240032, 1024, 1024, L.EPI_BIAS_RESIDUAL),
-    }.items():
+    }).items():
         A = torch.randn(M, K, device="cuda", dtype=bf)
         W = torch.randn(N, K, device="cuda", dtype=bf) * 0.02
         n_out = N // 2 if epi == L.EPI_SWIGLU else N
@@ -101,11 +101,12 @@ def perf():
         D = heads * hd
         qkv = torch.randn(nseq * T, 3 * D, device="cuda", dtype=bf)
         o = torch.empty(nseq * T, D, device="cuda", dtype=bf)
-        ms = timeit(lambda: ops.attention(qkv, qkv[:, D:], qkv[:, 2 * D:], o, 3 * D, D, nseq, T, None, None, heads, hd,
-                                          causal, hd ** -0.5))
         fl = 4.0 * nseq * heads * T * T * hd * (0.5 if causal else 1.0)
-        res["attn_" + name] = {"ms": ms, "tflops": fl / ms / 1e9}
-        print(f"attention {name}: {ms:.3f} ms {fl / ms / 1e9:.0f} TF/s", flush=True)
+        for impl, iname in ((L.ATTN_TCGEN05, "tcgen05"), (L.ATTN_MMA_SYNC, "mma.sync")):
+            ms = timeit(lambda: ops.attention(qkv, qkv[:, D:], qkv[:, 2 * D:], o, 3 * D, D, nseq, T, None, None, heads,
+                                              hd, causal, hd ** -0.5, impl))
+            res[f"attn_{name}_{iname}"] = {"ms": ms, "tflops": fl / ms / 1e9}
+            print(f"attention {name} {iname}: {ms:.3f} ms {fl / ms / 1e9:.0f} TF/s", flush=True)
     # norms
     x = torch.randn(65536, 3072, device="cuda", dtype=bf)
     w = torch.ones(3072, device="cuda", dtype=bf)
@@ -122,6 +123,8 @@ if __name__ == "__main__":
         gemm_diag()
     if "perf" in what:
         perf()
+    if "attn" in what:
+        perf(gemms=False)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "diag.json"), "w") as f:
         json.dump(out, f, indent=1)

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "attention and not impl1" -x > gpurun_out/t_attn_tc.log 2>&1; echo "attn tc exit $?"; tail -25 gpurun_out/t_attn_tc.log
+timeout 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "layernorm or impl1" > gpurun_out/t_other.log 2>&1; echo "other exit $?"; tail -3 gpurun_out/t_other.log
+timeout 600 python tools/gpu_diag.py perf > gpurun_out/diag_perf.log 2>&1; echo "diag_perf exit $?"; tail -6 gpurun_out/diag_perf.log
