@@ -139,6 +139,23 @@ int lr_skipca_head(const float* scores, const void* kv, int ldkv, const int* pla
 int lr_preference(const void* chosen, const void* reject, float* prob, int n, int vhd, int is_gpm, float tau,
                   void* stream);
 
+/* One pass of Pillow's 8-bit antialiased resample (ImagingResampleHorizontal/Vertical_8bpc) along `axis`
+ * (1 = horizontal, 0 = vertical) of an H x W x 3 uint8 image on the device. bounds[o] = {first source index, taps},
+ * coeffs[o][ksize] = 22-bit fixed-point taps, both precomputed on the host exactly as Pillow's precompute_coeffs +
+ * normalize_coeffs_8bpc (device pointers). Replaces torchvision.transforms.functional.resize on a PIL image
+ * (processing_phi3_v.py:98). Bit-exact. */
+int lr_resample_u8(const uint8_t* src, int src_h, int src_w, uint8_t* dst, int dst_h, int dst_w, int axis,
+                   const int* bounds, const int* coeffs, int ksize, void* stream);
+
+/* Resized uint8 image [rh, rw, 3] placed at (pad_top, pad_left) inside a white H x W canvas (H, W multiples of 336)
+ * -> out fp32 [n_slots, 3, 336, 336]: slot 0 = bicubic (A=-0.75, align_corners=False) 336x336 view of the normalised
+ * canvas, slots 1..(H/336*W/336) = its 336x336 crops in row-major order, remaining slots zero. Normalisation =
+ * (u8/255 - mean)/std in IEEE fp32 (mean3/std3 are HOST pointers to 3 floats). Replaces padding_336, ToTensor,
+ * Normalize, F.interpolate(bicubic), the crop reshape/permute and pad_to_max_num_crops_tensor
+ * (processing_phi3_v.py:62-71, 128-136, 252-277). Crops bit-exact, global view within 1e-5. */
+int lr_hd_pack_f32(const uint8_t* img, int rh, int rw, int pad_top, int pad_left, int H, int W, const float* mean3,
+                   const float* std3, float* out, int n_slots, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

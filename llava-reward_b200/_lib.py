@@ -38,6 +38,8 @@ SIGNATURES = {
     "lr_skipca_scores": ([p, i32, p, i32, p, p, i32, i32, i32, p], i32),
     "lr_skipca_head": ([p, p, i32, p, p, i32, p, p, p, i32, i32, i32, i32, f32, p], i32),
     "lr_preference": ([p, p, p, i32, i32, i32, f32, p], i32),
+    "lr_resample_u8": ([p, i32, i32, p, i32, i32, i32, p, p, i32, p], i32),
+    "lr_hd_pack_f32": ([p, i32, i32, i32, i32, i32, i32, p, p, p, i32, p], i32),
 }
 
 

@@ -248,11 +248,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
             sv[c][i] = ok ? sv[c][i] : 0xff800000u;  // -inf
           }
       }
-      float mx = -INFINITY;
+      float mxc[8];  // 8 independent chains instead of one 128-long dependent FMNMX chain
+#pragma unroll
+      for (int c = 0; c < 8; ++c) mxc[c] = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[c][i]));
+        for (int i = 0; i < 32; ++i) mxc[(c * 2 + (i >> 4)) & 7] = fmaxf(mxc[(c * 2 + (i >> 4)) & 7], __uint_as_float(sv[c][i]));
+      float mx = fmaxf(fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3])), fmaxf(fmaxf(mxc[4], mxc[5]), fmaxf(mxc[6], mxc[7])));
       mx *= scale_log2;  // scale > 0, so max commutes with the scaling
       // lazy rescale: move the reference max only when it grew by more than the threshold
       float alpha = 1.f;
@@ -265,15 +268,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       const float msafe = (m_ref == -INFINITY) ? 0.f : m_ref;
       // P = exp2(S*scale - m_ref) (masked entries: exp2(-inf) = 0), row sum in fp32, packed to bf16 in place
       uint32_t pk[4][16];
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};  // independent partial row sums (short dependency chains)
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float e0 = exp2f(fmaf(__uint_as_float(sv[c][2 * i]), scale_log2, -msafe));
           const float e1 = exp2f(fmaf(__uint_as_float(sv[c][2 * i + 1]), scale_log2, -msafe));
-          l_sum += e0 + e1;
+          ls[i & 3] += e0 + e1;
           pk[c][i] = pack_bf16x2(e0, e1);
         }
+      l_sum += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       // P_x buffer and O_x may be touched only after O_x += P_x(j-1) V_(j-1) has retired
       if (j > 0) {
         mbar_wait(&pv_done[x], (j - 1) & 1);
