@@ -128,3 +128,56 @@ if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "diag.json"), "w") as f:
         json.dump(out, f, indent=1)
+
+
+def accuracy():
+    """relative L2 error of kernels against float64 references (is any kernel systematically less accurate?)"""
+    import torch.nn.functional as F
+    torch.manual_seed(1)
+    for name, (nseq, T, heads, hd, causal) in {"clip": (2, 577, 16, 64, False), "dec": (2, 2048, 8, 96, True)}.items():
+        D = heads * hd
+        qkv = (torch.randn(nseq * T, 3 * D, device="cuda") * 1.0).to(bf)
+        f = qkv.double().view(nseq, T, 3, heads, hd)
+        q, k, v = (f[:, :, i].transpose(1, 2) for i in range(3))
+        s = q @ k.transpose(-1, -2) * hd ** -0.5
+        if causal:
+            s = s.masked_fill(~torch.ones(T, T, dtype=torch.bool, device="cuda").tril(), float("-inf"))
+        ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(nseq * T, D)
+        for impl, iname in ((L.ATTN_TCGEN05, "tcgen05"), (L.ATTN_MMA_SYNC, "mma.sync")):
+            o = torch.empty(nseq * T, D, device="cuda", dtype=bf)
+            ops.attention(qkv, qkv[:, D:], qkv[:, 2 * D:], o, 3 * D, D, nseq, T, None, None, heads, hd, causal, hd ** -0.5, impl)
+            torch.cuda.synchronize()
+            err = (o.double() - ref).norm() / ref.norm()
+            bias = ((o.double() - ref).mean() / ref.abs().mean()).item()
+            print(f"attention {name} {iname}: rel L2 err {err.item():.3e}, mean signed err/|ref| {bias:.2e}")
+        # torch SDPA bf16 for comparison
+        o2 = F.scaled_dot_product_attention(q.to(bf), k.to(bf), v.to(bf), is_causal=causal).transpose(1, 2).reshape(nseq * T, D)
+        print(f"attention {name} torch sdpa bf16: rel L2 err {((o2.double() - ref).norm() / ref.norm()).item():.3e}")
+    M, N, K = 4096, 1024, 3200
+    A = torch.randn(M, K, device="cuda").to(bf)
+    W = (torch.randn(N, K, device="cuda") * K ** -0.5).to(bf)
+    acc = A.double() @ W.double().t()
+    a = acc.view(M, N // 256, 2, 128)
+    ref = (a[:, :, 1] * F.silu(a[:, :, 0])).reshape(M, N // 2)
+    for impl, iname in ((L.GEMM_TCGEN05, "tcgen05"), (L.GEMM_SIMT, "simt")):
+        C = torch.empty(M, N // 2, device="cuda", dtype=bf)
+        ops.gemm(A, W, C, M, N, K, L.EPI_SWIGLU, impl=impl)
+        torch.cuda.synchronize()
+        print(f"gemm swiglu {iname}: rel L2 err {((C.double() - ref).norm() / ref.norm()).item():.3e}")
+    gate, up = (a[:, :, 0].float().to(bf), a[:, :, 1].float().to(bf))
+    t = (up * F.silu(gate)).reshape(M, N // 2)
+    print(f"torch bf16 silu*up: rel L2 err {((t.double() - ref).norm() / ref.norm()).item():.3e}")
+    bias = torch.randn(N, device="cuda").to(bf)
+    x = (acc + bias.double())
+    ref = x * torch.sigmoid(1.702 * x)
+    C = torch.empty(M, N, device="cuda", dtype=bf)
+    ops.gemm(A, W, C, M, N, K, L.EPI_BIAS_QUICKGELU, bias)
+    torch.cuda.synchronize()
+    print(f"gemm quickgelu tcgen05: rel L2 err {((C.double() - ref).norm() / ref.norm()).item():.3e}")
+    xb = x.float().to(bf)
+    t = xb * torch.sigmoid(1.702 * xb)
+    print(f"torch bf16 quickgelu: rel L2 err {((t.double() - ref).norm() / ref.norm()).item():.3e}")
+
+
+if __name__ == "__main__" and "acc" in sys.argv[1:]:
+    accuracy()
