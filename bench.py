@@ -81,9 +81,13 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on the host cores, bounded sample
 # --------------------------------------------------------------------------------------------------
+CPU_SAMPLE = ("1 sample (13 crops, N_v=1921, S=2048, fp32, eager attention) through the oracle port at (CLIP,decoder) "
+              "depths (1,1),(3,1),(1,3), best of 2 after a warm-up pass, extrapolated linearly to (23,32) layers")
+
+
 def cpu_sample_seconds(threads: int):
-    """Seconds per sample of the full-depth config-1-shaped workload on `threads` host cores, from three
-    reduced-depth runs of the oracle ((clip,dec) layers = (1,1),(2,1),(1,2)) extrapolated linearly to (23,32)."""
+    """Seconds per sample of the full-depth config-2-shaped workload on `threads` host cores, from reduced-depth
+    runs of the oracle ((clip,dec) layers = (1,1),(3,1),(1,3)) extrapolated linearly to (23,32) layers."""
     import torch
     from llava_reward_b200.config import RewardConfig
     from llava_reward_b200.synth import SynthProvider, synth_batch
@@ -91,19 +95,24 @@ def cpu_sample_seconds(threads: int):
 
     torch.set_num_threads(threads)
     times = {}
-    for depth in ((1, 1), (2, 1), (1, 2)):
+    for depth in ((1, 1), (3, 1), (1, 3)):
         cfg = RewardConfig(clip_layers=depth[0], num_layers=depth[1])
         P = O.Params(SynthProvider(cfg, seed=1234), dtype=torch.float32)
         ids, mask, pix, sizes = synth_batch(cfg, 1, IMAGE_HW, SEQ_LEN, seed=7, tag="c", text_len_range=TEXT_LEN_RANGE)
         for n in SynthProvider(cfg).names():
             P(n)  # materialise weights outside the timed region
+        best = None
         with torch.no_grad():
-            t0 = time.perf_counter()
-            O.custom_forward(P, cfg, ids, mask, pix[:, :13], sizes)  # 13 real crops (padded slots skipped)
-            times[depth] = time.perf_counter() - t0
+            for rep in range(3 if depth == (1, 1) else 2):  # the very first pass also warms the thread pool
+                t0 = time.perf_counter()
+                O.custom_forward(P, cfg, ids, mask, pix[:, :13], sizes)  # 13 real crops (padded slots skipped)
+                dt = time.perf_counter() - t0
+                if not (depth == (1, 1) and rep == 0):
+                    best = dt if best is None else min(best, dt)
+        times[depth] = best
         del P
-    d_clip = max(times[(2, 1)] - times[(1, 1)], 0.0)
-    d_dec = max(times[(1, 2)] - times[(1, 1)], 0.0)
+    d_clip = max(times[(3, 1)] - times[(1, 1)], 0.0) / 2
+    d_dec = max(times[(1, 3)] - times[(1, 1)], 0.0) / 2
     fixed = max(times[(1, 1)] - d_clip - d_dec, 0.0)
     return fixed + 23 * d_clip + 32 * d_dec, times
 
@@ -114,16 +123,12 @@ def run_reference_arm(a):
         return
     threads = os.cpu_count() or 1
     per_sample = []
-    for _ in range(max(1, min(a.warmup, 1))):
-        cpu_sample_seconds(threads)
     for _ in range(max(1, min(a.steps, 3))):
         s, _ = cpu_sample_seconds(threads)
         per_sample.append(s)
     sec = sum(per_sample) / len(per_sample)
     value = 1.0 / (2.0 * sec)
-    sample = ("1 sample (13 crops, N_v=1921, S=2048, fp32, eager attention) through the oracle port at "
-              "(CLIP,decoder) depths (1,1),(2,1),(1,2), extrapolated linearly to (23,32) layers; "
-              f"{len(per_sample)} repetition(s)")
+    sample = CPU_SAMPLE + f"; {len(per_sample)} repetition(s)"
     line = {"impl": "reference", "metric": "text-image pairs scored/sec", "value": value, "unit": "pairs/s",
             "n_gpus": a.gpus, "steps": len(per_sample), "warmup": 1, "ms_per_step": sec * 2 * PAIRS_PER_STEP * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -198,22 +203,52 @@ def main():
 
     gather_buf = torch.empty(world * PAIRS_PER_STEP, dtype=torch.float32, device=dev) if world > 1 else None
 
-    def step(from_host: bool):
+    # end-to-end feeding: two device input slots filled from pinned host memory on a copy stream, so the H2D of
+    # the next forward overlaps the current one (the copies are still inside the timed region)
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [tuple(torch.empty_like(t, device=dev) for t in host["c"][:3]) for _ in range(2)]
+    slot_ready = [torch.cuda.Event() for _ in range(2)]   # H2D into the slot finished
+    slot_free = [torch.cuda.Event() for _ in range(2)]    # the forward that read the slot finished
+    feed = {"n": 0}
+
+    def enqueue_copy(tag):
+        i = feed["n"] % 2
+        feed["n"] += 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(slot_free[i])
+            for d, h in zip(slots[i], host[tag][:3]):
+                d.copy_(h, non_blocking=True)
+            slot_ready[i].record(copy_stream)
+        return i
+
+    for ev in slot_free:
+        ev.record(torch.cuda.current_stream())
+
+    def step(from_host: bool, pending=None):
+        """-> (probabilities, slot index of the prefetched 'c' inputs of the next step or None)"""
         rs = {}
+        cur = torch.cuda.current_stream()
+        nxt = None
         for tag in ("c", "r"):
             if from_host:
-                ids, mask, pix = (t.to(dev, non_blocking=True) for t in host[tag][:3])
+                i = pending if pending is not None else enqueue_copy(tag)
+                pending = enqueue_copy("r" if tag == "c" else "c")   # prefetch the next forward's inputs
+                cur.wait_event(slot_ready[i])
+                ids, mask, pix = slots[i]
                 sizes = host[tag][3]
+                rs[tag], _ = model.custom_forward(ids, mask, pix, sizes)
+                slot_free[i].record(cur)
+                nxt = pending
             else:
                 ids, mask, pix, sizes = resident[tag]
-            rs[tag], _ = model.custom_forward(ids, mask, pix, sizes)
+                rs[tag], _ = model.custom_forward(ids, mask, pix, sizes)
         prob = eng.preference(rs["c"], rs["r"])
         if world > 1:
             dist.all_gather_into_tensor(gather_buf, prob)
             prob = gather_buf
         if from_host:
-            return prob.cpu()
-        return prob
+            return prob.cpu(), nxt
+        return prob, None
 
     def timed(from_host: bool, steps: int):
         if world > 1:
@@ -221,8 +256,9 @@ def main():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        pending = None
         for _ in range(steps):
-            step(from_host)
+            _, pending = step(from_host, pending)
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -248,7 +284,11 @@ def main():
     prof = eng.profile
     eng.profile = None
     clocks = sampler.stop() if sampler else None
-    step(True)  # warm the pinned path
+    step(True)  # warm the pinned path (its prefetched slot is simply overwritten later)
+    torch.cuda.synchronize()
+    feed["n"] = 0
+    for ev in slot_free:
+        ev.record(torch.cuda.current_stream())
     ms_e2e = timed(True, a.steps)
 
     if rank == 0:
@@ -290,8 +330,7 @@ def main():
             sec, times = cpu_sample_seconds(threads)
             line["cpu_baseline"] = {
                 "value": 1.0 / (2.0 * sec), "unit": "pairs/s", "cores": threads, "kind": "port",
-                "sample": "1 sample (13 crops, N_v=1921, S=2048, fp32, eager attention) through the oracle port at "
-                          "(CLIP,decoder) depths (1,1),(2,1),(1,2), extrapolated linearly to (23,32) layers",
+                "sample": CPU_SAMPLE,
                 "seconds_per_sample_extrapolated": sec,
                 "raw_seconds": {f"{k[0]},{k[1]}": v for k, v in times.items()}}
         print(json.dumps(line), flush=True)
