@@ -293,3 +293,64 @@ def test_decision_agreement_many_pairs(tmp_path_factory):
     clear = (p32 - 0.5).abs() > 0.25     # margin well outside the bf16 noise band
     assert ((pe > 0.5) == (p32 > 0.5))[clear].all()
     assert agree_engine >= agree_ref16 - 0.05
+
+
+def test_right_padding_single_sample_and_max_crops(tmp_path_factory):
+    """Edge cases of the batch layout: right-padded mask (EOS is not the last column), B=1, and the 4x4-crop maximum
+    image (17 crop slots all real, N_v=2509), against the oracle in fp32."""
+    fx = load_fixture("slim_gpm")
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    from llava_reward_b200.synth import synth_batch
+    P32 = O.Params(SynthProvider(cfg, seed=fx["seed_w"], device="cuda"), dtype=torch.float32, device="cuda")
+    P16 = O.Params(SynthProvider(cfg, seed=fx["seed_w"], device="cuda"), dtype=torch.bfloat16, device="cuda")
+    # (a) right padding: roll every row so the valid run starts at column 0
+    ids, mask, pix, sizes = synth_batch(cfg, 3, (336, 672), None, seed=31, tag="rp", device="cuda",
+                                        image_hw_list=[(336, 672), (672, 336), (336, 336)])
+    ids_r, mask_r = ids.clone(), mask.clone()
+    for b in range(ids.shape[0]):
+        n_pad = int((mask[b] == 0).sum())
+        ids_r[b] = torch.roll(ids[b], -n_pad)
+        mask_r[b] = torch.roll(mask[b], -n_pad)
+    assert int(mask_r[:, -1].sum()) < ids.shape[0]  # at least one row really is right-padded
+    r_e, _ = model.custom_forward(ids_r, mask_r, pix, sizes)
+    with torch.no_grad():
+        r32 = O.custom_forward(P32, cfg, ids_r, mask_r, pix, sizes)
+        r16 = O.custom_forward(P16, cfg, ids_r, mask_r, pix, sizes)
+    floor = (r16.float() - r32).abs().max().item()
+    err = (r_e.float() - r32).abs().max().item()
+    print(f"right padding: engine-vs-fp32 {err:.4g}, reference bf16-vs-fp32 {floor:.4g}")
+    assert err < REWARD_TOL + 3 * floor
+    # (b) B = 1 with the maximum HD size
+    ids, mask, pix, sizes = synth_batch(cfg, 1, (1344, 1344), None, seed=32, tag="mx", device="cuda")
+    assert int((ids < 0).sum()) == 2509
+    r_e, _ = model.custom_forward(ids, mask, pix, sizes)
+    with torch.no_grad():
+        r32 = O.custom_forward(P32, cfg, ids, mask, pix, sizes)
+        r16 = O.custom_forward(P16, cfg, ids, mask, pix, sizes)
+    floor = (r16.float() - r32).abs().max().item()
+    err = (r_e.float() - r32).abs().max().item()
+    print(f"B=1, 17 crops: engine-vs-fp32 {err:.4g}, reference bf16-vs-fp32 {floor:.4g}")
+    assert err < REWARD_TOL + 3 * floor
+
+
+def test_gpu_preprocessing_feeds_the_engine(tmp_path_factory):
+    """uint8 image -> GPU preprocessing -> custom_forward: same reward as feeding the oracle-preprocessed pixels."""
+    import numpy as np
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from preprocess_util import synth_image
+    from oracle import preprocess_oracle as PO
+    from llava_reward_b200.processing import Phi3VImageProcessorB200
+    from llava_reward_b200.synth import BOS, USER, NL, EOS
+    fx = load_fixture("slim_gpm")
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    img = synth_image("small_200x333", 200, 333)
+    out = Phi3VImageProcessorB200(num_crops=16).preprocess([img], return_tensors="pt")
+    ntok = int(out["num_img_tokens"][0])
+    ids = torch.tensor([[BOS, USER, NL] + [-1] * ntok + [NL, 100, 200, 300, EOS]], device="cuda")
+    mask = torch.ones_like(ids)
+    r_gpu, _ = model.custom_forward(ids, mask, out["pixel_values"], out["image_sizes"])
+    ref_pix, (h, w), ntok2 = PO.preprocess(img)
+    assert ntok2 == ntok and [h, w] == out["image_sizes"][0].tolist()
+    r_ref, _ = model.custom_forward(ids, mask, torch.from_numpy(ref_pix)[None].cuda(), torch.tensor([[h, w]]))
+    assert (r_gpu.float() - r_ref.float()).abs().max().item() < 1e-2
