@@ -41,8 +41,11 @@ extern "C" {
 #define LR_EPI_BIAS_RESIDUAL 5  /* C = bf16(bf16(acc+bias) + R)                    CLIP out_proj / fc2 */
 #define LR_EPI_SWIGLU 6         /* W rows packed [gate128|up128] per 256; C[:,N/2] = up*silu(gate)  Phi3MLP (:566-572) */
 
-#define LR_GEMM_TCGEN05 0 /* tcgen05.mma + TMEM + TMA pipeline (product path) */
+#define LR_GEMM_TCGEN05 0 /* tcgen05.mma + TMEM + TMA pipeline (product path): CTA-pair kernel when N % 256 == 0 and
+                             M > 256, else the single-CTA kernel */
 #define LR_GEMM_SIMT 1    /* plain CUDA-core kernel, used only to cross-check the tcgen05 path in tests */
+#define LR_GEMM_TCGEN05_PAIR 2   /* force the CTA-pair kernel (cta_group::2, 256x256 tile per cluster of 2); N % 256 == 0 */
+#define LR_GEMM_TCGEN05_SINGLE 3 /* force the single-CTA kernel (128 x BN tile, BN = 256 or 128) */
 
 int lr_version(void);
 /* 0 when the current CUDA device is compute capability 10.x, else LR_ERR_UNSUPPORTED / cudaError. */

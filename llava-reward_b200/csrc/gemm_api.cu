@@ -5,6 +5,8 @@ namespace lr {
 
 int gemm_tcgen05(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K, int epi,
                  const void* bias, const void* R, int ldr, cudaStream_t s);
+int gemm_tcgen05_pair(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K, int epi,
+                      const void* bias, const void* R, int ldr, cudaStream_t s);
 
 // Verification-only kernel: 32x32 output tile per CTA, fp32 accumulation on CUDA cores, same epilogue math.
 // It exists so tests can tell a tcgen05/TMA descriptor bug from an epilogue/packing bug; the engine never
@@ -106,6 +108,10 @@ extern "C" int lr_gemm_bf16(const void* A, int lda, const void* W, int ldw, void
     return LR_ERR_ALIGN;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (impl == LR_GEMM_SIMT) return gemm_simt(A, lda, W, ldw, C, ldc, M, N, K, epilogue, bias, R, ldr, s);
-  if (impl != LR_GEMM_TCGEN05) return LR_ERR_BAD_ARG;
+  if (impl == LR_GEMM_TCGEN05_PAIR || (impl == LR_GEMM_TCGEN05 && N % 256 == 0 && M > 256)) {
+    if (N % 256) return LR_ERR_BAD_ARG;
+    return gemm_tcgen05_pair(A, lda, W, ldw, C, ldc, M, N, K, epilogue, bias, R, ldr, s);
+  }
+  if (impl != LR_GEMM_TCGEN05 && impl != LR_GEMM_TCGEN05_SINGLE) return LR_ERR_BAD_ARG;
   return gemm_tcgen05(A, lda, W, ldw, C, ldc, M, N, K, epilogue, bias, R, ldr, s);
 }

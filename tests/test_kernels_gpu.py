@@ -63,11 +63,13 @@ GEMM_SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("impl", [L.GEMM_TCGEN05, L.GEMM_SIMT])
+@pytest.mark.parametrize("impl", [L.GEMM_TCGEN05, L.GEMM_SIMT, L.GEMM_TCGEN05_PAIR, L.GEMM_TCGEN05_SINGLE])
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 def test_gemm_plain(M, N, K, impl):
     if impl == L.GEMM_SIMT and M * N * K > 2e10:
         pytest.skip("SIMT cross-check kernel only on small shapes")
+    if impl == L.GEMM_TCGEN05_PAIR and N % 256:
+        pytest.skip("CTA-pair kernel needs N % 256 == 0")
     A, W = rnd(M, K, seed=1), rnd(N, K, std=K ** -0.5, seed=2)
     C = torch.full((M, N), float("nan"), dtype=bf, device=DEV)
     ops.gemm(A, W, C, M, N, K, L.EPI_NONE, impl=impl)
@@ -75,7 +77,7 @@ def test_gemm_plain(M, N, K, impl):
     check_close(C, gemm_ref(A, W, L.EPI_NONE), f"gemm {M}x{N}x{K} impl={impl}")
 
 
-@pytest.mark.parametrize("impl", [L.GEMM_TCGEN05, L.GEMM_SIMT])
+@pytest.mark.parametrize("impl", [L.GEMM_TCGEN05, L.GEMM_SIMT, L.GEMM_TCGEN05_PAIR, L.GEMM_TCGEN05_SINGLE])
 @pytest.mark.parametrize("epi", [L.EPI_BIAS, L.EPI_BIAS_QUICKGELU, L.EPI_BIAS_GELU, L.EPI_RESIDUAL,
                                  L.EPI_BIAS_RESIDUAL, L.EPI_SWIGLU])
 def test_gemm_epilogues(epi, impl):

@@ -89,8 +89,11 @@ def perf(gemms=True):
         C = torch.empty(M, n_out, device="cuda", dtype=bf)
         bias = torch.zeros(N, device="cuda", dtype=bf)
         R = torch.zeros(M, n_out, device="cuda", dtype=bf) if epi in (L.EPI_RESIDUAL, L.EPI_BIAS_RESIDUAL) else None
-        ms = timeit(lambda: ops.gemm(A, W, C, M, N, K, epi, bias, R))
+        ms = timeit(lambda: ops.gemm(A, W, C, M, N, K, epi, bias, R, impl=L.GEMM_TCGEN05_SINGLE))
         tf = 2.0 * M * N * K / ms / 1e9
+        if N % 256 == 0 and os.environ.get("LR_DIAG_PAIR", "1") == "1":
+            ms2 = timeit(lambda: ops.gemm(A, W, C, M, N, K, epi, bias, R, impl=L.GEMM_TCGEN05_PAIR))
+            print(f"gemm {name:9s} pair kernel: {ms2:.3f} ms {2.0 * M * N * K / ms2 / 1e9:.0f} TF/s", flush=True)
         ms_t = timeit(lambda: torch.matmul(A, W.t()))
         res[name] = {"ms": ms, "tflops": tf, "torch_ms": ms_t, "torch_tflops": 2.0 * M * N * K / ms_t / 1e9}
         print(f"gemm {name:9s} {M}x{N}x{K}: {ms:.3f} ms {tf:.0f} TF/s | torch.matmul {ms_t:.3f} ms "
