@@ -11,7 +11,7 @@ results are all-gathered (NCCL) inside the timed region.
   value : pairs/s with the step's inputs already resident in HBM (CUDA events, max over ranks)
   e2e   : pairs/s through the reference-shaped API with HOST (pinned) inputs: H2D of ids/mask/pixels and the
           D2H of the probabilities are inside the timed region
-  roofline     : dominant kernel = the tcgen05 gate_up GEMM of the decoder, timed live with CUDA events
+  roofline     : dominant kernel = the tcgen05 (CTA-pair) gate_up GEMM of the decoder, timed live with CUDA events
   cpu_baseline : the oracle port (fp32, eager attention, all host cores) on a bounded sample, rank 0 only
 """
 from __future__ import annotations
@@ -315,7 +315,7 @@ def main():
             "config": workload_config(world), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<256,SWIGLU> (decoder gate_up_proj + LoRA-B)",
+            "roofline": {"bound": "tensor", "kernel": "pair::gemm_pair_kernel<256,SWIGLU> (tcgen05 cta_group::2; decoder gate_up_proj + LoRA-B)",
                          "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": (ach / peaks["bf16_sustained"]) if ach else None, "traffic": traffic,
                          "launches_timed": len(durs), "flops_per_launch": flops, "peak_source": peaks["source"]},
