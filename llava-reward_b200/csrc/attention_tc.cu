@@ -12,6 +12,11 @@
 //                row into 128B-swizzled smem -> mbarrier; O is rescaled in TMEM (tcgen05.ld/st) lazily, only when
 //                the row max grew by > 2^8)
 // The softmax warpgroups therefore run back to back; all MMA work hides behind them.
+// Softmax is MUFU-bound on this part (16 ex2/clk/SM, measured with the in-kernel timeline of tools/attn_trace.py;
+// ex2.approx.bf16x2 has the same per-element rate, so it is not used). Everything else is kept off the critical
+// path: the P stores are interleaved with the exponentials, and the row sums come from the tensor core - V carries
+// 16 extra columns of ones, so column HD of O accumulates sum_j P_ij in fp32 from exactly the bf16 values that
+// multiply V (and is rescaled together with O).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -19,9 +24,25 @@
 
 namespace lr {
 
+// Optional in-kernel timeline (tools/attn_trace.py builds a separate .so with -DLR_ATTN_TRACE): clock64 stamps of
+// CTA (0,0,0) at the main pipeline events, [role][event][block] -> global buffer.
+#ifdef LR_ATTN_TRACE
+__device__ long long* g_attn_trace = nullptr;
+#define ATTN_TRACE(role, ev, j)                                                                     \
+  do {                                                                                              \
+    if (g_attn_trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 32)          \
+      g_attn_trace[((role) * 8 + (ev)) * 32 + (j)] = clock64();                                     \
+  } while (0)
+#else
+#define ATTN_TRACE(role, ev, j) \
+  do {                          \
+  } while (0)
+#endif
+
 constexpr int kTcThreads = 384;
 constexpr int kAtomBytes = 128 * 64;      // [128 rows x 32 bf16], 64B swizzle
 constexpr int kPBytes = 128 * 128 * 2;    // P tile: two [128 x 64 bf16] 128B-swizzled atoms
+constexpr long long kStaggerCycles = 1100;
 constexpr float kRescaleThreshold = 8.f;  // log2 units: P stays <= 2^8 between rescales
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
@@ -51,9 +72,10 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 template <int HD>
 struct AttnTcCfg {
   static constexpr int kAtoms = HD / 32;
-  static constexpr int kTileBytes = kAtoms * kAtomBytes;  // one Q / K / V tile
-  static constexpr int kSmemBytes = 2 * kTileBytes /*Q_A,Q_B*/ + 4 * kTileBytes /*K,V x 2 stages*/ + 2 * kPBytes +
-                                    1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kTileBytes = kAtoms * kAtomBytes;         // one Q / K tile, and the TMA-loaded part of a V tile
+  static constexpr int kVTileBytes = (kAtoms + 1) * kAtomBytes;  // V tile + one atom of ones (row sums via the MMA)
+  static constexpr int kSmemBytes = 2 * kTileBytes /*Q_A,Q_B*/ + 2 * kTileBytes /*K*/ + 2 * kVTileBytes /*V*/ +
+                                    2 * kPBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 template <int HD, bool CAUSAL>
@@ -64,12 +86,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
   using Cfg = AttnTcCfg<HD>;
   constexpr int NA = Cfg::kAtoms;
   constexpr int TILE = Cfg::kTileBytes;
+  constexpr int VTILE = Cfg::kVTileBytes;
+  constexpr int HDX = HD + 16;  // O columns incl. the row-sum columns
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                    // [2][TILE]
   uint8_t* sK = sQ + 2 * TILE;           // [2][TILE]
-  uint8_t* sV = sK + 2 * TILE;           // [2][TILE]
-  uint8_t* sP = sV + 2 * TILE;           // [2][kPBytes]
+  uint8_t* sV = sK + 2 * TILE;           // [2][VTILE]
+  uint8_t* sP = sV + 2 * VTILE;          // [2][kPBytes]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
   uint64_t* q_full = bars;               // [1]
   uint64_t* k_full = bars + 1;           // [2]
@@ -108,9 +132,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
+      mbar_init(&k_empty[i], 2);  // one arrival per MMA-issuing thread (tile A, tile B)
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&v_empty[i], 2);
       mbar_init(&s_full[i], 1);
       mbar_init(&s_free[i], 4);
       mbar_init(&p_full[i], 4);
@@ -123,6 +147,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  // the ones atom of both V stages (bf16 1.0 everywhere, so the swizzle is irrelevant)
+  for (int i = threadIdx.x; i < 2 * kAtomBytes / 16; i += kTcThreads) {
+    const int st = i / (kAtomBytes / 16), o16 = i % (kAtomBytes / 16);
+    *reinterpret_cast<uint4*>(sV + st * VTILE + NA * kAtomBytes + o16 * 16) =
+        make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  }
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -130,6 +161,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
   const uint32_t tm_S[2] = {tmem_base, tmem_base + 128};
   const uint32_t tm_O[2] = {tmem_base + 256, tmem_base + 384};
 
+  // register re-allocation between warpgroups: the softmax threads keep a whole 128-column S row in registers
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0 && n > 0) {
@@ -141,27 +175,42 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
           for (int a = 0; a < NA; ++a)
             tma_load_2d(sQ + x * TILE + a * kAtomBytes, &tm_qkv, q_full, q_col0 + head * HD + a * 32,
                         slot_row0 + m0 + x * 128);
-      for (int j = 0; j < n; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        const int row = slot_row0 + start + j * 128;
-        mbar_wait(&k_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[s], TILE);
-        for (int a = 0; a < NA; ++a)
-          tma_load_2d(sK + s * TILE + a * kAtomBytes, &tm_qkv, &k_full[s], k_col0 + head * HD + a * 32, row);
-        mbar_wait(&v_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[s], TILE);
-        for (int a = 0; a < NA; ++a)
-          tma_load_2d(sV + s * TILE + a * kAtomBytes, &tm_qkv, &v_full[s], v_col0 + head * HD + a * 32, row);
+      // K and V rings advance independently (the MMA thread consumes them out of lock-step)
+      int kj = 0, vj = 0;
+      while (kj < n || vj < n) {
+        if (kj < n && mbar_test_wait(&k_empty[kj & 1], ((kj >> 1) & 1) ^ 1)) {
+          const int s = kj & 1;
+          mbar_arrive_expect_tx(&k_full[s], TILE);
+          for (int a = 0; a < NA; ++a)
+            tma_load_2d(sK + s * TILE + a * kAtomBytes, &tm_qkv, &k_full[s], k_col0 + head * HD + a * 32,
+                        slot_row0 + start + kj * 128);
+          ++kj;
+        }
+        if (vj < n && vj < kj && mbar_test_wait(&v_empty[vj & 1], ((vj >> 1) & 1) ^ 1)) {
+          const int s = vj & 1;
+          mbar_arrive_expect_tx(&v_full[s], TILE);
+          for (int a = 0; a < NA; ++a)
+            tma_load_2d(sV + s * VTILE + a * kAtomBytes, &tm_qkv, &v_full[s], v_col0 + head * HD + a * 32,
+                        slot_row0 + start + vj * 128);
+          ++vj;
+        }
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 || warp == 3) {
+    // ------------------------------------------------------------------ MMA issuers: warp 1 -> tile A, warp 3 -> tile B
+    // One thread per tile: a tcgen05.mma costs ~90 cycles of issue latency (measured with tools/attn_trace.py),
+    // more than these 128x128x16 / 128x112x16 MMAs take to execute, so two issuing threads keep the tensor core fed.
+    // Each tile advances as soon as ITS inputs are ready: S_x(j+1) the moment the softmax warps hold S_x(j) in
+    // registers, O_x += P_x(j) V_j the moment P_x(j) is in smem. A K (V) stage goes back to the producer when both
+    // threads have arrived on its `empty` barrier (tcgen05.commit after the last MMA that reads it, or a plain arrive
+    // for blocks a tile does not need).
     if (lane == 0 && n > 0) {
+      const int x = warp == 1 ? 0 : 1;
+      const int nx = nblk[x];
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD) | (1u << 16);  // B (= V) is MN-major
-      auto issue_s = [&](int x, int ks) {  // S_x = Q_x K^T : A = Q (K-major, SW64), B = K stage ks (K-major, SW64)
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, HDX) | (1u << 16);  // B (= [V | 1]) is MN-major
+      auto issue_s = [&](int ks) {  // S_x = Q_x K^T : A = Q (K-major, SW64), B = K stage ks (K-major, SW64)
         const uint32_t qa = smem_u32(sQ + x * TILE), ka = smem_u32(sK + ks * TILE);
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
@@ -170,52 +219,64 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
                        idesc_s, kk != 0);
         }
         umma_commit(&s_full[x]);
+        umma_commit(&k_empty[ks]);
       };
-      auto issue_pv = [&](int x, int vs, bool acc) {  // O_x += P_x V : A = P (K-major, SW128), B = V (MN-major, SW64)
-        const uint32_t pa = smem_u32(sP + x * kPBytes), va = smem_u32(sV + vs * TILE);
+      auto issue_pv = [&](int vs, bool acc) {  // O_x += P_x V : A = P (K-major, SW128), B = V (MN-major, SW64)
+        const uint32_t pa = smem_u32(sP + x * kPBytes), va = smem_u32(sV + vs * VTILE);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           umma_bf16_ss(tm_O[x], umma_desc(pa + (kk >> 2) * (kPBytes / 2) + (kk & 3) * 32, 16, 1024, kLayoutSW128),
                        umma_desc(va + kk * 1024, kAtomBytes, 512, kLayoutSW64), idesc_o, acc || kk != 0);
         }
+        umma_commit(&pv_done[x]);
+        umma_commit(&v_empty[vs]);
       };
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      if (nblk[0] > 0) issue_s(0, 0);
-      if (nblk[1] > 0) issue_s(1, 0);
-      umma_commit(&k_empty[0]);
-      for (int j = 0; j < n; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        const bool more = j + 1 < n;
-        if (more) mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-        bool v_ready = false;
-#pragma unroll
-        for (int x = 0; x < 2; ++x) {
-          if (j < nblk[x]) {
-            if (j + 1 < nblk[x]) {  // next S as soon as the softmax warps hold S_x(j) in registers
-              mbar_wait(&s_free[x], j & 1);
-              tc_fence_after();
-              issue_s(x, (j + 1) & 1);
-            }
-            if (!v_ready) {
-              mbar_wait(&v_full[s], ph);
-              v_ready = true;
-            }
-            mbar_wait(&p_full[x], j & 1);
-            tc_fence_after();
-            issue_pv(x, s, j > 0);
-            umma_commit(&pv_done[x]);
-            if (j + 1 == nblk[x]) umma_commit(&o_final[x]);
+      if (nx > 0) {
+        mbar_wait(q_full, 0);
+        mbar_wait(&k_full[0], 0);
+        if (x == 1 && nblk[0] > 0) {
+          // Start tile B half a softmax period after tile A: both softmax warpgroups share the SM's 16 ex2/clk, and
+          // the exponential phase is about half of an iteration, so in anti-phase each runs its exponentials alone.
+          mbar_wait(&s_free[0], 0);
+          const long long t0 = clock64();
+          while (clock64() - t0 < kStaggerCycles) {
           }
         }
-        umma_commit(&v_empty[s]);
-        if (more) umma_commit(&k_empty[(j + 1) & 1]);
+        tc_fence_after();
+        issue_s(0);
+        int s_next = 1, pv_next = 0;
+        while (pv_next < nx) {
+          if (s_next < nx && mbar_test_wait(&s_free[x], (s_next - 1) & 1) &&
+              mbar_test_wait(&k_full[s_next & 1], (s_next >> 1) & 1)) {
+            tc_fence_after();
+            ATTN_TRACE(0, x * 4 + 0, s_next - 1);
+            issue_s(s_next & 1);
+            ++s_next;
+          }
+          if (mbar_test_wait(&p_full[x], pv_next & 1) && mbar_test_wait(&v_full[pv_next & 1], (pv_next >> 1) & 1)) {
+            tc_fence_after();
+            ATTN_TRACE(0, x * 4 + 1, pv_next);
+            issue_pv(pv_next & 1, pv_next > 0);
+            if (pv_next + 1 == nx) umma_commit(&o_final[x]);
+            ATTN_TRACE(0, x * 4 + 2, pv_next);
+            ++pv_next;
+          }
+        }
+      }
+      for (int j = nx; j < n; ++j) {  // K/V blocks only the other tile reads: arrive in phase order
+        const int st = j & 1;
+        if (j >= 2) {
+          mbar_wait(&k_empty[st], ((j - 2) >> 1) & 1);
+          mbar_wait(&v_empty[st], ((j - 2) >> 1) & 1);
+        }
+        mbar_arrive(&k_empty[st]);
+        mbar_arrive(&v_empty[st]);
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     // ------------------------------------------------------------------ softmax warpgroups
     const int x = (warp - 4) >> 2;   // tile A (warps 4-7) or B (warps 8-11)
     const int q = warp & 3;          // TMEM lane quarter
@@ -223,11 +284,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     const int row_abs = m0 + x * 128 + r;
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     uint8_t* prow = sP + x * kPBytes + r * 128;
-    float m_ref = -INFINITY, l_sum = 0.f;
+    float m_ref = -INFINITY;
     const int nx = nblk[x];
+    const bool tr = (q == 0 && lane == 0);
     for (int j = 0; j < nx; ++j) {
+      if (tr) ATTN_TRACE(1 + x, 0, j);
       mbar_wait(&s_full[x], j & 1);
       tc_fence_after();
+      if (tr) ATTN_TRACE(1 + x, 1, j);
       const int kv0 = start + j * 128;
       const bool need_mask = (kv0 + 128 > kv_end[x]) || (CAUSAL && kv0 + 127 > m0 + x * 128);
       // whole S row -> registers, then give the TMEM buffer back to the MMA warp
@@ -235,6 +299,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld_32x32(tm_S[x] + lane_addr + c * 32, sv[c]);
       tmem_ld_wait();
+      if (tr) ATTN_TRACE(1 + x, 2, j);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[x]);
@@ -263,29 +328,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       if (grow) {
         alpha = exp2f(m_ref - mx);  // 0 when m_ref = -inf
         m_ref = mx;
-        l_sum *= alpha;
       }
       const float msafe = (m_ref == -INFINITY) ? 0.f : m_ref;
-      // P = exp2(S*scale - m_ref) (masked entries: exp2(-inf) = 0), row sum in fp32, packed to bf16 in place
-      uint32_t pk[4][16];
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};  // independent partial row sums (short dependency chains)
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float e0 = exp2f(fmaf(__uint_as_float(sv[c][2 * i]), scale_log2, -msafe));
-          const float e1 = exp2f(fmaf(__uint_as_float(sv[c][2 * i + 1]), scale_log2, -msafe));
-          ls[i & 3] += e0 + e1;
-          pk[c][i] = pack_bf16x2(e0, e1);
-        }
-      l_sum += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      if (tr) ATTN_TRACE(1 + x, 3, j);
       // P_x buffer and O_x may be touched only after O_x += P_x(j-1) V_(j-1) has retired
       if (j > 0) {
         mbar_wait(&pv_done[x], (j - 1) & 1);
         tc_fence_after();
         if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll 1
-          for (int c = 0; c < HD / 32; ++c) {
+          for (int c = 0; c < HD / 32 + 1; ++c) {  // +1: the chunk that holds the row-sum column
             uint32_t ov[32];
             tmem_ld_32x32(tm_O[x] + lane_addr + c * 32, ov);
             tmem_ld_wait();
@@ -296,21 +348,30 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
           tmem_st_wait();
         }
       }
-      // 128 columns = 2 atoms x 8 chunks of 16 B; chunk position XOR (row & 7) = the 128B swizzle
+      if (tr) ATTN_TRACE(1 + x, 4, j);
+      // P = exp2(S*scale - m_ref) (masked entries: exp2(-inf) = 0) -> bf16 -> smem, 32 columns at a time so the
+      // stores issue under the MUFU-bound exponentials. 128 columns = 2 atoms x 8 chunks of 16 B; chunk position
+      // XOR (row & 7) = the 128B swizzle.
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          pk[i] = pack_bf16x2(exp2f(fmaf(__uint_as_float(sv[c][2 * i]), scale_log2, -msafe)),
+                              exp2f(fmaf(__uint_as_float(sv[c][2 * i + 1]), scale_log2, -msafe)));
         uint8_t* base = prow + (c >> 1) * (kPBytes / 2);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int chunk = ((c & 1) * 4 + t) ^ (r & 7);
-          *reinterpret_cast<uint4*>(base + (chunk << 4)) =
-              make_uint4(pk[c][4 * t], pk[c][4 * t + 1], pk[c][4 * t + 2], pk[c][4 * t + 3]);
+          *reinterpret_cast<uint4*>(base + (chunk << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
         }
       }
       fence_proxy_async_smem();  // P (generic-proxy stores) must be visible to the tensor core's async proxy
+      if (tr) ATTN_TRACE(1 + x, 5, j);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[x]);
+      if (tr) ATTN_TRACE(1 + x, 6, j);
     }
     // epilogue: O / l -> bf16 -> global; rows outside the valid run are zero-filled
     const bool row_in_slot = row_abs < rows_per_seq;
@@ -319,7 +380,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     if (nx > 0) {
       mbar_wait(&o_final[x], 0);
       tc_fence_after();
-      const float inv = l_sum > 0.f ? 1.f / l_sum : 0.f;
+      float inv;
+      {
+        uint32_t lv[32];
+        tmem_ld_32x32(tm_O[x] + lane_addr + HD, lv);  // column HD = sum_j P_ij (accumulated by the PV MMAs)
+        tmem_ld_wait();
+        const float l_sum = __uint_as_float(lv[0]);
+        inv = l_sum > 0.f ? 1.f / l_sum : 0.f;
+      }
 #pragma unroll 1
       for (int c = 0; c < HD / 32; ++c) {
         uint32_t ov[32];
@@ -420,3 +488,9 @@ int attention_tc(const void* q, const void* k, const void* v, void* o, int ld_qk
 }
 
 }  // namespace lr
+
+#ifdef LR_ATTN_TRACE
+extern "C" int lr_attn_trace_set(long long* buf) {
+  return static_cast<int>(cudaMemcpyToSymbol(lr::g_attn_trace, &buf, sizeof(buf)));
+}
+#endif
