@@ -40,6 +40,7 @@ extern "C" {
 #define LR_EPI_RESIDUAL 4       /* C = bf16(bf16(acc) + R)                         o_proj / down_proj (:1189,1194) */
 #define LR_EPI_BIAS_RESIDUAL 5  /* C = bf16(bf16(acc+bias) + R)                    CLIP out_proj / fc2 */
 #define LR_EPI_SWIGLU 6         /* W rows packed [gate128|up128] per 256; C[:,N/2] = up*silu(gate)  Phi3MLP (:566-572) */
+#define LR_EPI_ROPE 7           /* su-RoPE on columns [0, rope_cols) (only through lr_gemm_rope_bf16)                  */
 
 #define LR_GEMM_TCGEN05 0 /* tcgen05.mma + TMEM + TMA pipeline (product path): CTA-pair kernel when N % 256 == 0 and
                              M > 256, else the single-CTA kernel */
@@ -58,6 +59,18 @@ int lr_device_check(void);
  * rw_model_general_preference.py:378-380; HF modeling_clip.py CLIPMLP/CLIPAttention). */
 int lr_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
                  int epilogue, const void* bias, const void* R, int ldr, int impl, void* stream);
+
+/* Fused qkv projection + rotary embedding: C = A . W^T with su-RoPE applied in the epilogue to columns
+ * [0, rope_cols) (the q and k thirds). W's q/k rows must be packed with the two halves of every head interleaved
+ * (new row 2i = old i, 2i+1 = old i + head_dim/2), so a rotation pair is two adjacent output columns; q.k^T is
+ * invariant under this common permutation of q and k, v is untouched. Arithmetic per pair (x1, x2) = bf16(acc):
+ * out1 = bf16(bf16(x1*cos) + bf16(-x2*sin)), out2 = bf16(bf16(x2*cos) + bf16(x1*sin)) with bf16 tables
+ * cos/sin[pos, head_dim/2] - the same op-by-op rounding as lr_rope_su_bf16 / apply_rotary_pos_emb
+ * (modeling_phi3_v.py:529-553). N % 256 == 0, rope_cols % 256 == 0, head_dim % 32 == 0.
+ * impl: LR_GEMM_TCGEN05 (CTA-pair kernel) or LR_GEMM_SIMT (cross-check). */
+int lr_gemm_rope_bf16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
+                      const int* position_ids, const void* cos_tab, const void* sin_tab, int rope_cols, int head_dim,
+                      int impl, void* stream);
 
 /* y[i,:] = w * bf16(x[r,:] * rsqrt(mean(x[r,:]^2) + eps)),  r = row_index ? row_index[i] : i.
  * Replaces Phi3RMSNorm.forward (modeling_phi3_v.py:386-391). cols % 8 == 0, cols <= 8192. */

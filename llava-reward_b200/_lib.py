@@ -26,6 +26,7 @@ SIGNATURES = {
     "lr_version": ([], i32),
     "lr_device_check": ([], i32),
     "lr_gemm_bf16": ([p, i32, p, i32, p, i32, i32, i32, i32, i32, p, p, i32, i32, p], i32),
+    "lr_gemm_rope_bf16": ([p, i32, p, i32, p, i32, i32, i32, i32, p, p, p, i32, i32, i32, p], i32),
     "lr_rmsnorm_bf16": ([p, i32, p, p, p, i32, i32, i32, f32, p], i32),
     "lr_layernorm_bf16": ([p, i32, p, p, p, i32, i32, i32, f32, p], i32),
     "lr_clip_im2col": ([p, p, p, i32, p], i32),

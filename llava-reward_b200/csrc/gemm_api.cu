@@ -8,13 +8,17 @@ int gemm_tcgen05(const void* A, int lda, const void* W, int ldw, void* C, int ld
 int gemm_tcgen05_pair(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K, int epi,
                       const void* bias, const void* R, int ldr, cudaStream_t s);
 
+int gemm_rope_pair(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K, const int* pos,
+                   const void* cos_tab, const void* sin_tab, int rope_cols, int head_dim, cudaStream_t s);
+
 // Verification-only kernel: 32x32 output tile per CTA, fp32 accumulation on CUDA cores, same epilogue math.
 // It exists so tests can tell a tcgen05/TMA descriptor bug from an epilogue/packing bug; the engine never
 // selects it on its own.
 template <int EPI>
 __global__ void __launch_bounds__(1024)
 gemm_simt_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__ W, int ldw, bf16* __restrict__ C,
-                 int ldc, int M, int N, int K, const bf16* __restrict__ bias, const bf16* __restrict__ R, int ldr) {
+                 int ldc, int M, int N, int K, const bf16* __restrict__ bias, const bf16* __restrict__ R, int ldr,
+                 const int* __restrict__ pos = nullptr, int rope_hd = 0) {
   __shared__ float As[32][33], Ws[32][33], Us[32][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int m = blockIdx.y * 32 + ty;   // output row of this thread
@@ -35,6 +39,19 @@ gemm_simt_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__ W
     }
     __syncthreads();
   }
+  if (EPI == LR_EPI_ROPE) {  // bias = cos table, R = sin table, ldr = rotated columns, pos/rope_hd extra
+    const float xr = bf16_round(acc);
+    const float other = __shfl_xor_sync(0xffffffffu, xr, 1);  // the rotation partner is the adjacent column
+    if (m >= M) return;
+    float out = xr;
+    if (j < ldr) {
+      const int half = rope_hd >> 1, i = (j % rope_hd) >> 1;
+      const float cs = __bfloat162float(bias[size_t(pos[m]) * half + i]), sn = __bfloat162float(R[size_t(pos[m]) * half + i]);
+      out = (j & 1) ? bf16_round(xr * cs) + bf16_round(other * sn) : bf16_round(xr * cs) + bf16_round(-other * sn);
+    }
+    C[size_t(m) * ldc + j] = __float2bfloat16_rn(out);
+    return;
+  }
   if (m >= M) return;
   float out;
   if (EPI == LR_EPI_SWIGLU) {
@@ -49,13 +66,14 @@ gemm_simt_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__ W
 
 template <int EPI>
 static int launch_simt(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
-                       const void* bias, const void* R, int ldr, cudaStream_t s) {
+                       const void* bias, const void* R, int ldr, cudaStream_t s, const int* pos = nullptr,
+                       int rope_hd = 0) {
   const int n_out = EPI == LR_EPI_SWIGLU ? N / 2 : N;
   dim3 grid(n_out / 32, (M + 31) / 32), block(32, 32);
   gemm_simt_kernel<EPI><<<grid, block, 0, s>>>(reinterpret_cast<const bf16*>(A), lda, reinterpret_cast<const bf16*>(W),
                                                ldw, reinterpret_cast<bf16*>(C), ldc, M, N, K,
                                                reinterpret_cast<const bf16*>(bias), reinterpret_cast<const bf16*>(R),
-                                               ldr);
+                                               ldr, pos, rope_hd);
   return lr_launch_status();
 }
 
@@ -94,10 +112,25 @@ extern "C" int lr_device_check(void) {
   return major == 10 ? LR_OK : LR_ERR_UNSUPPORTED;
 }
 
+extern "C" int lr_gemm_rope_bf16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N,
+                                 int K, const int* position_ids, const void* cos_tab, const void* sin_tab,
+                                 int rope_cols, int head_dim, int impl, void* stream) {
+  LR_CHECK_ARG(A && W && C && position_ids && cos_tab && sin_tab && M > 0 && N > 0 && K > 0 && K % 64 == 0);
+  LR_CHECK_ARG(N % 256 == 0 && rope_cols % 256 == 0 && rope_cols >= 0 && rope_cols <= N && head_dim > 0 &&
+               head_dim % 32 == 0 && lda >= K && ldw >= K && ldc >= N);
+  auto mis = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; };
+  if (mis(A) || mis(W) || mis(C) || mis(cos_tab) || mis(sin_tab) || (lda % 8) || (ldw % 8) || (ldc % 8)) return LR_ERR_ALIGN;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (impl == LR_GEMM_SIMT)
+    return launch_simt<LR_EPI_ROPE>(A, lda, W, ldw, C, ldc, M, N, K, cos_tab, sin_tab, rope_cols, s, position_ids, head_dim);
+  if (impl != LR_GEMM_TCGEN05 && impl != LR_GEMM_TCGEN05_PAIR) return LR_ERR_BAD_ARG;
+  return gemm_rope_pair(A, lda, W, ldw, C, ldc, M, N, K, position_ids, cos_tab, sin_tab, rope_cols, head_dim, s);
+}
+
 extern "C" int lr_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
                             int epilogue, const void* bias, const void* R, int ldr, int impl, void* stream) {
   LR_CHECK_ARG(A && W && C && M > 0 && N > 0 && K > 0 && K % 64 == 0 && N % 128 == 0);
-  LR_CHECK_ARG(epilogue >= LR_EPI_NONE && epilogue <= LR_EPI_SWIGLU);
+  LR_CHECK_ARG(epilogue >= LR_EPI_NONE && epilogue <= LR_EPI_SWIGLU);  // LR_EPI_ROPE: lr_gemm_rope_bf16 only
   if (epi_has_bias(epilogue)) LR_CHECK_ARG(bias != nullptr);
   if (epi_has_res(epilogue)) LR_CHECK_ARG(R != nullptr && ldr >= N);
   if (epilogue == LR_EPI_SWIGLU) LR_CHECK_ARG(N % 256 == 0);

@@ -104,7 +104,9 @@ template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const __grid_constant__ CUtensorMap tma_c, int M, int N, int K,
-                    const bf16* __restrict__ bias, const bf16* __restrict__ R, int ldr, int group_m) {
+                    const bf16* __restrict__ bias, const bf16* __restrict__ R, int ldr, int group_m,
+                    const int* __restrict__ pos, int rope_hd) {
+  // LR_EPI_ROPE reuses the generic slots: bias = cos table, R = sin table, ldr = number of rotated columns
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -247,6 +249,30 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = epi_swiglu(__uint_as_float(acc[j]), __uint_as_float(up[j]));
+          } else if constexpr (EPI == LR_EPI_ROPE) {
+            tmem_ld_wait();
+            const int cg = col_g + hh * 32;
+            if (cg < ldr) {
+              const int half = rope_hd >> 1;
+              const int p = row_ok ? pos[row] : 0;
+              const int i0 = (cg % rope_hd) >> 1;  // 16 consecutive rotation pairs start here (cg % 32 == 0)
+              float cs[16], sn[16];
+              const uint4* cp = reinterpret_cast<const uint4*>(bias + size_t(p) * half + i0);
+              const uint4* sp = reinterpret_cast<const uint4*>(R + size_t(p) * half + i0);
+              unpack8_bf16(__ldg(cp), cs);
+              unpack8_bf16(__ldg(cp + 1), cs + 8);
+              unpack8_bf16(__ldg(sp), sn);
+              unpack8_bf16(__ldg(sp + 1), sn + 8);
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                const float x1 = bf16_round(__uint_as_float(acc[2 * k])), x2 = bf16_round(__uint_as_float(acc[2 * k + 1]));
+                v[2 * k] = bf16_round(x1 * cs[k]) + bf16_round(-x2 * sn[k]);
+                v[2 * k + 1] = bf16_round(x2 * cs[k]) + bf16_round(x1 * sn[k]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+            }
           } else {
             float bv[32], rv[32];
             if constexpr (epi_has_bias(EPI)) {
@@ -354,7 +380,8 @@ static int sm_count() {
 
 template <int BN, int EPI>
 static int launch_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
-                       const void* bias, const void* R, int ldr, cudaStream_t stream) {
+                       const void* bias, const void* R, int ldr, cudaStream_t stream, const int* pos = nullptr,
+                       int rope_hd = 0) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap ta, tb, tc;
   int st = make_tmap(&ta, A, M, K, lda, kBM);
@@ -378,7 +405,7 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, void* C, 
   int group_m = int((32ll << 20) / (int64_t(2 * kBM) * K * 2));
   group_m = group_m < 4 ? 4 : (group_m > 32 ? 32 : group_m);
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, M, N, K, reinterpret_cast<const bf16*>(bias),
-                                                        reinterpret_cast<const bf16*>(R), ldr, group_m);
+                                                        reinterpret_cast<const bf16*>(R), ldr, group_m, pos, rope_hd);
   return lr_launch_status();
 }
 
@@ -399,6 +426,11 @@ static int dispatch_epi(int epi, const void* A, int lda, const void* W, int ldw,
 }
 
 }  // namespace pair
+
+int gemm_rope_pair(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K, const int* pos,
+                   const void* cos_tab, const void* sin_tab, int rope_cols, int head_dim, cudaStream_t s) {
+  return pair::launch_gemm<256, LR_EPI_ROPE>(A, lda, W, ldw, C, ldc, M, N, K, cos_tab, sin_tab, rope_cols, s, pos, head_dim);
+}
 
 int gemm_tcgen05_pair(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K, int epi,
                       const void* bias, const void* R, int ldr, cudaStream_t s) {

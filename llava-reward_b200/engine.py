@@ -179,8 +179,10 @@ class RewardEngine:
             ops.rmsnorm(hid, lw["in_ln"], xn, M, H, cfg.rms_eps)
             if r:
                 self._gemm(xn, lw["qkv_a"], xn[:, H:], M, r, H)
-            self._gemm(xn, lw["qkv_w"], dqkv, M, 3 * H, H + r)
-            ops.rope_su(dqkv, pos, cos_tab, sin_tab, M, nh, hd)
+            if self.gemm_impl == L.GEMM_SIMT:
+                ops.gemm_rope(xn, lw["qkv_w"], dqkv, M, 3 * H, H + r, pos, cos_tab, sin_tab, 2 * H, hd, L.GEMM_SIMT)
+            else:  # qkv projection with su-RoPE in the epilogue (q/k rows are head-interleaved, see weights.py)
+                ops.gemm_rope(xn, lw["qkv_w"], dqkv, M, 3 * H, H + r, pos, cos_tab, sin_tab, 2 * H, hd)
             ops.attention(dqkv, dqkv[:, H:], dqkv[:, 2 * H:], dao, 3 * H, H + r, B, S, seq_start, seq_len, nh, hd,
                           True, att_scale, self.attn_impl)
             if r:

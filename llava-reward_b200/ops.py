@@ -31,6 +31,13 @@ def gemm(A: torch.Tensor, W: torch.Tensor, C: torch.Tensor, M: int, N: int, K: i
            M, N, K, epilogue, _ptr(bias), _ptr(R), (ldr or (R.stride(0) if R is not None else 0)), impl, _stream())
 
 
+def gemm_rope(A, W, C, M, N, K, position_ids, cos_tab, sin_tab, rope_cols, head_dim, impl: int = L.GEMM_TCGEN05):
+    """C = A W^T with su-RoPE fused on columns [0, rope_cols) (W's q/k rows head-interleaved, see weights.py)."""
+    _need_cuda(A, W, C, position_ids, cos_tab, sin_tab)
+    L.call("lr_gemm_rope_bf16", _ptr(A), A.stride(0), _ptr(W), W.stride(0), _ptr(C), C.stride(0), M, N, K,
+           _ptr(position_ids), _ptr(cos_tab), _ptr(sin_tab), rope_cols, head_dim, impl, _stream())
+
+
 def rmsnorm(x, w, y, rows, cols, eps, row_index=None):
     _need_cuda(x, w, y, row_index)
     L.call("lr_rmsnorm_bf16", _ptr(x), x.stride(0), _ptr(row_index), _ptr(w), _ptr(y), y.stride(0), rows, cols, eps,

@@ -118,7 +118,7 @@ class Phi3VImageProcessorB200:
                torch.cuda.current_stream().cuda_stream)
         return dst
 
-    def preprocess(self, images, image_mean=None, image_std=None, do_convert_rgb=None, return_tensors=None):
+    def preprocess(self, images, image_mean=None, image_std=None, do_convert_rgb=None, return_tensors=None, out=None):
         if self.device.type != "cuda":
             raise RuntimeError("Phi3VImageProcessorB200 runs on CUDA only (no CPU fallback)")
         import ctypes
@@ -127,14 +127,19 @@ class Phi3VImageProcessorB200:
         mean_c, std_c = (ctypes.c_float * 3)(*mean), (ctypes.c_float * 3)(*std)
         images = list(images) if isinstance(images, (list, tuple)) else [images]
         n_slots = self.num_crops + 1
-        out = torch.empty(len(images), n_slots, 3, 336, 336, dtype=torch.float32, device=self.device)
+        out = out if out is not None else torch.empty(len(images), n_slots, 3, 336, 336, dtype=torch.float32,
+                                                      device=self.device)
         shapes, ntoks = [], []
         with torch.cuda.device(self.device):
             for i, image in enumerate(images):
-                arr = _to_hwc_u8(image)
-                H0, W0 = arr.shape[:2]
+                if torch.is_tensor(image):  # uint8 HWC tensor, already on the device or in (pinned) host memory
+                    if image.dtype != torch.uint8 or image.dim() != 3 or image.shape[2] != 3:
+                        raise ValueError("image tensors must be uint8 HxWx3")
+                    x = image.to(self.device, non_blocking=True).contiguous()
+                else:
+                    x = torch.from_numpy(_to_hwc_u8(image)).to(self.device, non_blocking=True)
+                H0, W0 = int(x.shape[0]), int(x.shape[1])
                 trans, new_w, new_h, tar = _hd_geometry(W0, H0, self.num_crops)
-                x = torch.from_numpy(arr).to(self.device, non_blocking=True)
                 # Pillow resizes the (possibly transposed) image horizontally first, then vertically; in the
                 # original orientation a transposed image is therefore resampled along axis 0 first.
                 if trans:

@@ -9,6 +9,9 @@ Output: bf16 CUDA tensors
   * LoRA folded by K-extension: W_ext = [W | (alpha/r) B]  ([out, in + r]); lora_A kept as its own [r, in] GEMM
   * gate_up_proj rows interleaved in blocks of 128 ([gate_b | up_b]) so silu(gate)*up is a GEMM epilogue
   * W_k and W_v stacked into one [2H, H] weight
+  * qkv_proj rows of the q and k thirds re-ordered inside every head so that the two halves are interleaved
+    (new row 2i = old i, 2i+1 = old i + head_dim/2): a RoPE rotation pair becomes two adjacent output columns and
+    the rotation runs in the GEMM epilogue (lr_gemm_rope_bf16). q.k^T is invariant under this common permutation.
 """
 from __future__ import annotations
 
@@ -88,9 +91,14 @@ def pack_weights(cfg: RewardConfig, get: Callable[[str], torch.Tensor], device="
         B = (get(name + ".lora_B.weight").to(device=device, dtype=torch.float32) * cfg.lora_scale).to(bf)
         return torch.cat([W, B], dim=1).contiguous(), A
 
+    hd, nh = cfg.head_dim, cfg.num_heads
+    inter = torch.stack([torch.arange(hd // 2), torch.arange(hd // 2) + hd // 2], dim=1).reshape(-1)  # 0,48,1,49,..
+    qk_perm = (torch.arange(2 * nh)[:, None] * hd + inter[None, :]).reshape(-1)
+    qkv_perm = torch.cat([qk_perm, torch.arange(2 * H, 3 * H)]).to(device)
     for i in range(cfg.num_layers):
         p = f"model.layers.{i}."
         qkv_w, qkv_a = ext(p + "self_attn.qkv_proj")
+        qkv_w = qkv_w[qkv_perm].contiguous()
         o_w, o_a = ext(p + "self_attn.o_proj")
         gu_w, gu_a = ext(p + "mlp.gate_up_proj")
         gu_w = gu_w[perm].contiguous()

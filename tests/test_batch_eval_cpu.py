@@ -1,0 +1,38 @@
+"""Host-side batch-eval helpers vs the reference's own `zero_pad_sequences` semantics (left padding, pad id / 0) and
+sklearn metrics (what eval/batch_inference_rm_phi.py:142-152 prints)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from llava_reward_b200.batch_eval import binary_metrics, collate_samples, zero_pad_sequences
+
+
+def test_left_padding_matches_reference_semantics():
+    seqs = [torch.arange(1, 6)[None], torch.arange(1, 3)[None], torch.arange(1, 9)[None]]
+    out = zero_pad_sequences(seqs, value=32000)
+    assert out.shape == (3, 1, 8)
+    assert out[1, 0].tolist() == [32000] * 6 + [1, 2] and out[2, 0].tolist() == list(range(1, 9))
+    right = zero_pad_sequences(seqs, side="right")
+    assert right[1, 0].tolist() == [1, 2] + [0] * 6
+
+
+def test_collate_samples_layout():
+    items = []
+    for n in (4, 7):
+        items.append({"input_ids": torch.arange(n)[None], "attention_mask": torch.ones(1, n, dtype=torch.long),
+                      "pixel_values": torch.zeros(1, 17, 3, 4, 4), "image_sizes": torch.tensor([[336, 672]])})
+    b = collate_samples(items, pad_token_id=9)
+    assert b["input_ids"].shape == (2, 7) and b["attention_mask"].shape == (2, 7)
+    assert b["input_ids"][0].tolist() == [9, 9, 9, 0, 1, 2, 3] and b["attention_mask"][0].tolist() == [0, 0, 0, 1, 1, 1, 1]
+    assert b["pixel_values"].shape == (2, 17, 3, 4, 4) and b["image_sizes"].tolist() == [[336, 672], [336, 672]]
+
+
+def test_binary_metrics_match_sklearn():
+    from sklearn.metrics import f1_score, recall_score
+    rng = np.random.default_rng(0)
+    label, pred = rng.integers(0, 2, 200), rng.integers(0, 2, 200)
+    m = binary_metrics(pred, label)
+    assert abs(m["f1"] - f1_score(label, pred, average="binary")) < 1e-12
+    assert abs(m["recall"] - recall_score(label, pred)) < 1e-12
+    assert abs(m["accuracy"] - (pred == label).mean()) < 1e-12

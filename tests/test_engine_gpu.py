@@ -354,3 +354,33 @@ def test_gpu_preprocessing_feeds_the_engine(tmp_path_factory):
     assert ntok2 == ntok and [h, w] == out["image_sizes"][0].tolist()
     r_ref, _ = model.custom_forward(ids, mask, torch.from_numpy(ref_pix)[None].cuda(), torch.tensor([[h, w]]))
     assert (r_gpu.float() - r_ref.float()).abs().max().item() < 1e-2
+
+
+def test_batch_eval_loops(tmp_path_factory):
+    """Pairwise and single-image eval loops (reference eval/batch_inference_rm_phi.py:70-152) over ragged samples:
+    collated left-padded batches give the same rewards as scoring each sample alone (BT model: batch-invariant)."""
+    from llava_reward_b200.batch_eval import collate_samples, score_pairs, score_single
+    from llava_reward_b200.synth import synth_batch, PAD
+    fx = load_fixture("slim_bt")
+    args, model, cfg = build_model(fx, tmp_path_factory)
+
+    def samples(tag, n):
+        out = []
+        for i in range(n):
+            ids, mask, pix, sizes = synth_batch(cfg, 1, (336, 336 * (1 + i % 2)), None, seed=50 + i, tag=f"{tag}{i}",
+                                                device="cuda", text_len_range=(5, 40))
+            out.append({"input_ids": ids, "attention_mask": mask, "pixel_values": pix, "image_sizes": sizes})
+        return out
+
+    ch, rj = samples("c", 4), samples("r", 4)
+    batches = [(collate_samples(ch[i:i + 2], PAD), collate_samples(rj[i:i + 2], PAD)) for i in (0, 2)]
+    res = score_pairs(model, args, batches)
+    assert res["probs"].shape == (4,) and 0.0 <= res["proportion"] <= 1.0
+    alone_c = [model.custom_forward(**s)[0].float().item() for s in ch]
+    assert max(abs(a - b) for a, b in zip(alone_c, res["chosen_rewards"])) < REWARD_TOL
+    single = score_single(model, args, [(collate_samples(ch, PAD), torch.tensor([1, 0, 1, 0]))], cls_based=True)
+    assert len(single["rewards"]) == 4 and 0.0 <= single["accuracy"] <= 1.0
+    gfx = load_fixture("slim_gpm")
+    gargs, gmodel, _ = build_model(gfx, tmp_path_factory)
+    with pytest.raises(ValueError):
+        score_single(gmodel, gargs, [])

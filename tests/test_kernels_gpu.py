@@ -109,6 +109,32 @@ def test_gemm_strided_lora_extension():
     check_close(y, ref, "lora ext", atol=2e-2)
 
 
+@pytest.mark.parametrize("impl", [L.GEMM_TCGEN05, L.GEMM_SIMT])
+def test_gemm_rope_fused_equals_gemm_then_rope(impl):
+    """qkv projection with RoPE in the epilogue (head-interleaved q/k rows) == plain GEMM followed by lr_rope_su_bf16,
+    bit for bit after undoing the interleave (same accumulations, same op-by-op bf16 rounding)."""
+    M, heads, hd, K = 700, 8, 96, 3200
+    H = heads * hd
+    N = 3 * H  # 2304 = 9 * 256
+    x = rnd(M, K, seed=21)
+    W = rnd(N, K, std=K ** -0.5, seed=22)
+    pos = torch.randint(0, 2048, (M,), device=DEV, dtype=torch.int32)
+    ang = torch.rand(2048, hd // 2, device=DEV) * 6.0
+    cos, sin = (ang.cos() * 1.19).to(bf).contiguous(), (ang.sin() * 1.19).to(bf).contiguous()
+    ref = torch.empty(M, N, dtype=bf, device=DEV)
+    ops.gemm(x, W, ref, M, N, K, impl=L.GEMM_TCGEN05_PAIR if impl == L.GEMM_TCGEN05 else impl)
+    ops.rope_su(ref, pos, cos, sin, M, heads, hd)
+    inter = torch.stack([torch.arange(hd // 2), torch.arange(hd // 2) + hd // 2], dim=1).reshape(-1)
+    qk_perm = (torch.arange(2 * heads)[:, None] * hd + inter[None, :]).reshape(-1)
+    perm = torch.cat([qk_perm, torch.arange(2 * H, 3 * H)]).to(DEV)
+    out = torch.full((M, N), float("nan"), dtype=bf, device=DEV)
+    ops.gemm_rope(x, W[perm].contiguous(), out, M, N, K, pos, cos, sin, 2 * H, hd, impl)
+    torch.cuda.synchronize()
+    unperm = torch.empty_like(out)
+    unperm[:, perm] = out
+    assert torch.equal(unperm, ref)
+
+
 def test_gemm_inplace_residual():
     M, N, K = 2048, 1024, 4096
     A, W, b = rnd(M, K, seed=11), rnd(N, K, std=K ** -0.5, seed=12), rnd(N, seed=13)
