@@ -232,11 +232,9 @@ static int launch_attn(const void* q, const void* k, const void* v, void* o, int
                        cudaStream_t stream) {
   constexpr int smem = (kAttBM + 4 * kAttBN) * (HD + 8) * 2;
   auto kern = attn_fwd_kernel<HD, CAUSAL>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  {  // per-device attribute; setting it on every launch keeps multi-device processes correct
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return static_cast<int>(e);
-    attr_done = true;
   }
   dim3 grid((rows_per_seq + kAttBM - 1) / kAttBM, n_heads, n_seq);
   kern<<<grid, kAttThreads, smem, stream>>>(reinterpret_cast<const bf16*>(q), reinterpret_cast<const bf16*>(k),

@@ -457,11 +457,9 @@ static int launch_attn_tc(const void* base, int total_rows, int ld_qkv, int q_co
          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return LR_ERR_BAD_ARG;
   auto kern = attn_tc_kernel<HD, CAUSAL>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  {  // per-device attribute; setting it on every launch keeps multi-device processes correct
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
-    attr_done = true;
   }
   dim3 grid((rows_per_seq + 255) / 256, n_heads, n_seq);
   kern<<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(tm, reinterpret_cast<bf16*>(o), ld_o, rows_per_seq, seq_start,

@@ -292,13 +292,12 @@ static int make_tmap(CUtensorMap* map, const void* ptr, int rows, int cols, int 
 }
 
 static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cached[dev] == 0) cudaDeviceGetAttribute(&cached[dev], cudaDevAttrMultiProcessorCount, dev);
+  return cached[dev];
 }
 
 template <int BN, int EPI>
@@ -313,11 +312,9 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, void* C, 
   st = make_tmap(&tc, C, M, EPI == LR_EPI_SWIGLU ? N / 2 : N, ldc, 32);
   if (st != LR_OK) return st;
   auto kern = gemm_tcgen05_kernel<BN, EPI>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  {  // per-device attribute; setting it on every launch keeps multi-device processes correct
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
-    attr_done = true;
   }
   const int num_tiles = ((M + kBM - 1) / kBM) * (N / BN);
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();

@@ -27,7 +27,7 @@ class RewardEngine:
         self.attn_impl = attn_impl
         self._bufs: Dict[Tuple[str, Tuple[int, ...], torch.dtype], torch.Tensor] = {}
         self._rope: Dict[Tuple[int, bool], Tuple[torch.Tensor, torch.Tensor]] = {}
-        self.launches = 0        # kernels launched by the last forward (for bench `gpu_launches`)
+        self.launches = 0        # C-ABI calls issued by the last forward (= kernel launches, see _lib.launch_count)
         self.taps: Optional[dict] = None  # set to {} to capture intermediates (tests)
         self.profile: Optional[dict] = None  # {"gate_up": []} -> CUDA-event pairs around that GEMM (bench roofline)
 
@@ -61,7 +61,6 @@ class RewardEngine:
 
     def _gemm(self, A, W, C, M, N, K, epi=L.EPI_NONE, bias=None, R=None):
         ops.gemm(A, W, C, M, N, K, epi, bias, R, impl=self.gemm_impl)
-        self.launches += 1
 
     def _tap(self, name, t):
         if self.taps is not None:
@@ -73,7 +72,7 @@ class RewardEngine:
                 image_sizes) -> torch.Tensor:
         cfg, w, dev = self.cfg, self.w, self.device
         bf = torch.bfloat16
-        self.launches = 0
+        launches0 = L.launch_count()
         B, S = input_ids.shape
         H, I, r = cfg.hidden_size, cfg.intermediate_size, (cfg.lora_rank if cfg.use_lora else 0)
         ids = input_ids.to(dev, torch.int64).contiguous()
@@ -91,7 +90,6 @@ class RewardEngine:
         seq_start, seq_len, eos_row, n_img, flags = meta[:B], meta[B:2 * B], meta[2 * B:3 * B], meta[3 * B:4 * B], meta[4 * B:]
         flags.zero_()
         ops.token_plan(ids, mask, B, S, pos, img_ord, seq_start, seq_len, eos_row, n_img, flags)
-        self.launches += 1
         meta_h = meta.cpu().numpy()
         sizes_h = image_sizes.cpu().numpy() if torch.is_tensor(image_sizes) else np.asarray(image_sizes)
         sizes_h = sizes_h.reshape(B, 2).astype(np.int64)
@@ -131,7 +129,6 @@ class RewardEngine:
         self._gemm(a0, w.clip["patch_w"], patch, n_crops * (T - 1), D, 640)
         x = self.buf("clip_x", (Mv, D))
         ops.clip_embed_ln(patch, w.clip["cls"], w.clip["pos"], w.clip["pre_w"], w.clip["pre_b"], x, n_crops, cfg.clip_eps)
-        self.launches += 2
         self._tap("clip_embed", x)
         hn = self.buf("clip_hn", (Mv, D))
         qkv = self.buf("clip_qkv", (Mv, 3 * D))
@@ -147,7 +144,6 @@ class RewardEngine:
             ops.layernorm(x, lw["ln2_w"], lw["ln2_b"], hn, Mv, D, cfg.clip_eps)
             self._gemm(hn, lw["fc1_w"], ff, Mv, DI, D, L.EPI_BIAS_QUICKGELU, lw["fc1_b"])
             self._gemm(ff, lw["fc2_w"], x, Mv, D, DI, L.EPI_BIAS_RESIDUAL, lw["fc2_b"], x)
-            self.launches += 3
             if li == 0:
                 self._tap("clip_layer0", x)
         self._tap("clip_out", x)
@@ -164,7 +160,6 @@ class RewardEngine:
         # 4. embeddings
         hid = self.buf("hidden", (M, H))
         ops.embed_scatter(ids, img_ord, plan, w.embed, img, hid, B, S, H, cfg.vocab_size)
-        self.launches += 2
         self._tap("inputs_embeds", hid)
 
         # 5. decoder
@@ -201,7 +196,6 @@ class RewardEngine:
             if r:
                 self._gemm(gg, lw["dn_a"], gg[:, I:], M, r, I)
             self._gemm(gg, lw["dn_w"], hid, M, H, I + r, L.EPI_RESIDUAL, None, hid)
-            self.launches += 4
             if self.taps is not None:
                 self._tap(f"hidden_{li}", hid)
 
@@ -219,10 +213,9 @@ class RewardEngine:
             scores = self.buf("ca_scores", (B, max_nv), torch.float32)
             ops.skipca_scores(q, kv, plan, scores, B, H, max_nv)
             ops.skipca_head(scores, kv, plan, xe, w.head["ca_ln"], w.head["vh"], reward, B, H, max_nv, vhd, cfg.rms_eps)
-            self.launches += 3
         else:
             ops.skipca_head(None, None, None, xe, None, w.head["vh"], reward, B, H, 0, vhd, cfg.rms_eps)
-            self.launches += 2
+        self.launches = L.launch_count() - launches0
         return reward
 
     @torch.no_grad()
