@@ -8,11 +8,10 @@ python - <<'PY'
 import json
 try:
     d=json.loads(open('gpurun_out/bench.log').read().strip().splitlines()[-1])
-    print({k:d[k] for k in ('value','ms_per_step','gpu_launches','clocks')}, 'e2e', d['e2e']['value'], 'gate_up', d['roofline']['achieved'], d['step_roofline']['frac_of_sustained'], d.get('cpu_baseline',{}).get('value'))
+    print({k:d[k] for k in ('value','ms_per_step','gpu_launches','clocks')}, 'e2e', d['e2e']['value'], 'u8', d['e2e_uint8']['value'], 'gate_up', d['roofline']['achieved'], d['step_roofline']['frac_of_sustained'], d.get('cpu_baseline',{}).get('value'))
 except Exception as e: print("parse fail", e)
 PY
 tail -3 gpurun_out/bench.err
-timeout 200 python tools/attn_trace.py > gpurun_out/attn_trace.txt 2>&1
 K='regex:^(gemm_|attn_|rmsnorm|layernorm|clip_|token_plan|rope_su|hd_gather|embed_scatter|skipca|preference)'
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -s 1119 -c 1119 --csv --log-file gpurun_out/launches.csv python bench.py --profile-run > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches exit $?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_tc -c 2 -o gpurun_out/prof_attn_tc3 -f python tools/attn_only.py > gpurun_out/ncu_attn_tc.log 2>&1; echo "ncu attn exit $?"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -s 1055 -c 1055 --csv --log-file gpurun_out/launches.csv python bench.py --profile-run > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches exit $?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_pair -s 97 -c 1 -o gpurun_out/prof_gate_up_pair -f python bench.py --profile-run > gpurun_out/ncu_gemm.log 2>&1; echo "ncu gate_up exit $?"
