@@ -176,14 +176,16 @@ class Phi3VProcessorB200:
 
     def __init__(self, image_processor: Phi3VImageProcessorB200, tokenizer):
         self.image_processor, self.tokenizer = image_processor, tokenizer
-        self.num_img_tokens = image_processor.num_crops and 144
-        self.img_tokens = [f"<|image_{i + 1}|>" for i in range(1000000)] if False else None
+        self.num_img_tokens = 144  # per 336x336 crop after the 2x2 merge (config img_processor.num_img_tokens)
+
+    def _image_inputs(self, images):
+        return self.image_processor(images, return_tensors="pt")
 
     def __call__(self, text, images=None, padding=False, truncation=None, max_length=None, return_tensors="pt"):
         if images is None:
             return self.tokenizer(text, return_tensors=return_tensors, padding=padding, truncation=truncation,
                                   max_length=max_length)
-        image_inputs = self.image_processor(images, return_tensors="pt")
+        image_inputs = self._image_inputs(images)
         pattern = r"<\|image_\d+\|>"
         chunks = [self.tokenizer(c).input_ids for c in re.split(pattern, text)]
         tags = re.findall(pattern, text)
@@ -193,9 +195,10 @@ class Phi3VProcessorB200:
             raise AssertionError("image tags must be 1..n and match the number of images")  # reference :429-432
         ntok = image_inputs["num_img_tokens"].tolist()
         pads = [[-iid] * ntok[iid - 1] for iid in image_ids]
+        # chunks and image-token runs alternate; like the reference (offset = 0) nothing is stripped from the chunks
         ids: List[int] = []
         for j, c in enumerate(chunks):
-            ids.extend(c if j == 0 else c[1:] if c and c[0] == getattr(self.tokenizer, "bos_token_id", None) else c)
+            ids.extend(c)
             if j < len(pads):
                 ids.extend(pads[j])
         input_ids = torch.tensor(ids, dtype=torch.long).unsqueeze(0)
