@@ -101,6 +101,8 @@ int lr_clip_embed_ln(const void* patch, const void* class_emb, const void* pos_e
  * For LR_ATTN_TCGEN05 q, k, v must be column offsets into one row-major buffer (the fused qkv projection). */
 #define LR_ATTN_TCGEN05 0 /* tcgen05.mma + TMEM + TMA, two 128-row query tiles per CTA (product path) */
 #define LR_ATTN_MMA_SYNC 1 /* mma.sync kernel, kept to cross-check the tcgen05 path in tests */
+#define LR_ATTN_TCGEN05_SPLIT 2 /* tcgen05 kernel with two softmax threads per query row (4 softmax warpgroups);
+                                   measured slower than the default (the kernel is shared-memory-bandwidth bound) */
 int lr_attention_bf16(const void* q, const void* k, const void* v, void* o, int ld_qkv, int ld_o, int n_seq,
                       int rows_per_seq, const int* seq_start, const int* seq_len, int n_heads, int head_dim,
                       int causal, float scale, int impl, void* stream);

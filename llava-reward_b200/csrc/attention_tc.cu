@@ -39,7 +39,6 @@ __device__ long long* g_attn_trace = nullptr;
   } while (0)
 #endif
 
-constexpr int kTcThreads = 384;
 constexpr int kAtomBytes = 128 * 64;      // [128 rows x 32 bf16], 64B swizzle
 constexpr int kPBytes = 128 * 128 * 2;    // P tile: two [128 x 64 bf16] 128B-swizzled atoms
 constexpr long long kStaggerCycles = 1100;
@@ -75,11 +74,17 @@ struct AttnTcCfg {
   static constexpr int kTileBytes = kAtoms * kAtomBytes;         // one Q / K tile, and the TMA-loaded part of a V tile
   static constexpr int kVTileBytes = (kAtoms + 1) * kAtomBytes;  // V tile + one atom of ones (row sums via the MMA)
   static constexpr int kSmemBytes = 2 * kTileBytes /*Q_A,Q_B*/ + 2 * kTileBytes /*K*/ + 2 * kVTileBytes /*V*/ +
-                                    2 * kPBytes + 1024 /*align*/ + 256 /*barriers*/;
+                                    2 * kPBytes + 256 /*barriers*/ + 2048 /*row-max exchange*/;
 };
 
-template <int HD, bool CAUSAL>
-__global__ void __launch_bounds__(kTcThreads, 1)
+// SPLIT = threads per query row in the softmax: 1 -> one thread owns the whole 128-column S row (2 warpgroups,
+// the product path), 2 -> two threads own 64 columns each (4 warpgroups, row maxima exchanged through shared memory).
+// The split variant was built to test whether more warps per scheduler help; it is ~15 % SLOWER: per pair of tiles
+// and K/V block the kernel moves ~344 KB through shared memory (Q, K, P, V operand reads of the MMAs + P stores +
+// TMA fills) = ~2700 cycles at 128 B/clk, which - not MUFU, not latency - bounds the iteration (r01 finding; the next
+// step is P through TMEM, aliasing S, as the A operand of the PV MMA).
+template <int HD, bool CAUSAL, int SPLIT>
+__global__ void __launch_bounds__(128 + 256 * SPLIT, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o, int ld_o, int rows_per_seq,
                const int* __restrict__ seq_start, const int* __restrict__ seq_len, int q_col0, int k_col0, int v_col0,
                float scale_log2) {
@@ -88,8 +93,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
   constexpr int TILE = Cfg::kTileBytes;
   constexpr int VTILE = Cfg::kVTileBytes;
   constexpr int HDX = HD + 16;  // O columns incl. the row-sum columns
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];  // the swizzled tiles need a 1024 B aligned base
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+  uint8_t* smem = smem_raw;
   uint8_t* sQ = smem;                    // [2][TILE]
   uint8_t* sK = sQ + 2 * TILE;           // [2][TILE]
   uint8_t* sV = sK + 2 * TILE;           // [2][VTILE]
@@ -106,6 +112,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
   uint64_t* pv_done = bars + 15;         // [2] per tile  MMA -> softmax : O_x += P_x(j) V_j retired
   uint64_t* o_final = bars + 17;         // [2] per tile
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  float* mbuf = reinterpret_cast<float*>(bars + 32);  // [2 tiles][2 halves][128] row-max exchange (SPLIT == 2)
+  constexpr int kThreads = 128 + 256 * SPLIT;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int seq = blockIdx.z, head = blockIdx.y;
@@ -136,8 +144,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 2);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 4);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&s_free[i], 4 * SPLIT);
+      mbar_init(&p_full[i], 4 * SPLIT);
       mbar_init(&pv_done[i], 1);
       mbar_init(&o_final[i], 1);
     }
@@ -148,7 +156,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     tmem_relinquish();
   }
   // the ones atom of both V stages (bf16 1.0 everywhere, so the swizzle is irrelevant)
-  for (int i = threadIdx.x; i < 2 * kAtomBytes / 16; i += kTcThreads) {
+  for (int i = threadIdx.x; i < 2 * kAtomBytes / 16; i += kThreads) {
     const int st = i / (kAtomBytes / 16), o16 = i % (kAtomBytes / 16);
     *reinterpret_cast<uint4*>(sV + st * VTILE + NA * kAtomBytes + o16 * 16) =
         make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
@@ -276,17 +284,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     __syncwarp();
   }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    if constexpr (SPLIT == 1) {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    } else {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    }
     // ------------------------------------------------------------------ softmax warpgroups
-    const int x = (warp - 4) >> 2;   // tile A (warps 4-7) or B (warps 8-11)
-    const int q = warp & 3;          // TMEM lane quarter
-    const int r = q * 32 + lane;     // row inside the tile
+    constexpr int NCH = 4 / SPLIT;                 // 32-column chunks of S owned by one thread
+    const int sw = warp - 4;
+    const int x = sw / (4 * SPLIT);                // tile A or B
+    const int h = (sw >> 2) % SPLIT;               // column half (SPLIT == 2)
+    const int q = warp & 3;                        // TMEM lane quarter
+    const int r = q * 32 + lane;                   // row inside the tile
     const int row_abs = m0 + x * 128 + r;
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     uint8_t* prow = sP + x * kPBytes + r * 128;
     float m_ref = -INFINITY;
     const int nx = nblk[x];
-    const bool tr = (q == 0 && lane == 0);
+    const bool tr = (q == 0 && lane == 0 && h == 0);
     for (int j = 0; j < nx; ++j) {
       if (tr) ATTN_TRACE(1 + x, 0, j);
       mbar_wait(&s_full[x], j & 1);
@@ -295,32 +310,41 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       const int kv0 = start + j * 128;
       const bool need_mask = (kv0 + 128 > kv_end[x]) || (CAUSAL && kv0 + 127 > m0 + x * 128);
       // whole S row -> registers, then give the TMEM buffer back to the MMA warp
-      uint32_t sv[4][32];
+      uint32_t sv[NCH][32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32(tm_S[x] + lane_addr + c * 32, sv[c]);
+      for (int c = 0; c < NCH; ++c) tmem_ld_32x32(tm_S[x] + lane_addr + (h * NCH + c) * 32, sv[c]);
       tmem_ld_wait();
       if (tr) ATTN_TRACE(1 + x, 2, j);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[x]);
       if (need_mask) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < NCH; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const int col = kv0 + c * 32 + i;
+            const int col = kv0 + (h * NCH + c) * 32 + i;
             const bool ok = col < kv_end[x] && (!CAUSAL || col <= row_abs);
             sv[c][i] = ok ? sv[c][i] : 0xff800000u;  // -inf
           }
       }
-      float mxc[8];  // 8 independent chains instead of one 128-long dependent FMNMX chain
+      float mxc[8];  // 8 independent chains instead of one long dependent FMNMX chain
 #pragma unroll
       for (int c = 0; c < 8; ++c) mxc[c] = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < NCH; ++c)
 #pragma unroll
         for (int i = 0; i < 32; ++i) mxc[(c * 2 + (i >> 4)) & 7] = fmaxf(mxc[(c * 2 + (i >> 4)) & 7], __uint_as_float(sv[c][i]));
       float mx = fmaxf(fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3])), fmaxf(fmaxf(mxc[4], mxc[5]), fmaxf(mxc[6], mxc[7])));
+      if constexpr (SPLIT == 2) {
+        // The other 64 columns of this row live in a thread of the partner warpgroup: exchange the partial maxima
+        // through smem. The S buffer is released only AFTER the exchange, so S_x(j+1) - and with it the next write
+        // to this buffer - cannot happen before every thread has read its partner's value of block j.
+        float* mb = mbuf + x * 256;
+        mb[h * 128 + r] = mx;
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + x) : "memory");
+        mx = fmaxf(mx, mb[(h ^ 1) * 128 + r]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[x]);
       mx *= scale_log2;  // scale > 0, so max commutes with the scaling
       // lazy rescale: move the reference max only when it grew by more than the threshold
       float alpha = 1.f;
@@ -337,7 +361,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         tc_fence_after();
         if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll 1
-          for (int c = 0; c < HD / 32 + 1; ++c) {  // +1: the chunk that holds the row-sum column
+          for (int c = h; c < HD / 32 + 1; c += SPLIT) {  // +1: the chunk that holds the row-sum column
             uint32_t ov[32];
             tmem_ld_32x32(tm_O[x] + lane_addr + c * 32, ov);
             tmem_ld_wait();
@@ -353,16 +377,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       // stores issue under the MUFU-bound exponentials. 128 columns = 2 atoms x 8 chunks of 16 B; chunk position
       // XOR (row & 7) = the 128B swizzle.
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < NCH; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i)
           pk[i] = pack_bf16x2(exp2f(fmaf(__uint_as_float(sv[c][2 * i]), scale_log2, -msafe)),
                               exp2f(fmaf(__uint_as_float(sv[c][2 * i + 1]), scale_log2, -msafe)));
-        uint8_t* base = prow + (c >> 1) * (kPBytes / 2);
+        const int cg = h * NCH + c;  // chunk index inside the 128-column row
+        uint8_t* base = prow + (cg >> 1) * (kPBytes / 2);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          const int chunk = ((c & 1) * 4 + t) ^ (r & 7);
+          const int chunk = ((cg & 1) * 4 + t) ^ (r & 7);
           *reinterpret_cast<uint4*>(base + (chunk << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
         }
       }
@@ -389,7 +414,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         inv = l_sum > 0.f ? 1.f / l_sum : 0.f;
       }
 #pragma unroll 1
-      for (int c = 0; c < HD / 32; ++c) {
+      for (int c = h; c < HD / 32; c += SPLIT) {
         uint32_t ov[32];
         tmem_ld_32x32(tm_O[x] + lane_addr + c * 32, ov);
         tmem_ld_wait();
@@ -407,7 +432,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
           }
         }
       }
-    } else if (row_in_slot) {
+    } else if (row_in_slot && h == 0) {
 #pragma unroll 1
       for (int c = 0; c < HD / 8; ++c) *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(0, 0, 0, 0);
     }
@@ -440,7 +465,7 @@ static EncodeTiledFn attn_encode_fn() {
   return fn;
 }
 
-template <int HD, bool CAUSAL>
+template <int HD, bool CAUSAL, int SPLIT>
 static int launch_attn_tc(const void* base, int total_rows, int ld_qkv, int q_col0, int k_col0, int v_col0, void* o,
                           int ld_o, int n_seq, int rows_per_seq, const int* seq_start, const int* seq_len, int n_heads,
                           float scale, cudaStream_t stream) {
@@ -456,13 +481,13 @@ static int launch_attn_tc(const void* base, int total_rows, int ld_qkv, int q_co
          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return LR_ERR_BAD_ARG;
-  auto kern = attn_tc_kernel<HD, CAUSAL>;
+  auto kern = attn_tc_kernel<HD, CAUSAL, SPLIT>;
   {  // per-device attribute; setting it on every launch keeps multi-device processes correct
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
   dim3 grid((rows_per_seq + 255) / 256, n_heads, n_seq);
-  kern<<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(tm, reinterpret_cast<bf16*>(o), ld_o, rows_per_seq, seq_start,
+  kern<<<grid, 128 + 256 * SPLIT, Cfg::kSmemBytes, stream>>>(tm, reinterpret_cast<bf16*>(o), ld_o, rows_per_seq, seq_start,
                                                       seq_len, q_col0, k_col0, v_col0, scale * 1.4426950408889634f);
   return lr_launch_status();
 }
@@ -470,18 +495,23 @@ static int launch_attn_tc(const void* base, int total_rows, int ld_qkv, int q_co
 // q, k, v must be column offsets into ONE row-major buffer (the fused qkv projection): base = q.
 int attention_tc(const void* q, const void* k, const void* v, void* o, int ld_qkv, int ld_o, int n_seq,
                  int rows_per_seq, const int* seq_start, const int* seq_len, int n_heads, int head_dim, int causal,
-                 float scale, cudaStream_t s) {
+                 float scale, int split, cudaStream_t s) {
   const ptrdiff_t kd = (reinterpret_cast<const char*>(k) - reinterpret_cast<const char*>(q)) / 2;
   const ptrdiff_t vd = (reinterpret_cast<const char*>(v) - reinterpret_cast<const char*>(q)) / 2;
   const int width = n_heads * head_dim;
   if (kd < 0 || vd < 0 || kd + width > ld_qkv || vd + width > ld_qkv) return LR_ERR_BAD_ARG;
   const int total_rows = n_seq * rows_per_seq;
-  if (head_dim == 64 && !causal)
-    return launch_attn_tc<64, false>(q, total_rows, ld_qkv, 0, int(kd), int(vd), o, ld_o, n_seq, rows_per_seq,
-                                     seq_start, seq_len, n_heads, scale, s);
-  if (head_dim == 96 && causal)
-    return launch_attn_tc<96, true>(q, total_rows, ld_qkv, 0, int(kd), int(vd), o, ld_o, n_seq, rows_per_seq,
-                                    seq_start, seq_len, n_heads, scale, s);
+#define LR_ATTN_CASE(HD_, CAUSAL_)                                                                                  \
+  if (head_dim == HD_ && bool(causal) == CAUSAL_) {                                                                 \
+    if (split == 2)                                                                                                 \
+      return launch_attn_tc<HD_, CAUSAL_, 2>(q, total_rows, ld_qkv, 0, int(kd), int(vd), o, ld_o, n_seq, rows_per_seq, \
+                                             seq_start, seq_len, n_heads, scale, s);                                \
+    return launch_attn_tc<HD_, CAUSAL_, 1>(q, total_rows, ld_qkv, 0, int(kd), int(vd), o, ld_o, n_seq, rows_per_seq, \
+                                           seq_start, seq_len, n_heads, scale, s);                                  \
+  }
+  LR_ATTN_CASE(64, false)
+  LR_ATTN_CASE(96, true)
+#undef LR_ATTN_CASE
   return LR_ERR_BAD_ARG;
 }
 
