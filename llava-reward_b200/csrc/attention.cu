@@ -258,9 +258,9 @@ extern "C" int lr_attention_bf16(const void* q, const void* k, const void* v, vo
                                      reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(o)) & 15)
     return LR_ERR_ALIGN;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (impl == LR_ATTN_TCGEN05 || impl == LR_ATTN_TCGEN05_SPLIT)
+  if (impl == LR_ATTN_TCGEN05 || impl == LR_ATTN_TCGEN05_SPLIT || impl == LR_ATTN_TCGEN05_2TILE)
     return attention_tc(q, k, v, o, ld_qkv, ld_o, n_seq, rows_per_seq, seq_start, seq_len, n_heads, head_dim, causal,
-                        scale, impl == LR_ATTN_TCGEN05_SPLIT ? 2 : 1, s);
+                        scale, impl == LR_ATTN_TCGEN05_SPLIT ? 2 : (impl == LR_ATTN_TCGEN05 ? 3 : 1), s);
   if (impl != LR_ATTN_MMA_SYNC) return LR_ERR_BAD_ARG;
   if (head_dim == 64 && !causal)
     return launch_attn<64, false>(q, k, v, o, ld_qkv, ld_o, n_seq, rows_per_seq, seq_start, seq_len, n_heads, scale, s);

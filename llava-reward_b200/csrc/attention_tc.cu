@@ -2,7 +2,10 @@
 // the accumulators in TMEM; K/V/Q tiles arrive by TMA (64B-swizzled atoms of 32 head-dim columns, so head_dim 96
 // needs no padding); softmax runs thread-per-row out of TMEM.
 //
-// One CTA = 256 query rows of one head (two 128-row tiles A and B), 384 threads:
+// Product configuration (NT = 1): one CTA = one 128-row query tile of one head, 256 threads, 112 KB smem and 256 TMEM
+// columns, so TWO CTAs share an SM: their softmax phases de-phase naturally and each CTA's prologue/epilogue hides
+// behind the other's main loop (measured: CLIP 1.70 -> 1.37 ms, decoder 1.35 -> 1.34 ms vs NT = 2).
+// Alternative (NT = 2, kept for comparison) - one CTA = 256 query rows (tiles A and B) sharing K/V, 384 threads:
 //   warp 0    : TMA producer (Q_A, Q_B once; K_j / V_j through two 2-stage rings shared by both tiles)
 //   warp 1    : MMA issuer   (S_X(j) = Q_X K_j^T  [128x128xHD],  O_X += P_X(j) V_j  [128xHDx128], X in {A,B})
 //   warp 2    : TMEM allocator (S_A, S_B: 128 fp32 columns each; O_A, O_B: HD columns each)
@@ -68,13 +71,18 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int HD>
+// NT = query tiles per CTA. NT = 2: one CTA per SM, K/V shared by both tiles, 2-stage rings.
+// NT = 1: one tile per CTA, single-stage K/V, 112 KB of smem and 256 TMEM columns -> TWO CTAs per SM, which de-phases
+// the two softmax warpgroups of an SM naturally and hides each CTA's prologue/epilogue behind the other's main loop.
+template <int HD, int NT>
 struct AttnTcCfg {
+  static constexpr int kStages = NT == 2 ? 2 : 1;
+  static constexpr int kTmemCols = NT == 2 ? 512 : 256;
   static constexpr int kAtoms = HD / 32;
   static constexpr int kTileBytes = kAtoms * kAtomBytes;         // one Q / K tile, and the TMA-loaded part of a V tile
   static constexpr int kVTileBytes = (kAtoms + 1) * kAtomBytes;  // V tile + one atom of ones (row sums via the MMA)
-  static constexpr int kSmemBytes = 2 * kTileBytes /*Q_A,Q_B*/ + 2 * kTileBytes /*K*/ + 2 * kVTileBytes /*V*/ +
-                                    2 * kPBytes + 256 /*barriers*/ + 2048 /*row-max exchange*/;
+  static constexpr int kSmemBytes = NT * kTileBytes /*Q*/ + kStages * kTileBytes /*K*/ + kStages * kVTileBytes /*V*/ +
+                                    NT * kPBytes + 256 /*barriers*/ + (NT == 2 ? 2048 : 0) /*row-max exchange*/;
 };
 
 // SPLIT = threads per query row in the softmax: 1 -> one thread owns the whole 128-column S row (2 warpgroups,
@@ -83,12 +91,13 @@ struct AttnTcCfg {
 // and K/V block the kernel moves ~344 KB through shared memory (Q, K, P, V operand reads of the MMAs + P stores +
 // TMA fills) = ~2700 cycles at 128 B/clk, which - not MUFU, not latency - bounds the iteration (r01 finding; the next
 // step is P through TMEM, aliasing S, as the A operand of the PV MMA).
-template <int HD, bool CAUSAL, int SPLIT>
-__global__ void __launch_bounds__(128 + 256 * SPLIT, 1)
+template <int HD, bool CAUSAL, int SPLIT, int NT>
+__global__ void __launch_bounds__(128 + 128 * NT * SPLIT, NT == 2 ? 1 : 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o, int ld_o, int rows_per_seq,
                const int* __restrict__ seq_start, const int* __restrict__ seq_len, int q_col0, int k_col0, int v_col0,
                float scale_log2) {
-  using Cfg = AttnTcCfg<HD>;
+  using Cfg = AttnTcCfg<HD, NT>;
+  constexpr int NS = Cfg::kStages;
   constexpr int NA = Cfg::kAtoms;
   constexpr int TILE = Cfg::kTileBytes;
   constexpr int VTILE = Cfg::kVTileBytes;
@@ -96,11 +105,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // the swizzled tiles need a 1024 B aligned base
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
   uint8_t* smem = smem_raw;
-  uint8_t* sQ = smem;                    // [2][TILE]
-  uint8_t* sK = sQ + 2 * TILE;           // [2][TILE]
-  uint8_t* sV = sK + 2 * TILE;           // [2][VTILE]
-  uint8_t* sP = sV + 2 * VTILE;          // [2][kPBytes]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
+  uint8_t* sQ = smem;                    // [NT][TILE]
+  uint8_t* sK = sQ + NT * TILE;          // [NS][TILE]
+  uint8_t* sV = sK + NS * TILE;          // [NS][VTILE]
+  uint8_t* sP = sV + NS * VTILE;         // [NT][kPBytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NT * kPBytes);
   uint64_t* q_full = bars;               // [1]
   uint64_t* k_full = bars + 1;           // [2]
   uint64_t* k_empty = bars + 3;          // [2]
@@ -113,12 +122,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
   uint64_t* o_final = bars + 17;         // [2] per tile
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
   float* mbuf = reinterpret_cast<float*>(bars + 32);  // [2 tiles][2 halves][128] row-max exchange (SPLIT == 2)
-  constexpr int kThreads = 128 + 256 * SPLIT;
+  constexpr int kThreads = 128 + 128 * NT * SPLIT;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int seq = blockIdx.z, head = blockIdx.y;
   const int qt = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
-  const int m0 = qt * 256;
+  const int m0 = qt * 128 * NT;
   const int start = seq_start ? seq_start[seq] : 0;
   const int len = seq_len ? seq_len[seq] : rows_per_seq;
   const int end = start + len;
@@ -129,7 +138,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
   for (int x = 0; x < 2; ++x) {
     lo[x] = max(m0 + x * 128, start);
     hi[x] = min(min(m0 + x * 128 + 128, end), rows_per_seq);
-    const bool valid = lo[x] < hi[x];
+    const bool valid = lo[x] < hi[x] && x < NT;
     kv_end[x] = valid ? (CAUSAL ? min(end, hi[x]) : end) : start;
     nblk[x] = (kv_end[x] - start + 127) / 128;
   }
@@ -140,9 +149,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 2);  // one arrival per MMA-issuing thread (tile A, tile B)
+      mbar_init(&k_empty[i], NT);  // one arrival per MMA-issuing thread (one per tile)
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 2);
+      mbar_init(&v_empty[i], NT);
       mbar_init(&s_full[i], 1);
       mbar_init(&s_free[i], 4 * SPLIT);
       mbar_init(&p_full[i], 4 * SPLIT);
@@ -152,11 +161,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
   // the ones atom of both V stages (bf16 1.0 everywhere, so the swizzle is irrelevant)
-  for (int i = threadIdx.x; i < 2 * kAtomBytes / 16; i += kThreads) {
+  for (int i = threadIdx.x; i < NS * kAtomBytes / 16; i += kThreads) {
     const int st = i / (kAtomBytes / 16), o16 = i % (kAtomBytes / 16);
     *reinterpret_cast<uint4*>(sV + st * VTILE + NA * kAtomBytes + o16 * 16) =
         make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
@@ -166,12 +175,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // NT = 2: S_A 0, S_B 128, O_A 256, O_B 384;  NT = 1: S 0, O 128
   const uint32_t tm_S[2] = {tmem_base, tmem_base + 128};
-  const uint32_t tm_O[2] = {tmem_base + 256, tmem_base + 384};
+  const uint32_t tm_O[2] = {tmem_base + (NT == 2 ? 256 : 128), tmem_base + 384};
 
   // register re-allocation between warpgroups: the softmax threads keep a whole 128-column S row in registers
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if constexpr (NT == 1) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  }
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0 && n > 0) {
@@ -186,16 +200,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       // K and V rings advance independently (the MMA thread consumes them out of lock-step)
       int kj = 0, vj = 0;
       while (kj < n || vj < n) {
-        if (kj < n && mbar_test_wait(&k_empty[kj & 1], ((kj >> 1) & 1) ^ 1)) {
-          const int s = kj & 1;
+        if (kj < n && mbar_test_wait(&k_empty[kj % NS], ((kj / NS) & 1) ^ 1)) {
+          const int s = kj % NS;
           mbar_arrive_expect_tx(&k_full[s], TILE);
           for (int a = 0; a < NA; ++a)
             tma_load_2d(sK + s * TILE + a * kAtomBytes, &tm_qkv, &k_full[s], k_col0 + head * HD + a * 32,
                         slot_row0 + start + kj * 128);
           ++kj;
         }
-        if (vj < n && vj < kj && mbar_test_wait(&v_empty[vj & 1], ((vj >> 1) & 1) ^ 1)) {
-          const int s = vj & 1;
+        if (vj < n && vj < kj && mbar_test_wait(&v_empty[vj % NS], ((vj / NS) & 1) ^ 1)) {
+          const int s = vj % NS;
           mbar_arrive_expect_tx(&v_full[s], TILE);
           for (int a = 0; a < NA; ++a)
             tma_load_2d(sV + s * VTILE + a * kAtomBytes, &tm_qkv, &v_full[s], v_col0 + head * HD + a * 32,
@@ -205,7 +219,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       }
     }
     __syncwarp();
-  } else if (warp == 1 || warp == 3) {
+  } else if (warp == 1 || (warp == 3 && NT == 2)) {
     // ------------------------------------------------------------------ MMA issuers: warp 1 -> tile A, warp 3 -> tile B
     // One thread per tile: a tcgen05.mma costs ~90 cycles of issue latency (measured with tools/attn_trace.py),
     // more than these 128x128x16 / 128x112x16 MMAs take to execute, so two issuing threads keep the tensor core fed.
@@ -242,7 +256,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       if (nx > 0) {
         mbar_wait(q_full, 0);
         mbar_wait(&k_full[0], 0);
-        if (x == 1 && nblk[0] > 0) {
+        if (NT == 2 && x == 1 && nblk[0] > 0) {
           // Start tile B half a softmax period after tile A: both softmax warpgroups share the SM's 16 ex2/clk, and
           // the exponential phase is about half of an iteration, so in anti-phase each runs its exponentials alone.
           mbar_wait(&s_free[0], 0);
@@ -255,16 +269,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         int s_next = 1, pv_next = 0;
         while (pv_next < nx) {
           if (s_next < nx && mbar_test_wait(&s_free[x], (s_next - 1) & 1) &&
-              mbar_test_wait(&k_full[s_next & 1], (s_next >> 1) & 1)) {
+              mbar_test_wait(&k_full[s_next % NS], (s_next / NS) & 1)) {
             tc_fence_after();
             ATTN_TRACE(0, x * 4 + 0, s_next - 1);
-            issue_s(s_next & 1);
+            issue_s(s_next % NS);
             ++s_next;
           }
-          if (mbar_test_wait(&p_full[x], pv_next & 1) && mbar_test_wait(&v_full[pv_next & 1], (pv_next >> 1) & 1)) {
+          if (mbar_test_wait(&p_full[x], pv_next & 1) && mbar_test_wait(&v_full[pv_next % NS], (pv_next / NS) & 1)) {
             tc_fence_after();
             ATTN_TRACE(0, x * 4 + 1, pv_next);
-            issue_pv(pv_next & 1, pv_next > 0);
+            issue_pv(pv_next % NS, pv_next > 0);
             if (pv_next + 1 == nx) umma_commit(&o_final[x]);
             ATTN_TRACE(0, x * 4 + 2, pv_next);
             ++pv_next;
@@ -272,10 +286,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         }
       }
       for (int j = nx; j < n; ++j) {  // K/V blocks only the other tile reads: arrive in phase order
-        const int st = j & 1;
-        if (j >= 2) {
-          mbar_wait(&k_empty[st], ((j - 2) >> 1) & 1);
-          mbar_wait(&v_empty[st], ((j - 2) >> 1) & 1);
+        const int st = j % NS;
+        if (j >= NS) {
+          mbar_wait(&k_empty[st], ((j - NS) / NS) & 1);
+          mbar_wait(&v_empty[st], ((j - NS) / NS) & 1);
         }
         mbar_arrive(&k_empty[st]);
         mbar_arrive(&v_empty[st]);
@@ -284,7 +298,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     __syncwarp();
   }
   } else {
-    if constexpr (SPLIT == 1) {
+    if constexpr (NT == 1) {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");  // 2 CTAs/SM: 2 x (128 x 208 + 128 x 40) <= 64 K
+    } else if constexpr (SPLIT == 1) {
       asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     } else {
       asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
@@ -442,7 +458,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -465,11 +481,11 @@ static EncodeTiledFn attn_encode_fn() {
   return fn;
 }
 
-template <int HD, bool CAUSAL, int SPLIT>
+template <int HD, bool CAUSAL, int SPLIT, int NT>
 static int launch_attn_tc(const void* base, int total_rows, int ld_qkv, int q_col0, int k_col0, int v_col0, void* o,
                           int ld_o, int n_seq, int rows_per_seq, const int* seq_start, const int* seq_len, int n_heads,
                           float scale, cudaStream_t stream) {
-  using Cfg = AttnTcCfg<HD>;
+  using Cfg = AttnTcCfg<HD, NT>;
   EncodeTiledFn fn = attn_encode_fn();
   if (!fn) return LR_ERR_NO_DRIVER;
   CUtensorMap tm;
@@ -481,13 +497,13 @@ static int launch_attn_tc(const void* base, int total_rows, int ld_qkv, int q_co
          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return LR_ERR_BAD_ARG;
-  auto kern = attn_tc_kernel<HD, CAUSAL, SPLIT>;
+  auto kern = attn_tc_kernel<HD, CAUSAL, SPLIT, NT>;
   {  // per-device attribute; setting it on every launch keeps multi-device processes correct
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
-  dim3 grid((rows_per_seq + 255) / 256, n_heads, n_seq);
-  kern<<<grid, 128 + 256 * SPLIT, Cfg::kSmemBytes, stream>>>(tm, reinterpret_cast<bf16*>(o), ld_o, rows_per_seq, seq_start,
+  dim3 grid((rows_per_seq + 128 * NT - 1) / (128 * NT), n_heads, n_seq);
+  kern<<<grid, 128 + 128 * NT * SPLIT, Cfg::kSmemBytes, stream>>>(tm, reinterpret_cast<bf16*>(o), ld_o, rows_per_seq, seq_start,
                                                       seq_len, q_col0, k_col0, v_col0, scale * 1.4426950408889634f);
   return lr_launch_status();
 }
@@ -504,10 +520,13 @@ int attention_tc(const void* q, const void* k, const void* v, void* o, int ld_qk
 #define LR_ATTN_CASE(HD_, CAUSAL_)                                                                                  \
   if (head_dim == HD_ && bool(causal) == CAUSAL_) {                                                                 \
     if (split == 2)                                                                                                 \
-      return launch_attn_tc<HD_, CAUSAL_, 2>(q, total_rows, ld_qkv, 0, int(kd), int(vd), o, ld_o, n_seq, rows_per_seq, \
-                                             seq_start, seq_len, n_heads, scale, s);                                \
-    return launch_attn_tc<HD_, CAUSAL_, 1>(q, total_rows, ld_qkv, 0, int(kd), int(vd), o, ld_o, n_seq, rows_per_seq, \
-                                           seq_start, seq_len, n_heads, scale, s);                                  \
+      return launch_attn_tc<HD_, CAUSAL_, 2, 2>(q, total_rows, ld_qkv, 0, int(kd), int(vd), o, ld_o, n_seq,          \
+                                                rows_per_seq, seq_start, seq_len, n_heads, scale, s);               \
+    if (split == 3)                                                                                                 \
+      return launch_attn_tc<HD_, CAUSAL_, 1, 1>(q, total_rows, ld_qkv, 0, int(kd), int(vd), o, ld_o, n_seq,          \
+                                                rows_per_seq, seq_start, seq_len, n_heads, scale, s);               \
+    return launch_attn_tc<HD_, CAUSAL_, 1, 2>(q, total_rows, ld_qkv, 0, int(kd), int(vd), o, ld_o, n_seq,            \
+                                              rows_per_seq, seq_start, seq_len, n_heads, scale, s);                 \
   }
   LR_ATTN_CASE(64, false)
   LR_ATTN_CASE(96, true)

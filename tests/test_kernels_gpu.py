@@ -210,7 +210,7 @@ def attn_ref(q, k, v, causal, scale, start=0, length=None):
     return out
 
 
-@pytest.mark.parametrize("impl", [L.ATTN_TCGEN05, L.ATTN_MMA_SYNC, L.ATTN_TCGEN05_SPLIT])
+@pytest.mark.parametrize("impl", [L.ATTN_TCGEN05, L.ATTN_MMA_SYNC, L.ATTN_TCGEN05_SPLIT, L.ATTN_TCGEN05_2TILE])
 @pytest.mark.parametrize("hd,heads,T,nseq,causal", [(64, 16, 577, 3, False), (96, 32, 700, 2, True),
                                                     (96, 4, 130, 3, True), (64, 2, 64, 1, False),
                                                     (96, 2, 2048, 3, True), (64, 3, 1000, 2, False)])

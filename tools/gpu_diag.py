@@ -105,7 +105,7 @@ def perf(gemms=True):
         qkv = torch.randn(nseq * T, 3 * D, device="cuda", dtype=bf)
         o = torch.empty(nseq * T, D, device="cuda", dtype=bf)
         fl = 4.0 * nseq * heads * T * T * hd * (0.5 if causal else 1.0)
-        for impl, iname in ((L.ATTN_TCGEN05, "tcgen05"), (L.ATTN_TCGEN05_SPLIT, "tcgen05-split"), (L.ATTN_MMA_SYNC, "mma.sync")):
+        for impl, iname in ((L.ATTN_TCGEN05, "tcgen05"), (L.ATTN_TCGEN05_SPLIT, "tcgen05-split"), (L.ATTN_TCGEN05_2TILE, "tcgen05-2tile"), (L.ATTN_MMA_SYNC, "mma.sync")):
             ms = timeit(lambda: ops.attention(qkv, qkv[:, D:], qkv[:, 2 * D:], o, 3 * D, D, nseq, T, None, None, heads,
                                               hd, causal, hd ** -0.5, impl))
             res[f"attn_{name}_{iname}"] = {"ms": ms, "tflops": fl / ms / 1e9}
