@@ -17,7 +17,7 @@ from typing import Callable, Dict, Iterator, List, Optional, Tuple
 
 import torch
 
-from .config import RewardConfig, num_image_tokens
+from .config import LlavaNextRewardConfig, RewardConfig, anyres_geometry, num_image_tokens
 
 _M32 = 0xFFFFFFFF
 _IH_STD = 65536.0 / (3.0 ** 0.5)  # std of the sum of four U{0..65535} (Irwin-Hall, n=4)
@@ -126,13 +126,65 @@ def param_specs(cfg: RewardConfig) -> Iterator[Tuple[str, Tuple[int, ...], str]]
         yield "ca_layernorm.weight", (H,), "n"
 
 
+LLAVA_CLIP_PREFIX = "vision_tower.vision_model."
+LLAVA_LM_PREFIX = "language_model.model."
+
+
+def llava_param_specs(cfg: LlavaNextRewardConfig) -> Iterator[Tuple[str, Tuple[int, ...], str]]:
+    """Parameters of the LLaVA-v1.6 reward model under the state_dict names of the transformers release the
+    reference pins (4.50: `vision_tower.*`, `multi_modal_projector.*`, `image_newline`, `language_model.model.*` -
+    the names create_lora_config_llava16_vicuna targets, llava_reward/utils/utils.py:243-251) + `value_head`."""
+    H, I, V = cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size
+    D, DI = cfg.clip_hidden, cfg.clip_intermediate
+    lm, c = LLAVA_LM_PREFIX, LLAVA_CLIP_PREFIX
+    yield lm + "embed_tokens.weight", (V, H), "w"
+    yield "image_newline", (H,), "w"
+    yield "multi_modal_projector.linear_1.weight", (H, D), "w"
+    yield "multi_modal_projector.linear_1.bias", (H,), "w"
+    yield "multi_modal_projector.linear_2.weight", (H, H), "w"
+    yield "multi_modal_projector.linear_2.bias", (H,), "w"
+    yield c + "embeddings.class_embedding", (D,), "w"
+    yield c + "embeddings.patch_embedding.weight", (D, 3, cfg.patch, cfg.patch), "w"
+    yield c + "embeddings.position_embedding.weight", (cfg.clip_tokens, D), "w"
+    yield c + "pre_layrnorm.weight", (D,), "n"
+    yield c + "pre_layrnorm.bias", (D,), "w"
+    for i in range(cfg.clip_layers):
+        p = f"{c}encoder.layers.{i}."
+        for proj in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            yield p + f"self_attn.{proj}.weight", (D, D), "w"
+            yield p + f"self_attn.{proj}.bias", (D,), "w"
+        yield p + "layer_norm1.weight", (D,), "n"
+        yield p + "layer_norm1.bias", (D,), "w"
+        yield p + "mlp.fc1.weight", (DI, D), "w"
+        yield p + "mlp.fc1.bias", (DI,), "w"
+        yield p + "mlp.fc2.weight", (D, DI), "w"
+        yield p + "mlp.fc2.bias", (D,), "w"
+        yield p + "layer_norm2.weight", (D,), "n"
+        yield p + "layer_norm2.bias", (D,), "w"
+    r = cfg.lora_rank
+    for i in range(cfg.num_layers):
+        p = f"{lm}layers.{i}."
+        lin = [(f"self_attn.{n}_proj", H, H) for n in "qkvo"] + [("mlp.gate_proj", I, H), ("mlp.up_proj", I, H),
+                                                                ("mlp.down_proj", H, I)]
+        for nm, o, k in lin:
+            yield p + nm + ".weight", (o, k), "w"
+            if cfg.use_lora:
+                yield p + nm + ".lora_A.weight", (r, k), "w"
+                yield p + nm + ".lora_B.weight", (o, r), "w"
+        yield p + "input_layernorm.weight", (H,), "n"
+        yield p + "post_attention_layernorm.weight", (H,), "n"
+    yield lm + "norm.weight", (H,), "n"
+    yield "value_head.weight", (cfg.vhd, H), "w"
+
+
 class SynthProvider:
     """Callable ``name -> tensor`` producing synthetic parameters on demand."""
 
     def __init__(self, cfg: RewardConfig, seed: int = 1234, std: float = 0.02, device="cpu",
                  dtype=torch.float32):
         self.cfg, self.seed, self.std, self.device, self.dtype = cfg, seed, std, device, dtype
-        self.specs: Dict[str, Tuple[Tuple[int, ...], str]] = {n: (s, k) for n, s, k in param_specs(cfg)}
+        gen = llava_param_specs if isinstance(cfg, LlavaNextRewardConfig) else param_specs
+        self.specs: Dict[str, Tuple[Tuple[int, ...], str]] = {n: (s, k) for n, s, k in gen(cfg)}
 
     def names(self) -> List[str]:
         return list(self.specs)
@@ -187,3 +239,38 @@ def synth_batch(cfg: RewardConfig, batch: int, image_hw: Tuple[int, int], seq_le
         ids[b, S - len(row):] = torch.tensor(row, dtype=torch.int64)
         mask[b, S - len(row):] = 1
     return ids.to(device), mask.to(device), pix, sizes.to(device)
+
+
+def synth_batch_llava(cfg: LlavaNextRewardConfig, batch: int, orig_hw_list, seq_len: Optional[int], seed: int = 7,
+                      device="cpu", text_len_range: Tuple[int, int] = (40, 128), tag: str = "c",
+                      padding_side: str = "left"):
+    """The `inputs_batch` LlavaNextProcessor(images, text, padding=True) hands to custom_forward
+    (reference reward_dataset.py:334-346): input_ids [B,S] with `image_token_id` repeated N_v times, text FIRST then
+    the image (:267-277), attention_mask, pixel_values [B, max_patches, 3, 336, 336] zero-padded, image_sizes [B,2]
+    = ORIGINAL (h, w). Rows are [pad..., BOS, text..., IMG x N_v, EOS]."""
+    geos = [anyres_geometry(hw, cfg.image_grid_pinpoints, cfg.image_size, cfg.patch) for hw in orig_hw_list]
+    P = max(g["n_patches"] for g in geos)
+    pix = torch.zeros(batch, P, 3, cfg.image_size, cfg.image_size, dtype=torch.float32, device=device)
+    sizes = torch.tensor([list(hw) for hw in orig_hw_list], dtype=torch.int64)
+    tl = hash_randint(f"textlen.{tag}", batch, text_len_range[0], text_len_range[1], seed).tolist()
+    rows = []
+    for b in range(batch):
+        g = geos[b]
+        pix[b, : g["n_patches"]] = hash_normal(f"pixels.{tag}.{b}", (g["n_patches"], 3, cfg.image_size, cfg.image_size),
+                                               1.0, seed, device=device)
+        text = hash_randint(f"text.{tag}.{b}", tl[b], 3, 31999, seed).tolist()
+        rows.append([BOS] + text + [cfg.image_token_id] * g["n_tokens"] + [2])
+    S = max(len(r) for r in rows) if seq_len is None else seq_len
+    ids = torch.full((batch, S), 0, dtype=torch.int64)
+    mask = torch.zeros((batch, S), dtype=torch.int64)
+    for b, row in enumerate(rows):
+        if len(row) > S:
+            raise ValueError(f"sample {b} needs {len(row)} tokens > seq_len {S}")
+        if padding_side == "left":
+            ids[b, S - len(row):] = torch.tensor(row, dtype=torch.int64)
+            mask[b, S - len(row):] = 1
+        else:
+            ids[b, : len(row)] = torch.tensor(row, dtype=torch.int64)
+            mask[b, : len(row)] = 1
+    return {"input_ids": ids.to(device), "attention_mask": mask.to(device), "pixel_values": pix,
+            "image_sizes": sizes.to(device)}

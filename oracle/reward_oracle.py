@@ -55,7 +55,8 @@ class Params:
 # arithmetic: transformers/models/clip/modeling_clip.py (third-party; CLIPVisionEmbeddings.forward,
 # CLIPEncoderLayer.forward, eager_attention_forward, CLIPMLP.forward)
 # ----------------------------------------------------------------------------------------
-def clip_features(P: Params, cfg, pixel_values: torch.Tensor, taps=None) -> torch.Tensor:
+def clip_features(P: Params, cfg, pixel_values: torch.Tensor, taps=None, prefix: Optional[str] = None) -> torch.Tensor:
+    CLIP = prefix or globals()["CLIP"]
     n = pixel_values.shape[0]
     D, heads, hd = cfg.clip_hidden, cfg.clip_heads, cfg.clip_head_dim
     x = F.conv2d(pixel_values.to(P.dtype), P(CLIP + "embeddings.patch_embedding.weight"), stride=cfg.patch)

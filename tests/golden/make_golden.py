@@ -60,7 +60,12 @@ def import_reference():
     sys.path.insert(0, REF)
     from llava_reward.models import _get_reward_model  # noqa
     from llava_reward.models.base_mllm.phi3_v import modeling_phi3_v as mp
-    import eval.reward_adaptor_loader as ral
+    # /root/repo/eval is a regular package and would shadow the reference's namespace package `eval`:
+    # load the reference file by path
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_reward_adaptor_loader", os.path.join(REF, "eval", "reward_adaptor_loader.py"))
+    ral = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ral)
     return _get_reward_model, mp, ral
 
 

@@ -25,3 +25,15 @@ def fixture_batch(fx, entry, cfg, device="cpu"):
 
 def strided(t, stride, n=2048):
     return t.detach().float().flatten()[::stride][:n].cpu()
+
+
+def llava_fixture_cfg(fx):
+    from llava_reward_b200.config import LlavaNextRewardConfig
+    return LlavaNextRewardConfig(**fx["cfg_overrides"])
+
+
+def llava_fixture_batch(fx, entry, cfg, device="cpu"):
+    from llava_reward_b200.synth import synth_batch_llava
+    hw = [tuple(x) for x in entry["image_hw"]]
+    return synth_batch_llava(cfg, len(hw), hw, entry["seq_len"], seed=fx["seed_x"], tag=entry["tag"],
+                             padding_side=entry["padding_side"], device=device)
