@@ -122,6 +122,18 @@ int lr_rope_su_bf16(void* qkv, int ld, const int* position_ids, const void* cos_
 int lr_token_plan(const int64_t* input_ids, const int64_t* attention_mask, int B, int S, int* position_ids,
                   int* img_ord, int* seq_start, int* seq_len, int* eos_row, int* n_img, int* flags, void* stream);
 
+/* lr_token_plan with the image placeholder and position rule as parameters (LLaVA-v1.6 branch):
+ *   image_token_id >= 0: image positions are ids == image_token_id (LlavaNextModel.get_placeholder_mask,
+ *   transformers modeling_llava_next.py:419-441); < 0: negative ids as lr_token_plan.
+ *   position_mode LR_POS_FROM_MASK: as lr_token_plan; LR_POS_ARANGE: position_ids[b,s] = s - what LlamaModel uses
+ *   when the caller passes no position_ids, which is how the reference's llava branch calls it
+ *   (rw_model_general_preference.py:372-374). */
+#define LR_POS_FROM_MASK 0
+#define LR_POS_ARANGE 1
+int lr_token_plan_ex(const int64_t* input_ids, const int64_t* attention_mask, int B, int S, int64_t image_token_id,
+                     int position_mode, int* position_ids, int* img_ord, int* seq_start, int* seq_len, int* eos_row,
+                     int* n_img, int* flags, void* stream);
+
 /* per-sample plan record (int32 x 8) shared by lr_hd_gather_bf16 / lr_embed_scatter_bf16 / lr_skipca_* */
 #define LR_PLAN_STRIDE 8
 #define LR_PLAN_HCROP 0     /* image_sizes[b][0] / 336 */
@@ -129,6 +141,8 @@ int lr_token_plan(const int64_t* input_ids, const int64_t* attention_mask, int B
 #define LR_PLAN_CROP_BASE 2 /* index of the sample's global crop in the compacted crop list */
 #define LR_PLAN_ROW_BASE 3  /* first row of the sample in the concatenated image-token matrix */
 #define LR_PLAN_NV 4        /* number of image tokens of the sample */
+#define LR_PLAN_TOP 5       /* anyres only: feature rows removed at the top (= bottom) by unpad_image */
+#define LR_PLAN_LEFT 6      /* anyres only: feature columns removed at the left (= right) */
 
 /* HD feature transform: CLIP tokens [n_crops*577, 1024] (row 0 of each crop = CLS, skipped) ->
  * rows [sum N_v, 4096] in 'sub_glb' order with sub_GN newlines and the glb_GN separator.
@@ -140,6 +154,16 @@ int lr_hd_gather_bf16(const void* clip_tokens, const int* plan, const void* sub_
  * Replaces wte + index_put (modeling_phi3_v.py:230-231, 247-249). */
 int lr_embed_scatter_bf16(const int64_t* input_ids, const int* img_ord, const int* plan, const void* wte,
                           const void* img_proj, void* hidden, int ldh, int B, int S, int H, int V, void* stream);
+
+/* LLaVA-v1.6: hidden[b,s,:] = image position ? anyres-packed image feature : wte[id]. The packed order is
+ * [576 base-patch tokens | unpadded (grid_h*24 - 2*top) x (grid_w*24 - 2*left) grid, row-major, image_newline after each
+ * grid row]; plan record: HCROP/WCROP = grid_h/grid_w, CROP_BASE = first patch of the sample in `feat`, TOP, LEFT.
+ * feat = projector output for all 577 CLIP tokens of every patch (row stride ldf; the CLS rows are never read).
+ * Replaces pack_image_features + masked_scatter (transformers modeling_llava_next.py:277-343, 484-494) as called by
+ * the reference's llava branch (rw_model_general_preference.py:372-375). */
+int lr_anyres_embed_scatter_bf16(const int64_t* input_ids, const int* img_ord, const int* plan, const void* wte,
+                                 const void* feat, int ldf, const void* image_newline, void* hidden, int ldh, int B,
+                                 int S, int H, int V, void* stream);
 
 /* SkipCA, last-valid-token row only (the only row the reference consumes in eval, :420-421/439-444):
  * scores[b,j] = bf16(bf16(q_b . K_bj) / sqrt(H)), j < N_v(b).  kv = [K | V] rows of the concatenated image tokens. */

@@ -16,11 +16,12 @@ EPI_NONE, EPI_BIAS, EPI_BIAS_QUICKGELU, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_BIAS_RE
 GEMM_TCGEN05, GEMM_SIMT, GEMM_TCGEN05_PAIR, GEMM_TCGEN05_SINGLE = 0, 1, 2, 3
 ATTN_TCGEN05, ATTN_MMA_SYNC, ATTN_TCGEN05_SPLIT, ATTN_TCGEN05_2TILE = 0, 1, 2, 3
 PLAN_STRIDE = 8
-PLAN_HCROP, PLAN_WCROP, PLAN_CROP_BASE, PLAN_ROW_BASE, PLAN_NV = 0, 1, 2, 3, 4
+PLAN_HCROP, PLAN_WCROP, PLAN_CROP_BASE, PLAN_ROW_BASE, PLAN_NV, PLAN_TOP, PLAN_LEFT = 0, 1, 2, 3, 4, 5, 6
+POS_FROM_MASK, POS_ARANGE = 0, 1
 
 _ERR = {-1: "LR_ERR_BAD_ARG", -2: "LR_ERR_ALIGN", -3: "LR_ERR_NO_DRIVER", -4: "LR_ERR_UNSUPPORTED"}
 
-p, i32, f32 = C.c_void_p, C.c_int, C.c_float
+p, i32, f32, i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
 
 SIGNATURES = {
     "lr_version": ([], i32),
@@ -34,6 +35,8 @@ SIGNATURES = {
     "lr_attention_bf16": ([p, p, p, p, i32, i32, i32, i32, p, p, i32, i32, i32, f32, i32, p], i32),
     "lr_rope_su_bf16": ([p, i32, p, p, p, i32, i32, i32, p], i32),
     "lr_token_plan": ([p, p, i32, i32, p, p, p, p, p, p, p, p], i32),
+    "lr_token_plan_ex": ([p, p, i32, i32, i64, i32, p, p, p, p, p, p, p, p], i32),
+    "lr_anyres_embed_scatter_bf16": ([p, p, p, p, p, i32, p, p, i32, i32, i32, i32, i32, p], i32),
     "lr_hd_gather_bf16": ([p, p, p, p, p, i32, i32, p], i32),
     "lr_embed_scatter_bf16": ([p, p, p, p, p, p, i32, i32, i32, i32, i32, p], i32),
     "lr_skipca_scores": ([p, i32, p, i32, p, p, i32, i32, i32, p], i32),

@@ -12,7 +12,7 @@ from typing import Callable, Dict, Optional, Tuple
 
 import torch
 
-from .config import RewardConfig
+from .config import LlavaNextRewardConfig, RewardConfig
 
 
 def _load_file(path: str) -> Dict[str, torch.Tensor]:
@@ -77,6 +77,77 @@ def checkpoint_provider(cfg: RewardConfig, pretrain_dir: str, pm_path: Optional[
                         tensors[f"{mod}.{leaf}"] = v
                 if ft_projector and "img_projection" in k:
                     tensors["model.vision_embed_tokens.img_projection." + ".".join(k.split(".")[-2:])] = v
+
+    def get(name: str) -> torch.Tensor:
+        if name not in tensors:
+            raise KeyError(f"checkpoint is missing parameter {name!r}")
+        return tensors[name]
+
+    return cfg, get
+
+
+def _canonical_llava_name(k: str) -> str:
+    """Any era of transformers LlavaNext state_dict name -> the 4.50 names the reference was written against
+    (`language_model.model.*`, `vision_tower.*`, `multi_modal_projector.*`, `image_newline`)."""
+    if k.startswith("model.language_model."):
+        return "language_model.model." + k[len("model.language_model."):]
+    if k.startswith(("model.vision_tower.", "model.multi_modal_projector.", "model.image_newline")):
+        return k[len("model."):]
+    return k
+
+
+def llava_checkpoint_provider(cfg: LlavaNextRewardConfig, pretrain_dir: str, pm_path: Optional[str],
+                              ft_projector: bool = False):
+    """HF llava-v1.6-vicuna checkpoint directory + the reference's save_model_lora layout for the llava branch
+    (key selection of reference eval/reward_adaptor_loader.py:124-148) -> provider with synth.llava_param_specs names."""
+    if not os.path.isdir(pretrain_dir):
+        raise FileNotFoundError(f"args.pretrain={pretrain_dir!r} is not a local directory (no network access: "
+                                "hub ids cannot be resolved) - use 'synthetic' for random-init weights")
+    with open(os.path.join(pretrain_dir, "config.json")) as f:
+        hf = json.load(f)
+    t = hf.get("text_config", {})
+    cfg.vocab_size = t.get("vocab_size", cfg.vocab_size)
+    cfg.hidden_size = t.get("hidden_size", cfg.hidden_size)
+    cfg.intermediate_size = t.get("intermediate_size", cfg.intermediate_size)
+    cfg.num_layers = t.get("num_hidden_layers", cfg.num_layers)
+    cfg.num_heads = t.get("num_attention_heads", cfg.num_heads)
+    if t.get("num_key_value_heads", cfg.num_heads) != cfg.num_heads:
+        raise NotImplementedError("grouped-query attention (e.g. llava-v1.6-mistral): the reference's LoRA config and "
+                                  "training script target the Vicuna (MHA) checkpoints only")
+    cfg.rms_eps = t.get("rms_norm_eps", cfg.rms_eps)
+    cfg.rope_theta = t.get("rope_theta", cfg.rope_theta)
+    cfg.image_token_id = hf.get("image_token_index", hf.get("image_token_id", cfg.image_token_id))
+    cfg.image_grid_pinpoints = hf.get("image_grid_pinpoints", cfg.image_grid_pinpoints)
+    tensors: Dict[str, torch.Tensor] = {}
+    files = sorted(glob.glob(os.path.join(pretrain_dir, "*.safetensors"))) or \
+        sorted(glob.glob(os.path.join(pretrain_dir, "pytorch_model*.bin")))
+    if not files:
+        raise FileNotFoundError(f"no *.safetensors / pytorch_model*.bin under {pretrain_dir}")
+    for fpath in files:
+        tensors.update({_canonical_llava_name(k): v for k, v in _load_file(fpath).items()})
+    cfg.use_lora = False
+    if pm_path:
+        for cand in ("adapter_model.safetensors", "adapter_model.bin"):
+            p = os.path.join(pm_path, "lora", cand)
+            if os.path.exists(p):
+                for k, v in _load_file(p).items():
+                    k = _canonical_llava_name(k.replace("base_model.model.", "", 1).replace(".default", ""))
+                    tensors[k] = v
+                cfg.use_lora = True
+                acfg = os.path.join(pm_path, "lora", "adapter_config.json")
+                if os.path.exists(acfg):
+                    with open(acfg) as f:
+                        a = json.load(f)
+                    cfg.lora_rank, cfg.lora_alpha = int(a.get("r", cfg.lora_rank)), float(a.get("lora_alpha", cfg.lora_alpha))
+                break
+        heads = os.path.join(pm_path, "pytorch_model.bin")
+        if os.path.exists(heads):
+            sd = torch.load(heads, map_location="cpu", weights_only=True)
+            for k, v in sd.items():
+                if "value_head" in k:
+                    tensors["value_head." + k.split(".")[-1]] = v
+                if ft_projector and "multi_modal_projector" in k:
+                    tensors["multi_modal_projector." + ".".join(k.split(".")[-2:])] = v
 
     def get(name: str) -> torch.Tensor:
         if name not in tensors:

@@ -270,5 +270,7 @@ extern "C" int lr_attention_bf16(const void* q, const void* k, const void* v, vo
     return launch_attn<96, false>(q, k, v, o, ld_qkv, ld_o, n_seq, rows_per_seq, seq_start, seq_len, n_heads, scale, s);
   if (head_dim == 64 && causal)
     return launch_attn<64, true>(q, k, v, o, ld_qkv, ld_o, n_seq, rows_per_seq, seq_start, seq_len, n_heads, scale, s);
+  if (head_dim == 128 && causal)  // Llama decoder of the LLaVA-v1.6 branch
+    return launch_attn<128, true>(q, k, v, o, ld_qkv, ld_o, n_seq, rows_per_seq, seq_start, seq_len, n_heads, scale, s);
   return LR_ERR_BAD_ARG;
 }

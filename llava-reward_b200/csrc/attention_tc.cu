@@ -76,8 +76,11 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // the two softmax warpgroups of an SM naturally and hides each CTA's prologue/epilogue behind the other's main loop.
 template <int HD, int NT>
 struct AttnTcCfg {
-  static constexpr int kStages = NT == 2 ? 2 : 1;
-  static constexpr int kTmemCols = NT == 2 ? 512 : 256;
+  // head_dim 128 (Llama decoder of the LLaVA-v1.6 branch): S (128) + O (128 + 16) columns exceed 256 and one CTA
+  // needs 136 KB of smem, so it runs one CTA per SM with the 2-stage K/V ring and all 512 TMEM columns.
+  static constexpr bool kOnePerSm = NT == 2 || HD > 96;
+  static constexpr int kStages = kOnePerSm ? 2 : 1;
+  static constexpr int kTmemCols = kOnePerSm ? 512 : 256;
   static constexpr int kAtoms = HD / 32;
   static constexpr int kTileBytes = kAtoms * kAtomBytes;         // one Q / K tile, and the TMA-loaded part of a V tile
   static constexpr int kVTileBytes = (kAtoms + 1) * kAtomBytes;  // V tile + one atom of ones (row sums via the MMA)
@@ -92,7 +95,7 @@ struct AttnTcCfg {
 // TMA fills) = ~2700 cycles at 128 B/clk, which - not MUFU, not latency - bounds the iteration (r01 finding; the next
 // step is P through TMEM, aliasing S, as the A operand of the PV MMA).
 template <int HD, bool CAUSAL, int SPLIT, int NT>
-__global__ void __launch_bounds__(128 + 128 * NT * SPLIT, NT == 2 ? 1 : 2)
+__global__ void __launch_bounds__(128 + 128 * NT * SPLIT, AttnTcCfg<HD, NT>::kOnePerSm ? 1 : 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o, int ld_o, int rows_per_seq,
                const int* __restrict__ seq_start, const int* __restrict__ seq_len, int q_col0, int k_col0, int v_col0,
                float scale_log2) {
@@ -530,6 +533,13 @@ int attention_tc(const void* q, const void* k, const void* v, void* o, int ld_qk
   }
   LR_ATTN_CASE(64, false)
   LR_ATTN_CASE(96, true)
+#undef LR_ATTN_CASE
+  if (head_dim == 128 && causal) {  // only the one-tile configuration fits (smem / TMEM, see AttnTcCfg)
+    if (split != 3) return LR_ERR_BAD_ARG;
+    return launch_attn_tc<128, true, 1, 1>(q, total_rows, ld_qkv, 0, int(kd), int(vd), o, ld_o, n_seq, rows_per_seq,
+                                           seq_start, seq_len, n_heads, scale, s);
+  }
+#define LR_ATTN_CASE(a, b)
 #undef LR_ATTN_CASE
   return LR_ERR_BAD_ARG;
 }

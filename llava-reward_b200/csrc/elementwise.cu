@@ -8,7 +8,8 @@ namespace lr {
 __global__ void __launch_bounds__(256)
 token_plan_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mask, int S, int* __restrict__ pos,
                   int* __restrict__ img_ord, int* __restrict__ seq_start, int* __restrict__ seq_len,
-                  int* __restrict__ eos_row, int* __restrict__ n_img, int* __restrict__ flags) {
+                  int* __restrict__ eos_row, int* __restrict__ n_img, int* __restrict__ flags,
+                  int64_t image_token_id, int position_mode) {
   __shared__ int wsum_m[8], wsum_i[8];
   __shared__ int s_first, s_last;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -24,7 +25,8 @@ token_plan_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ m
     const bool in = s < S;
     const int64_t id = in ? ids[size_t(b) * S + s] : 0;
     const bool m = in && mask[size_t(b) * S + s] != 0;
-    const bool im = in && id < 0 && id > -1000000000LL;
+    // image placeholders: negative ids (Phi-3-V processor) or one dedicated token id (LlavaNext processor)
+    const bool im = in && (image_token_id >= 0 ? id == image_token_id : (id < 0 && id > -1000000000LL));
     const unsigned bm = __ballot_sync(0xffffffffu, m), bi = __ballot_sync(0xffffffffu, im);
     const unsigned lt = (1u << lane) - 1u;
     if (lane == 0) {
@@ -44,7 +46,7 @@ token_plan_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ m
     }
     if (in) {
       const int incl = run_m + pre_m + __popc(bm & lt) + (m ? 1 : 0);
-      pos[size_t(b) * S + s] = m ? incl - 1 : 1;
+      pos[size_t(b) * S + s] = position_mode == LR_POS_ARANGE ? s : (m ? incl - 1 : 1);
       img_ord[size_t(b) * S + s] = im ? run_i + pre_i + __popc(bi & lt) : -1;
       if (m) {
         my_first = min(my_first, s);
@@ -171,6 +173,46 @@ embed_scatter_kernel(const int64_t* __restrict__ ids, const int* __restrict__ im
   for (int c = threadIdx.x * 8; c < H; c += blockDim.x * 8) stg128(dst + c, ldg128(src + c));
 }
 
+// ---------------------------------------------------------------- LlavaNext: embedding gather + anyres pack in one pass
+// Token `ord` of sample b's image block: ord < 576 -> base patch token; else the unpadded grid in row-major order with
+// one image_newline after every grid row (pack_image_features, modeling_llava_next.py:277-343). `feat` holds the
+// projector output for ALL 577 CLIP tokens of every patch (row 0 of a patch = CLS, never referenced).
+__global__ void __launch_bounds__(128)
+anyres_embed_scatter_kernel(const int64_t* __restrict__ ids, const int* __restrict__ img_ord,
+                            const int* __restrict__ plan, const bf16* __restrict__ wte, const bf16* __restrict__ feat,
+                            int ldf, const bf16* __restrict__ newline, bf16* __restrict__ hidden, int ldh, int S, int H,
+                            int V) {
+  constexpr int T = 577, SIDE = 24;
+  const size_t tok = blockIdx.x;
+  const int b = int(tok / S);
+  const int ord = img_ord[tok];
+  const bf16* src;
+  if (ord >= 0) {
+    const int* pl = plan + b * LR_PLAN_STRIDE;
+    const int gw = pl[LR_PLAN_WCROP], patch_base = pl[LR_PLAN_CROP_BASE];
+    const int top = pl[LR_PLAN_TOP], left = pl[LR_PLAN_LEFT];
+    if (ord < SIDE * SIDE) {
+      src = feat + (size_t(patch_base) * T + 1 + ord) * ldf;
+    } else {
+      const int keep_w = gw * SIDE - 2 * left;
+      const int r = ord - SIDE * SIDE, y = r / (keep_w + 1), x = r % (keep_w + 1);
+      if (x == keep_w) {
+        src = newline;
+      } else {
+        const int Y = y + top, X = x + left;
+        const int patch = 1 + (Y / SIDE) * gw + X / SIDE, t = (Y % SIDE) * SIDE + X % SIDE;
+        src = feat + (size_t(patch_base + patch) * T + 1 + t) * ldf;
+      }
+    }
+  } else {
+    int64_t id = ids[tok];
+    id = id < 0 ? 0 : (id > V - 1 ? V - 1 : id);
+    src = wte + size_t(id) * H;
+  }
+  bf16* dst = hidden + tok * ldh;
+  for (int c = threadIdx.x * 8; c < H; c += blockDim.x * 8) stg128(dst + c, ldg128(src + c));
+}
+
 }  // namespace lr
 
 using namespace lr;
@@ -182,7 +224,33 @@ extern "C" int lr_token_plan(const int64_t* input_ids, const int64_t* attention_
   LR_CHECK_ARG(input_ids && attention_mask && position_ids && img_ord && seq_start && seq_len && eos_row && n_img &&
                flags && B > 0 && S > 0);
   token_plan_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      input_ids, attention_mask, S, position_ids, img_ord, seq_start, seq_len, eos_row, n_img, flags);
+      input_ids, attention_mask, S, position_ids, img_ord, seq_start, seq_len, eos_row, n_img, flags, -1,
+      LR_POS_FROM_MASK);
+  return lr_launch_status();
+}
+
+extern "C" int lr_token_plan_ex(const int64_t* input_ids, const int64_t* attention_mask, int B, int S,
+                                int64_t image_token_id, int position_mode, int* position_ids, int* img_ord,
+                                int* seq_start, int* seq_len, int* eos_row, int* n_img, int* flags, void* stream) {
+  LR_CHECK_ARG(input_ids && attention_mask && position_ids && img_ord && seq_start && seq_len && eos_row && n_img &&
+               flags && B > 0 && S > 0);
+  LR_CHECK_ARG(position_mode == LR_POS_FROM_MASK || position_mode == LR_POS_ARANGE);
+  token_plan_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      input_ids, attention_mask, S, position_ids, img_ord, seq_start, seq_len, eos_row, n_img, flags, image_token_id,
+      position_mode);
+  return lr_launch_status();
+}
+
+extern "C" int lr_anyres_embed_scatter_bf16(const int64_t* input_ids, const int* img_ord, const int* plan,
+                                            const void* wte, const void* feat, int ldf, const void* image_newline,
+                                            void* hidden, int ldh, int B, int S, int H, int V, void* stream) {
+  LR_CHECK_ARG(input_ids && img_ord && plan && wte && feat && image_newline && hidden && B > 0 && S > 0 && H > 0 &&
+               H % 8 == 0 && V > 0 && ldf >= H);
+  if ((ldh % 8) || (ldf % 8) || !aligned16(wte) || !aligned16(feat) || !aligned16(image_newline) || !aligned16(hidden))
+    return LR_ERR_ALIGN;
+  anyres_embed_scatter_kernel<<<B * S, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      input_ids, img_ord, plan, reinterpret_cast<const bf16*>(wte), reinterpret_cast<const bf16*>(feat), ldf,
+      reinterpret_cast<const bf16*>(image_newline), reinterpret_cast<bf16*>(hidden), ldh, S, H, V);
   return lr_launch_status();
 }
 

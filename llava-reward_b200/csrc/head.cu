@@ -170,12 +170,14 @@ extern "C" int lr_skipca_scores(const void* q, int ldq, const void* kv, int ldkv
 extern "C" int lr_skipca_head(const float* scores, const void* kv, int ldkv, const int* plan, const void* x, int ldx,
                               const void* ca_ln_w, const void* value_head_w, void* reward, int B, int H, int max_nv,
                               int vhd, float eps, void* stream) {
-  LR_CHECK_ARG(x && value_head_w && reward && B > 0 && H > 0 && H % 8 == 0 && (H / 8) * 2 <= kHeadThreads &&
-               vhd > 0);
+  // with cross-attention two thread groups split the P.V rows (H <= 3072); the value-head-only form needs one
+  // thread per 8 columns (H <= 6144: the 4096 / 5120 wide Vicuna decoders of the LLaVA-v1.6 branch)
+  LR_CHECK_ARG(x && value_head_w && reward && B > 0 && H > 0 && H % 8 == 0 && vhd > 0 &&
+               (H / 8) * (scores ? 2 : 1) <= kHeadThreads);
   if (scores) LR_CHECK_ARG(kv && plan && ca_ln_w && max_nv > 0 && max_nv <= kHeadMaxNv);
   if ((ldx % 8) || !aligned16(x) || !aligned16(value_head_w) || (scores && ((ldkv % 8) || !aligned16(kv))))
     return LR_ERR_ALIGN;
-  skipca_head_kernel<<<B, kHeadThreads, 2 * H * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+  skipca_head_kernel<<<B, kHeadThreads, scores ? 2 * H * sizeof(float) : 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       scores, reinterpret_cast<const bf16*>(kv), ldkv, plan, reinterpret_cast<const bf16*>(x), ldx,
       reinterpret_cast<const bf16*>(ca_ln_w), reinterpret_cast<const bf16*>(value_head_w),
       reinterpret_cast<bf16*>(reward), H, max_nv, vhd, eps);

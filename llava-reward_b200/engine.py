@@ -66,6 +66,80 @@ class RewardEngine:
         if self.taps is not None:
             self.taps[name] = t.clone()
 
+    def _clip_tower(self, pix: torch.Tensor, crop_idx: torch.Tensor, n_crops: int) -> torch.Tensor:
+        """CLIP ViT-L/14-336 up to encoder layer `clip_layers` on the crops pix.view(-1,3,336,336)[crop_idx]
+        -> tokens [n_crops*577, 1024] (row 0 of every crop = CLS)."""
+        cfg, w = self.cfg, self.w
+        D, DI, T = cfg.clip_hidden, cfg.clip_intermediate, cfg.clip_tokens
+        Mv = n_crops * T
+        a0 = self.buf("clip_a0", (n_crops * (T - 1), 640))
+        ops.clip_im2col(pix, crop_idx, a0, n_crops)
+        patch = self.buf("clip_patch", (n_crops * (T - 1), D))
+        self._gemm(a0, w.clip["patch_w"], patch, n_crops * (T - 1), D, 640)
+        x = self.buf("clip_x", (Mv, D))
+        ops.clip_embed_ln(patch, w.clip["cls"], w.clip["pos"], w.clip["pre_w"], w.clip["pre_b"], x, n_crops, cfg.clip_eps)
+        self._tap("clip_embed", x)
+        hn = self.buf("clip_hn", (Mv, D))
+        qkv = self.buf("clip_qkv", (Mv, 3 * D))
+        ao = self.buf("clip_ao", (Mv, D))
+        ff = self.buf("clip_ff", (Mv, DI))
+        scale = cfg.clip_head_dim ** -0.5
+        for li, lw in enumerate(w.clip_layers):
+            ops.layernorm(x, lw["ln1_w"], lw["ln1_b"], hn, Mv, D, cfg.clip_eps)
+            self._gemm(hn, lw["qkv_w"], qkv, Mv, 3 * D, D, L.EPI_BIAS, lw["qkv_b"])
+            ops.attention(qkv, qkv[:, D:], qkv[:, 2 * D:], ao, 3 * D, D, n_crops, T, None, None, cfg.clip_heads,
+                          cfg.clip_head_dim, False, scale, self.attn_impl)
+            self._gemm(ao, lw["out_w"], x, Mv, D, D, L.EPI_BIAS_RESIDUAL, lw["out_b"], x)
+            ops.layernorm(x, lw["ln2_w"], lw["ln2_b"], hn, Mv, D, cfg.clip_eps)
+            self._gemm(hn, lw["fc1_w"], ff, Mv, DI, D, L.EPI_BIAS_QUICKGELU, lw["fc1_b"])
+            self._gemm(ff, lw["fc2_w"], x, Mv, D, DI, L.EPI_BIAS_RESIDUAL, lw["fc2_b"], x)
+            if li == 0:
+                self._tap("clip_layer0", x)
+        self._tap("clip_out", x)
+        return x
+
+    def _decoder(self, hid, B: int, S: int, pos, seq_start, seq_len, cos_tab, sin_tab) -> None:
+        """Pre-norm decoder layers in place on hid [B*S, H] (Phi3DecoderLayer, modeling_phi3_v.py:1130-1205; the
+        Llama layers of the LLaVA-v1.6 branch have the same dataflow). LoRA ranks come from the packed weights:
+        the K-extension of a fused projection is the stack of its branches' ranks (weights.py)."""
+        cfg, w = self.cfg, self.w
+        M, H, I = B * S, cfg.hidden_size, cfg.intermediate_size
+        lw0 = w.layers[0] if w.layers else {}
+        rq, ro, rg, rd = (lw0[k].shape[0] if k in lw0 else 0 for k in ("qkv_a", "o_a", "gu_a", "dn_a"))
+        xn = self.buf("dec_xn", (M, H + max(rq, rg)))
+        dqkv = self.buf("dec_qkv", (M, 3 * H))
+        dao = self.buf("dec_ao", (M, H + ro))
+        gg = self.buf("dec_g", (M, I + rd))
+        att_scale = 1.0 / math.sqrt(cfg.head_dim)
+        nh, hd = cfg.num_heads, cfg.head_dim
+        for li, lw in enumerate(w.layers):
+            ops.rmsnorm(hid, lw["in_ln"], xn, M, H, cfg.rms_eps)
+            if rq:
+                self._gemm(xn, lw["qkv_a"], xn[:, H:], M, rq, H)
+            # qkv projection with RoPE in the epilogue (q/k rows are head-interleaved, see weights.py)
+            ops.gemm_rope(xn, lw["qkv_w"], dqkv, M, 3 * H, H + rq, pos, cos_tab, sin_tab, 2 * H, hd,
+                          L.GEMM_SIMT if self.gemm_impl == L.GEMM_SIMT else L.GEMM_TCGEN05)
+            ops.attention(dqkv, dqkv[:, H:], dqkv[:, 2 * H:], dao, 3 * H, H + ro, B, S, seq_start, seq_len, nh, hd,
+                          True, att_scale, self.attn_impl)
+            if ro:
+                self._gemm(dao, lw["o_a"], dao[:, H:], M, ro, H)
+            self._gemm(dao, lw["o_w"], hid, M, H, H + ro, L.EPI_RESIDUAL, None, hid)
+            ops.rmsnorm(hid, lw["post_ln"], xn, M, H, cfg.rms_eps)
+            if rg:
+                self._gemm(xn, lw["gu_a"], xn[:, H:], M, rg, H)
+            if self.profile is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
+            self._gemm(xn, lw["gu_w"], gg, M, 2 * I, H + rg, L.EPI_SWIGLU)
+            if self.profile is not None:
+                ev[1].record()
+                self.profile["gate_up"].append(ev)
+            if rd:
+                self._gemm(gg, lw["dn_a"], gg[:, I:], M, rd, I)
+            self._gemm(gg, lw["dn_w"], hid, M, H, I + rd, L.EPI_RESIDUAL, None, hid)
+            if self.taps is not None:
+                self._tap(f"hidden_{li}", hid)
+
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, pixel_values: torch.Tensor,
@@ -74,7 +148,7 @@ class RewardEngine:
         bf = torch.bfloat16
         launches0 = L.launch_count()
         B, S = input_ids.shape
-        H, I, r = cfg.hidden_size, cfg.intermediate_size, (cfg.lora_rank if cfg.use_lora else 0)
+        H = cfg.hidden_size
         ids = input_ids.to(dev, torch.int64).contiguous()
         mask = attention_mask.to(dev, torch.int64).contiguous()
         pix = pixel_values.to(dev, torch.float32).contiguous()
@@ -121,32 +195,8 @@ class RewardEngine:
         crop_idx = dev_plan[B * L.PLAN_STRIDE:]
 
         # 2. CLIP tower on the real crops only
-        D, DI, T = cfg.clip_hidden, cfg.clip_intermediate, cfg.clip_tokens
-        Mv = n_crops * T
-        a0 = self.buf("clip_a0", (n_crops * (T - 1), 640))
-        ops.clip_im2col(pix, crop_idx, a0, n_crops)
-        patch = self.buf("clip_patch", (n_crops * (T - 1), D))
-        self._gemm(a0, w.clip["patch_w"], patch, n_crops * (T - 1), D, 640)
-        x = self.buf("clip_x", (Mv, D))
-        ops.clip_embed_ln(patch, w.clip["cls"], w.clip["pos"], w.clip["pre_w"], w.clip["pre_b"], x, n_crops, cfg.clip_eps)
-        self._tap("clip_embed", x)
-        hn = self.buf("clip_hn", (Mv, D))
-        qkv = self.buf("clip_qkv", (Mv, 3 * D))
-        ao = self.buf("clip_ao", (Mv, D))
-        ff = self.buf("clip_ff", (Mv, DI))
-        scale = cfg.clip_head_dim ** -0.5
-        for li, lw in enumerate(w.clip_layers):
-            ops.layernorm(x, lw["ln1_w"], lw["ln1_b"], hn, Mv, D, cfg.clip_eps)
-            self._gemm(hn, lw["qkv_w"], qkv, Mv, 3 * D, D, L.EPI_BIAS, lw["qkv_b"])
-            ops.attention(qkv, qkv[:, D:], qkv[:, 2 * D:], ao, 3 * D, D, n_crops, T, None, None, cfg.clip_heads,
-                          cfg.clip_head_dim, False, scale, self.attn_impl)
-            self._gemm(ao, lw["out_w"], x, Mv, D, D, L.EPI_BIAS_RESIDUAL, lw["out_b"], x)
-            ops.layernorm(x, lw["ln2_w"], lw["ln2_b"], hn, Mv, D, cfg.clip_eps)
-            self._gemm(hn, lw["fc1_w"], ff, Mv, DI, D, L.EPI_BIAS_QUICKGELU, lw["fc1_b"])
-            self._gemm(ff, lw["fc2_w"], x, Mv, D, DI, L.EPI_BIAS_RESIDUAL, lw["fc2_b"], x)
-            if li == 0:
-                self._tap("clip_layer0", x)
-        self._tap("clip_out", x)
+        x = self._clip_tower(pix, crop_idx, n_crops)
+        D = cfg.clip_hidden
 
         # 3. HD transform gather + projector
         rows = self.buf("hd_rows", (sum_nv, 4 * D))
@@ -163,41 +213,8 @@ class RewardEngine:
         self._tap("inputs_embeds", hid)
 
         # 5. decoder
-        xn = self.buf("dec_xn", (M, H + r))
-        dqkv = self.buf("dec_qkv", (M, 3 * H))
-        dao = self.buf("dec_ao", (M, H + r))
-        gg = self.buf("dec_g", (M, I + r))
         cos_tab, sin_tab = self.rope_tables(max(S, 2), max_len > cfg.original_max_position_embeddings)
-        att_scale = 1.0 / math.sqrt(cfg.head_dim)
-        nh, hd = cfg.num_heads, cfg.head_dim
-        for li, lw in enumerate(w.layers):
-            ops.rmsnorm(hid, lw["in_ln"], xn, M, H, cfg.rms_eps)
-            if r:
-                self._gemm(xn, lw["qkv_a"], xn[:, H:], M, r, H)
-            if self.gemm_impl == L.GEMM_SIMT:
-                ops.gemm_rope(xn, lw["qkv_w"], dqkv, M, 3 * H, H + r, pos, cos_tab, sin_tab, 2 * H, hd, L.GEMM_SIMT)
-            else:  # qkv projection with su-RoPE in the epilogue (q/k rows are head-interleaved, see weights.py)
-                ops.gemm_rope(xn, lw["qkv_w"], dqkv, M, 3 * H, H + r, pos, cos_tab, sin_tab, 2 * H, hd)
-            ops.attention(dqkv, dqkv[:, H:], dqkv[:, 2 * H:], dao, 3 * H, H + r, B, S, seq_start, seq_len, nh, hd,
-                          True, att_scale, self.attn_impl)
-            if r:
-                self._gemm(dao, lw["o_a"], dao[:, H:], M, r, H)
-            self._gemm(dao, lw["o_w"], hid, M, H, H + r, L.EPI_RESIDUAL, None, hid)
-            ops.rmsnorm(hid, lw["post_ln"], xn, M, H, cfg.rms_eps)
-            if r:
-                self._gemm(xn, lw["gu_a"], xn[:, H:], M, r, H)
-            if self.profile is not None:
-                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                ev[0].record()
-            self._gemm(xn, lw["gu_w"], gg, M, 2 * I, H + r, L.EPI_SWIGLU)
-            if self.profile is not None:
-                ev[1].record()
-                self.profile["gate_up"].append(ev)
-            if r:
-                self._gemm(gg, lw["dn_a"], gg[:, I:], M, r, I)
-            self._gemm(gg, lw["dn_w"], hid, M, H, I + r, L.EPI_RESIDUAL, None, hid)
-            if self.taps is not None:
-                self._tap(f"hidden_{li}", hid)
+        self._decoder(hid, B, S, pos, seq_start, seq_len, cos_tab, sin_tab)
 
         # 6. reward head on the last valid token of each sample
         xe = self.buf("x_eos", (max(B, 1), H))
@@ -227,3 +244,106 @@ class RewardEngine:
         ops.preference(chosen.to(torch.bfloat16).contiguous(), reject.to(torch.bfloat16).contiguous(), prob, n,
                        chosen.shape[1], cfg.is_general_preference, cfg.general_preference_tau)
         return prob
+
+
+class LlavaNextRewardEngine(RewardEngine):
+    """The reference's llava branch (rw_model_general_preference.py:372-375 -> LlavaNextForConditionalGeneration.forward
+    with output_hidden_states, value head on the last valid token :407-448) as C-ABI launches:
+    CLIP (all real patches) -> projector on every CLIP token -> [embedding gather + anyres unpad/newline pack] in one
+    kernel -> Llama decoder (same kernels as the Phi-3 loop: fused q/k/v + RoPE epilogue, tcgen05 attention hd 128,
+    SwiGLU epilogue, LoRA K-extension) -> final RMSNorm on the last valid row -> value head.
+    The reference also runs the 32064-wide lm_head over every token and discards it; that GEMM is not executed."""
+
+    def rope_tables(self, n_pos: int, long: bool = False):
+        """cos/sin [n_pos, 64] bf16 of LlamaRotaryEmbedding (default rope; transformers modeling_llama.py:124-135)."""
+        key = (n_pos, False)
+        if key not in self._rope:
+            cfg = self.cfg
+            expo = torch.arange(0, cfg.head_dim, 2, dtype=torch.int64, device=self.device).float() / cfg.head_dim
+            inv_freq = 1.0 / (cfg.rope_theta ** expo)
+            ang = torch.arange(n_pos, dtype=torch.int64, device=self.device).float()[:, None] * inv_freq[None, :]
+            self._rope = {key: (ang.cos().to(torch.bfloat16).contiguous(), ang.sin().to(torch.bfloat16).contiguous())}
+        return self._rope[key]
+
+    @torch.no_grad()
+    def forward(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, pixel_values: torch.Tensor,
+                image_sizes) -> torch.Tensor:
+        from .config import anyres_geometry
+
+        cfg, w, dev = self.cfg, self.w, self.device
+        launches0 = L.launch_count()
+        B, S = input_ids.shape
+        H = cfg.hidden_size
+        ids = input_ids.to(dev, torch.int64).contiguous()
+        mask = attention_mask.to(dev, torch.int64).contiguous()
+        pix = pixel_values.to(dev, torch.float32).contiguous()
+        if pix.dim() != 5 or tuple(pix.shape[2:]) != (3, cfg.image_size, cfg.image_size):
+            # the 4-d "list of patches" form of get_image_features (modeling_llava_next.py:390-392) is not produced
+            # by the reference's collate_fn (reward_dataset.py:334-346)
+            raise ValueError(f"pixel_values of shape {tuple(pix.shape)}, expect [B, patches, 3, 336, 336]")
+        n_slots = pix.shape[1]
+
+        # 1. token plan (image positions = image_token_id, positions = arange) + ONE small D2H read
+        M = B * S
+        pos = self.buf("pos", (M,), torch.int32)
+        img_ord = self.buf("img_ord", (M,), torch.int32)
+        meta = self.buf("meta", (4 * B + 1,), torch.int32)
+        seq_start, seq_len, eos_row, n_img, flags = meta[:B], meta[B:2 * B], meta[2 * B:3 * B], meta[3 * B:4 * B], meta[4 * B:]
+        flags.zero_()
+        ops.token_plan_ex(ids, mask, B, S, cfg.image_token_id, L.POS_ARANGE, pos, img_ord, seq_start, seq_len, eos_row,
+                          n_img, flags)
+        meta_h = meta.cpu().numpy()
+        sizes_h = image_sizes.cpu().numpy() if torch.is_tensor(image_sizes) else np.asarray(image_sizes)
+        sizes_h = sizes_h.reshape(B, 2).astype(np.int64)
+        if meta_h[4 * B] & 1:
+            raise ValueError("attention_mask rows must be one contiguous run of ones (left/right padding)")
+        plan_h = np.zeros((B, L.PLAN_STRIDE), dtype=np.int32)
+        patch_src, patch_base, row_base = [], 0, 0
+        for b in range(B):
+            g = anyres_geometry((int(sizes_h[b, 0]), int(sizes_h[b, 1])), cfg.image_grid_pinpoints, cfg.image_size,
+                                cfg.patch)
+            if g["n_patches"] > n_slots:
+                raise ValueError(f"image_sizes[{b}] needs {g['n_patches']} patches but pixel_values has {n_slots}")
+            if int(meta_h[3 * B + b]) != g["n_tokens"]:
+                # transformers checks the batch total only (modeling_llava_next.py:437-441) and would shift features
+                # across samples on a per-sample mismatch; that is never a valid input, so it is an error here
+                raise ValueError(f"Image features and image tokens do not match, sample {b}: tokens: "
+                                 f"{int(meta_h[3 * B + b])}, features: {g['n_tokens']}")
+            plan_h[b, :7] = (g["grid_h"], g["grid_w"], patch_base, row_base, g["n_tokens"], g["top"], g["left"])
+            patch_src.extend(range(b * n_slots, b * n_slots + g["n_patches"]))
+            patch_base += g["n_patches"]
+            row_base += g["n_tokens"]
+        n_patches = patch_base
+        host = torch.from_numpy(np.concatenate([plan_h.reshape(-1), np.asarray(patch_src, dtype=np.int32)]))
+        dev_plan = self.buf("plan", (host.numel(),), torch.int32)
+        dev_plan.copy_(host.pin_memory() if dev.type == "cuda" else host, non_blocking=True)
+        plan = dev_plan[: B * L.PLAN_STRIDE]
+        patch_idx = dev_plan[B * L.PLAN_STRIDE:]
+
+        # 2. CLIP tower, 3. projector on all 577 tokens of every patch (the CLS rows are computed and never read:
+        #    0.17 % extra rows instead of a compaction pass)
+        x = self._clip_tower(pix, patch_idx, n_patches)
+        Mv = n_patches * cfg.clip_tokens
+        p1 = self.buf("proj1", (Mv, H))
+        self._gemm(x, w.proj["p0_w"], p1, Mv, H, cfg.clip_hidden, L.EPI_BIAS_GELU, w.proj["p0_b"])
+        feat = self.buf("img_proj", (Mv, H))
+        self._gemm(p1, w.proj["p2_w"], feat, Mv, H, H, L.EPI_BIAS, w.proj["p2_b"])
+        self._tap("projector_out", feat)
+
+        # 4. embeddings + anyres pack (unpad, image_newline) in one pass
+        hid = self.buf("hidden", (M, H))
+        ops.anyres_embed_scatter(ids, img_ord, plan, w.embed, feat, w.proj["newline"], hid, B, S, H, cfg.vocab_size)
+        self._tap("inputs_embeds", hid)
+
+        # 5. decoder
+        cos_tab, sin_tab = self.rope_tables(max(S, 2))
+        self._decoder(hid, B, S, pos, seq_start, seq_len, cos_tab, sin_tab)
+
+        # 6. final norm on the last valid row + value head
+        xe = self.buf("x_eos", (max(B, 1), H))
+        ops.rmsnorm(hid, w.head["norm"], xe, B, H, cfg.rms_eps, row_index=eos_row)
+        self._tap("last_hidden_eos", xe)
+        reward = torch.empty(B, cfg.vhd, dtype=torch.bfloat16, device=dev)
+        ops.skipca_head(None, None, None, xe, None, w.head["vh"], reward, B, H, 0, cfg.vhd, cfg.rms_eps)
+        self.launches = L.launch_count() - launches0
+        return reward

@@ -11,9 +11,9 @@ from typing import Callable, Optional
 import torch
 
 from . import _lib as L
-from .config import RewardConfig
-from .engine import RewardEngine
-from .weights import pack_weights
+from .config import LlavaNextRewardConfig, RewardConfig
+from .engine import LlavaNextRewardEngine, RewardEngine
+from .weights import pack_weights, pack_weights_llava
 
 
 class B200RewardModel:
@@ -44,10 +44,12 @@ class B200RewardModel:
         if hasattr(self._provider, "device"):
             self._provider.device = device  # synthetic weights are generated directly on the GPU
         with torch.cuda.device(device):
-            weights = pack_weights(self.config, self._provider, device=device)
-            self.engine = RewardEngine(self.config, weights, device=device)
+            self.engine = self._build_engine(device)
         self.device = device
         return self
+
+    def _build_engine(self, device):
+        return RewardEngine(self.config, pack_weights(self.config, self._provider, device=device), device=device)
 
     def cuda(self, device=None):
         return self.to("cuda" if device is None else device)
@@ -89,6 +91,43 @@ class B200RewardModel:
             raise NotImplementedError("training-mode gather (values[:, -1]) is not part of the scoring path")
         with torch.cuda.device(self.device):
             reward = self.engine.forward(input_ids, attention_mask, pixel_values, image_sizes)
+        return reward, None
+
+    __call__ = custom_forward
+
+
+class B200LlavaNextRewardModel(B200RewardModel):
+    """model_type 'llava' (LLaVA-v1.6 Vicuna): the caller passes the processor's BatchFeature as `inputs_batch`
+    (reference eval/batch_inference_rm_llava.py:86-87, rw_model_general_preference.py:372-375)."""
+    model_type = "llava"
+
+    def __init__(self, cfg: LlavaNextRewardConfig, provider: Callable[[str], torch.Tensor]):
+        super().__init__(cfg, provider)
+        self.layer_id = cfg.num_layers
+
+    def _build_engine(self, device):
+        return LlavaNextRewardEngine(self.config, pack_weights_llava(self.config, self._provider, device=device),
+                                     device=device)
+
+    def custom_forward(self, input_ids=None, attention_mask=None, pixel_values=None, image_sizes=None,
+                       return_output=False, inputs_batch=None):
+        if self.engine is None:
+            raise RuntimeError("call .to('cuda') before custom_forward (weights are packed on the device)")
+        if inputs_batch is None:
+            # the reference reads inputs_batch['attention_mask'] unconditionally in this branch (:373)
+            raise TypeError("model_type 'llava' is called as custom_forward(inputs_batch=processor_output)")
+        if return_output:
+            raise NotImplementedError("return_output=True (HF LlavaNextCausalLMOutputWithPast) is not produced by the fused path")
+        if self.mean_hidden_state:
+            raise NotImplementedError("mean_hidden_state pooling is off in all shipped reference configs")
+        if self.training:
+            raise NotImplementedError("training-mode gather (values[:, -1]) is not part of the scoring path")
+        for k in ("input_ids", "attention_mask", "pixel_values", "image_sizes"):
+            if k not in inputs_batch:
+                raise KeyError(k)
+        with torch.cuda.device(self.device):
+            reward = self.engine.forward(inputs_batch["input_ids"], inputs_batch["attention_mask"],
+                                         inputs_batch["pixel_values"], inputs_batch["image_sizes"])
         return reward, None
 
     __call__ = custom_forward

@@ -78,6 +78,19 @@ def token_plan(ids, mask, B, S, pos, img_ord, seq_start, seq_len, eos_row, n_img
            _ptr(eos_row), _ptr(n_img), _ptr(flags), _stream())
 
 
+def token_plan_ex(ids, mask, B, S, image_token_id, position_mode, pos, img_ord, seq_start, seq_len, eos_row, n_img,
+                  flags):
+    _need_cuda(ids, mask, pos, img_ord, seq_start, seq_len, eos_row, n_img, flags)
+    L.call("lr_token_plan_ex", _ptr(ids), _ptr(mask), B, S, int(image_token_id), int(position_mode), _ptr(pos),
+           _ptr(img_ord), _ptr(seq_start), _ptr(seq_len), _ptr(eos_row), _ptr(n_img), _ptr(flags), _stream())
+
+
+def anyres_embed_scatter(ids, img_ord, plan, wte, feat, newline, hidden, B, S, H, V):
+    _need_cuda(ids, img_ord, plan, wte, feat, newline, hidden)
+    L.call("lr_anyres_embed_scatter_bf16", _ptr(ids), _ptr(img_ord), _ptr(plan), _ptr(wte), _ptr(feat), feat.stride(0),
+           _ptr(newline), _ptr(hidden), hidden.stride(0), B, S, H, V, _stream())
+
+
 def hd_gather(clip_tokens, plan, sub_gn, glb_gn, rows, B, max_nv):
     _need_cuda(clip_tokens, plan, sub_gn, glb_gn, rows)
     L.call("lr_hd_gather_bf16", _ptr(clip_tokens), _ptr(plan), _ptr(sub_gn), _ptr(glb_gn), _ptr(rows), B, max_nv, _stream())

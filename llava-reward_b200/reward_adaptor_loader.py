@@ -11,9 +11,9 @@ import numpy as np
 import torch
 import yaml
 
-from .checkpoint import checkpoint_provider
-from .config import RewardConfig
-from .model import B200RewardModel
+from .checkpoint import checkpoint_provider, llava_checkpoint_provider
+from .config import LlavaNextRewardConfig, RewardConfig
+from .model import B200LlavaNextRewardModel, B200RewardModel
 from .synth import SynthProvider
 
 
@@ -31,12 +31,34 @@ def load_reward_adaptor(args, model_type, reward_config_path, load_tokenizer=Fal
     args.add_cross_attention = reward_cfg['add_cross_attention']
     args.value_head_dim = reward_cfg['value_head_dim']
     args.general_preference_tau = reward_cfg['general_preference_tau']
-    if model_type != 'phi3v':
-        raise NotImplementedError(f"model_type={model_type!r}: this build covers the phi3v backbone "
-                                  "(qwen / llava are the next rows of SURVEY.md 8f)")
+    if model_type not in ('phi3v', 'llava'):
+        raise NotImplementedError(f"model_type={model_type!r}: this build covers the phi3v and llava (v1.6 Vicuna) "
+                                  "backbones (qwen is the next row of SURVEY.md 8f)")
     overrides = dict(getattr(args, "config_overrides", None) or {})
     pretrain = str(args.pretrain)
     synthetic = pretrain.startswith("synthetic")
+    if model_type == 'llava':
+        # reference :110-151. add_cross_attention is read from the yaml but the llava branch of custom_forward never
+        # applies SkipCA (rw_model_general_preference.py:376-397), so it does not change the forward.
+        if synthetic and "13b" in pretrain:
+            overrides = {**dict(hidden_size=5120, intermediate_size=13824, num_layers=40, num_heads=40), **overrides}
+        lcfg = LlavaNextRewardConfig(is_general_preference=bool(args.is_general_preference),
+                                     value_head_dim=int(args.value_head_dim),
+                                     general_preference_tau=float(args.general_preference_tau), **overrides)
+        if synthetic:
+            parts = [x for x in pretrain.split(":")[1:] if x.isdigit()]
+            lprov: Callable[[str], torch.Tensor] = SynthProvider(lcfg, seed=int(parts[0]) if parts else 1234)
+        else:
+            lcfg, lprov = llava_checkpoint_provider(lcfg, pretrain, getattr(args, "pm_path", None),
+                                                    ft_projector=bool(getattr(args, "ft_projector", False)))
+        lmodel = B200LlavaNextRewardModel(lcfg, lprov)
+        if load_tokenizer:
+            from .processing import load_processor_llava
+            processor, tokenizer = load_processor_llava(pretrain, lcfg, cache_dir=getattr(args, "cache_dir", None),
+                                                        use_fast=not getattr(args, "disable_fast_tokenizer", False))
+            tokenizer.truncation_side = "right"
+            return args, lmodel, processor, tokenizer
+        return args, lmodel
     cfg = RewardConfig(is_general_preference=bool(args.is_general_preference),
                        add_cross_attention=bool(args.add_cross_attention),
                        value_head_dim=int(args.value_head_dim),

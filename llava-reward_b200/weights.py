@@ -19,8 +19,8 @@ from typing import Callable, Dict, List
 
 import torch
 
-from .config import RewardConfig
-from .synth import CLIP_PREFIX
+from .config import LlavaNextRewardConfig, RewardConfig
+from .synth import CLIP_PREFIX, LLAVA_CLIP_PREFIX, LLAVA_LM_PREFIX
 
 VE = "model.vision_embed_tokens."
 
@@ -41,14 +41,9 @@ class PackedWeights:
         return tot + self.embed.numel() * self.embed.element_size()
 
 
-def pack_weights(cfg: RewardConfig, get: Callable[[str], torch.Tensor], device="cuda") -> PackedWeights:
+def _pack_clip(pw: PackedWeights, cfg, g, c: str, device) -> None:
+    """CLIP ViT-L/14-336 tower (shared by the Phi-3-V and LLaVA-v1.6 branches; `c` = state_dict prefix)."""
     bf = torch.bfloat16
-
-    def g(name):
-        return get(name).to(device=device, dtype=bf).contiguous()
-
-    pw = PackedWeights()
-    c = CLIP_PREFIX
     D = cfg.clip_hidden
     pe = g(c + "embeddings.patch_embedding.weight").reshape(D, -1)  # [1024, 588], (ch, ky, kx) order
     patch_w = torch.zeros(D, 640, dtype=bf, device=device)
@@ -72,6 +67,23 @@ def pack_weights(cfg: RewardConfig, get: Callable[[str], torch.Tensor], device="
             "fc1_w": g(p + "mlp.fc1.weight"), "fc1_b": g(p + "mlp.fc1.bias"),
             "fc2_w": g(p + "mlp.fc2.weight"), "fc2_b": g(p + "mlp.fc2.bias"),
         })
+
+
+def _qk_interleave_perm(n_heads: int, head_dim: int, device) -> torch.Tensor:
+    """Row permutation of a [n_heads*head_dim, *] q or k projection: inside every head new row 2i = old i,
+    2i+1 = old i + head_dim/2 (RoPE pairs adjacent, see lr_gemm_rope_bf16)."""
+    inter = torch.stack([torch.arange(head_dim // 2), torch.arange(head_dim // 2) + head_dim // 2], dim=1).reshape(-1)
+    return (torch.arange(n_heads)[:, None] * head_dim + inter[None, :]).reshape(-1).to(device)
+
+
+def pack_weights(cfg: RewardConfig, get: Callable[[str], torch.Tensor], device="cuda") -> PackedWeights:
+    bf = torch.bfloat16
+
+    def g(name):
+        return get(name).to(device=device, dtype=bf).contiguous()
+
+    pw = PackedWeights()
+    _pack_clip(pw, cfg, g, CLIP_PREFIX, device)
     pw.proj = {
         "p0_w": g(VE + "img_projection.0.weight"), "p0_b": g(VE + "img_projection.0.bias"),
         "p2_w": g(VE + "img_projection.2.weight"), "p2_b": g(VE + "img_projection.2.bias"),
@@ -91,10 +103,8 @@ def pack_weights(cfg: RewardConfig, get: Callable[[str], torch.Tensor], device="
         B = (get(name + ".lora_B.weight").to(device=device, dtype=torch.float32) * cfg.lora_scale).to(bf)
         return torch.cat([W, B], dim=1).contiguous(), A
 
-    hd, nh = cfg.head_dim, cfg.num_heads
-    inter = torch.stack([torch.arange(hd // 2), torch.arange(hd // 2) + hd // 2], dim=1).reshape(-1)  # 0,48,1,49,..
-    qk_perm = (torch.arange(2 * nh)[:, None] * hd + inter[None, :]).reshape(-1)
-    qkv_perm = torch.cat([qk_perm, torch.arange(2 * H, 3 * H)]).to(device)
+    qkv_perm = torch.cat([_qk_interleave_perm(2 * cfg.num_heads, cfg.head_dim, device),  # q and k heads: 0,48,1,49,..
+                          torch.arange(2 * H, 3 * H, device=device)])
     for i in range(cfg.num_layers):
         p = f"model.layers.{i}."
         qkv_w, qkv_a = ext(p + "self_attn.qkv_proj")
@@ -115,4 +125,64 @@ def pack_weights(cfg: RewardConfig, get: Callable[[str], torch.Tensor], device="
             "wkv": torch.cat([g("W_k.weight"), g("W_v.weight")], 0).contiguous(),
             "ca_ln": g("ca_layernorm.weight"),
         })
+    return pw
+
+
+def pack_weights_llava(cfg: LlavaNextRewardConfig, get: Callable[[str], torch.Tensor], device="cuda") -> PackedWeights:
+    """LLaVA-v1.6 (reference names of transformers 4.50, see synth.llava_param_specs) -> the SAME per-layer dict the
+    Phi-3 decoder loop consumes, so one engine code path serves both backbones:
+      * q/k/v stacked into one [3H, H + 3r] weight: columns [W | 2B_q 0 0 ; 0 2B_k 0 ; 0 0 2B_v] against the stacked
+        A = [A_q; A_k; A_v] ([3r, H]) - three LoRA branches in one K-extension
+      * gate/up stacked the same way ([2I, H + 2r]), then interleaved in blocks of 128 rows for the SwiGLU epilogue
+      * q/k rows head-interleaved for the fused RoPE epilogue (head_dim 128)."""
+    bf = torch.bfloat16
+
+    def g(name):
+        return get(name).to(device=device, dtype=bf).contiguous()
+
+    pw = PackedWeights()
+    _pack_clip(pw, cfg, g, LLAVA_CLIP_PREFIX, device)
+    pw.proj = {
+        "p0_w": g("multi_modal_projector.linear_1.weight"), "p0_b": g("multi_modal_projector.linear_1.bias"),
+        "p2_w": g("multi_modal_projector.linear_2.weight"), "p2_b": g("multi_modal_projector.linear_2.bias"),
+        "newline": g("image_newline").reshape(-1),
+    }
+    lm = LLAVA_LM_PREFIX
+    pw.embed = g(lm + "embed_tokens.weight")
+    H, I, r = cfg.hidden_size, cfg.intermediate_size, cfg.lora_rank
+    assert I % 128 == 0 and H % 256 == 0
+    nb = I // 128
+    gu_perm = torch.arange(2 * I, device=device).view(2, nb, 128).permute(1, 0, 2).reshape(-1)
+    qk = _qk_interleave_perm(cfg.num_heads, cfg.head_dim, device)
+    qkv_perm = torch.cat([qk, H + qk, torch.arange(2 * H, 3 * H, device=device)])
+
+    def stacked(names):
+        """rows = concatenation of the named linears; LoRA B blocks on the block diagonal of the K-extension"""
+        Ws = [g(n + ".weight") for n in names]
+        if not cfg.use_lora:
+            return torch.cat(Ws, 0).contiguous(), None
+        k = len(names)
+        blocks = []
+        for j, n in enumerate(names):
+            B = (get(n + ".lora_B.weight").to(device=device, dtype=torch.float32) * cfg.lora_scale).to(bf)
+            ext = torch.zeros(B.shape[0], k * r, dtype=bf, device=device)
+            ext[:, j * r:(j + 1) * r] = B
+            blocks.append(torch.cat([Ws[j], ext], dim=1))
+        A = torch.cat([g(n + ".lora_A.weight") for n in names], 0).contiguous()
+        return torch.cat(blocks, 0).contiguous(), A
+
+    for i in range(cfg.num_layers):
+        p = f"{lm}layers.{i}."
+        qkv_w, qkv_a = stacked([p + f"self_attn.{n}_proj" for n in "qkv"])
+        qkv_w = qkv_w[qkv_perm].contiguous()
+        o_w, o_a = stacked([p + "self_attn.o_proj"])
+        gu_w, gu_a = stacked([p + "mlp.gate_proj", p + "mlp.up_proj"])
+        gu_w = gu_w[gu_perm].contiguous()
+        dn_w, dn_a = stacked([p + "mlp.down_proj"])
+        d = {"in_ln": g(p + "input_layernorm.weight"), "post_ln": g(p + "post_attention_layernorm.weight"),
+             "qkv_w": qkv_w, "o_w": o_w, "gu_w": gu_w, "dn_w": dn_w}
+        if cfg.use_lora:
+            d.update({"qkv_a": qkv_a, "o_a": o_a, "gu_a": gu_a, "dn_a": dn_a})
+        pw.layers.append(d)
+    pw.head = {"norm": g(lm + "norm.weight"), "vh": g("value_head.weight")}
     return pw
