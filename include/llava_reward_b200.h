@@ -199,6 +199,16 @@ int lr_resample_u8(const uint8_t* src, int src_h, int src_w, uint8_t* dst, int d
 int lr_hd_pack_f32(const uint8_t* img, int rh, int rw, int pad_top, int pad_left, int H, int W, const float* mean3,
                    const float* std3, float* out, int n_slots, void* stream);
 
+/* LLaVA-v1.6 anyres patches: uint8 HWC image [rh, rw, 3] (device) placed at (pad_top, pad_left) on a zero canvas of
+ * (grid_h*336) x (grid_w*336), split row-major into grid_h*grid_w patches out[p][3][336][336] fp32.
+ * lut768 (HOST pointer, [3][256] floats) maps a uint8 channel value to its rescaled + normalised float; the caller
+ * builds it with the processor's own arithmetic so the result is bit-identical. Replaces _pad_for_patching /
+ * divide_to_patches / rescale / normalize of transformers' LlavaNextImageProcessor (image_processing_pil_llava_next.py
+ * :105-146, 205-225) used by the reference through AutoProcessor (llava_reward/datasets/reward_dataset.py:334-346).
+ * The base view is the same call with grid 1x1 on the image resized to 336x336. */
+int lr_patch_pack_f32(const uint8_t* img, int rh, int rw, int pad_top, int pad_left, int grid_h, int grid_w,
+                      const float* lut768, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

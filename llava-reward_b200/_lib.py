@@ -43,6 +43,7 @@ SIGNATURES = {
     "lr_skipca_head": ([p, p, i32, p, p, i32, p, p, p, i32, i32, i32, i32, f32, p], i32),
     "lr_preference": ([p, p, p, i32, i32, i32, f32, p], i32),
     "lr_resample_u8": ([p, i32, i32, p, i32, i32, i32, p, p, i32, p], i32),
+    "lr_patch_pack_f32": ([p, i32, i32, i32, i32, i32, i32, p, p, p], i32),
     "lr_hd_pack_f32": ([p, i32, i32, i32, i32, i32, i32, p, p, p, i32, p], i32),
 }
 

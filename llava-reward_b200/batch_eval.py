@@ -1,7 +1,8 @@
 """Batch evaluation callers around the hot path: the collate step of
 `GeneralRewardDataset.collate_fn` (reference llava_reward/datasets/reward_dataset.py:137-202, left padding via
 `zero_pad_sequences`, datasets/utils.py:5-13) and the two loops of `batch_rm_inference`
-(reference eval/batch_inference_rm_phi.py:70-152): pairwise preference accuracy and single-image (BT / cls) scoring.
+(reference eval/batch_inference_rm_phi.py:70-152, eval/batch_inference_rm_llava.py:70-152 - the same loops with the
+`inputs_batch=` calling convention): pairwise preference accuracy and single-image (BT / cls) scoring.
 Inputs are per-sample dicts as produced by `inference_process_phi3v` / the processor; everything stays on the GPU
 until the final numpy conversion.
 """
@@ -36,6 +37,16 @@ def collate_samples(items: Sequence[Dict[str, torch.Tensor]], pad_token_id: int)
             "image_sizes": sizes.squeeze(1)}
 
 
+def _forward(model, batch):
+    """One scoring call in the backbone's own convention: positional tensors for phi3v
+    (eval/batch_inference_rm_phi.py:93), the processor's BatchFeature as `inputs_batch` for llava
+    (eval/batch_inference_rm_llava.py:86-87)."""
+    if getattr(model, "model_type", "phi3v") == "llava":
+        return model.custom_forward(inputs_batch=batch)[0]
+    return model.custom_forward(batch["input_ids"], batch["attention_mask"], batch["pixel_values"],
+                                batch["image_sizes"])[0]
+
+
 @torch.no_grad()
 def score_pairs(model, args, batches: Iterable) -> Dict[str, object]:
     """Pairwise mode (eval/batch_inference_rm_phi.py:70-121). `batches` yields (batch_chosen, batch_rejected) dicts.
@@ -44,8 +55,7 @@ def score_pairs(model, args, batches: Iterable) -> Dict[str, object]:
     probs: List[float] = []
     chosen_rewards, reject_rewards = [], []
     for bc, br in batches:
-        rc, _ = model.custom_forward(bc["input_ids"], bc["attention_mask"], bc["pixel_values"], bc["image_sizes"])
-        rr, _ = model.custom_forward(br["input_ids"], br["attention_mask"], br["pixel_values"], br["image_sizes"])
+        rc, rr = _forward(model, bc), _forward(model, br)
         if not args.is_general_preference:
             chosen_rewards.extend(rc.squeeze(-1).tolist())
             reject_rewards.extend(rr.squeeze(-1).tolist())
@@ -78,8 +88,7 @@ def score_single(model, args, batches: Iterable, cls_based: bool = False) -> Dic
                          "Please use BT model instead.")
     rewards, preds, labels = [], [], []
     for batch, lab in batches:
-        r, _ = model.custom_forward(input_ids=batch["input_ids"], attention_mask=batch["attention_mask"],
-                                    pixel_values=batch["pixel_values"], image_sizes=batch["image_sizes"])
+        r = _forward(model, batch)
         rewards.extend(r.squeeze(-1).tolist())
         labels.extend(torch.as_tensor(lab).tolist())
         if cls_based:
@@ -88,3 +97,16 @@ def score_single(model, args, batches: Iterable, cls_based: bool = False) -> Dic
     if cls_based:
         out.update(binary_metrics(preds, labels))
     return out
+
+
+@torch.no_grad()
+def best_of_n(model, batches: Iterable) -> Dict[str, object]:
+    """Inference-time scaling (BASELINE.json configs[4]): score N candidate images of one prompt with a BT model and
+    return the rewards and the arg-max candidate. `batches` yields processor outputs covering the N candidates."""
+    rewards: List[float] = []
+    for batch in batches:
+        r = _forward(model, batch)
+        if r.shape[1] != 1:
+            raise ValueError("best-of-N selection needs a scalar (BT) reward head")
+        rewards.extend(r.float().squeeze(-1).tolist())
+    return {"rewards": rewards, "best": int(np.argmax(rewards)) if rewards else -1}

@@ -104,6 +104,35 @@ hd_global_kernel(const uint8_t* __restrict__ img, int rh, int rw, int pad_top, i
   out[i] = acc;
 }
 
+// ---------------------------------------------------------------- LlavaNext anyres patches
+// A uint8 HWC image placed at (pad_top, pad_left) on a ZERO canvas of (gh*336) x (gw*336), split into gh*gw patches
+// [3,336,336] fp32 in row-major patch order. The uint8 -> normalised float map is a 3 x 256 table built on the host
+// with numpy's own arithmetic (float32(float64(u) * (1/255)) - mean) / std, so the output is bit-identical to
+// transformers' rescale + normalize.
+struct PatchLut {
+  float v[3][256];
+};
+
+__global__ void __launch_bounds__(256)
+patch_pack_kernel(const uint8_t* __restrict__ img, int rh, int rw, int pad_top, int pad_left, int gh, int gw,
+                  float* __restrict__ out, const __grid_constant__ PatchLut lut) {
+  const size_t i = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4;  // 4 consecutive x of one patch row
+  const size_t total = size_t(gh) * gw * 3 * 336 * 336;
+  if (i >= total) return;
+  const int x = int(i % 336), y = int((i / 336) % 336), c = int((i / (336 * 336)) % 3);
+  const int p = int(i / (3 * 336 * 336));
+  const int Y = (p / gw) * 336 + y - pad_top, X0 = (p % gw) * 336 + x - pad_left;
+  float4 o;
+  float* of = reinterpret_cast<float*>(&o);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int X = X0 + t;
+    const int u = (Y >= 0 && Y < rh && X >= 0 && X < rw) ? int(img[(size_t(Y) * rw + X) * 3 + c]) : 0;
+    of[t] = lut.v[c][u];
+  }
+  *reinterpret_cast<float4*>(out + i) = o;
+}
+
 }  // namespace lr
 
 using namespace lr;
@@ -131,5 +160,19 @@ extern "C" int lr_hd_pack_f32(const uint8_t* img, int rh, int rw, int pad_top, i
   const size_t n4 = size_t(n_slots - 1) * 3 * 336 * 336 / 4;
   hd_crops_kernel<<<unsigned((n4 + 255) / 256), 256, 0, s>>>(img, rh, rw, pad_top, pad_left, hc, wc, out, n_slots, np);
   hd_global_kernel<<<(3 * 336 * 336 + 255) / 256, 256, 0, s>>>(img, rh, rw, pad_top, pad_left, H, W, out, np);
+  return lr_launch_status();
+}
+
+extern "C" int lr_patch_pack_f32(const uint8_t* img, int rh, int rw, int pad_top, int pad_left, int grid_h, int grid_w,
+                                 const float* lut768, float* out, void* stream) {
+  LR_CHECK_ARG(img && out && lut768 && rh > 0 && rw > 0 && grid_h > 0 && grid_w > 0);
+  LR_CHECK_ARG(pad_top >= 0 && pad_left >= 0 && pad_top + rh <= grid_h * 336 && pad_left + rw <= grid_w * 336);
+  if (reinterpret_cast<uintptr_t>(out) & 15) return LR_ERR_ALIGN;
+  PatchLut lut;
+  for (int c = 0; c < 3; ++c)
+    for (int u = 0; u < 256; ++u) lut.v[c][u] = lut768[c * 256 + u];  // host pointer
+  const size_t n4 = size_t(grid_h) * grid_w * 3 * 336 * 336 / 4;
+  patch_pack_kernel<<<unsigned((n4 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      img, rh, rw, pad_top, pad_left, grid_h, grid_w, out, lut);
   return lr_launch_status();
 }

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .config import RewardConfig
+from .config import LlavaNextRewardConfig, RewardConfig, anyres_geometry, select_best_resolution
 
 OPENAI_CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 OPENAI_CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
@@ -44,6 +44,39 @@ def _hd_geometry(width: int, height: int, hd_num: int):
     new_h = int(new_w / ratio)
     tar = int(math.ceil(new_h / 336) * 336)
     return trans, new_w, new_h, tar
+
+
+def _pil_bicubic_weight(x: np.ndarray) -> np.ndarray:
+    """Pillow bicubic_filter (a = -0.5) on |x| (Resample.c)."""
+    a = -0.5
+    near = ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    far = (((x - 5) * x + 8) * x - 4) * a
+    return np.where(x < 1.0, near, np.where(x < 2.0, far, 0.0))
+
+
+@functools.lru_cache(maxsize=256)
+def _bicubic_taps(in_size: int, out_size: int):
+    """Pillow's BICUBIC resample taps (22-bit fixed point, negative lobes rounded away from zero like
+    normalize_coeffs_8bpc) for a full-image box: bounds [out,2], coeffs [out,ksize]."""
+    scale = in_size / out_size
+    filterscale = scale if scale > 1.0 else 1.0
+    support = 2.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    centers = (np.arange(out_size, dtype=np.float64) + 0.5) * scale
+    xmin = np.maximum((centers - support + 0.5).astype(np.int64), 0)
+    xmax = np.minimum((centers + support + 0.5).astype(np.int64), in_size)
+    n = (xmax - xmin).astype(np.int64)
+    t = np.arange(ksize, dtype=np.float64)[None, :]
+    arg = np.abs((t + xmin[:, None] - centers[:, None] + 0.5) * (1.0 / filterscale))
+    w = np.where(t < n[:, None], _pil_bicubic_weight(arg), 0.0)
+    ww = np.zeros(out_size, dtype=np.float64)
+    for j in range(ksize):          # sequential accumulation, as the C loop does
+        ww = ww + w[:, j]
+    w = np.where(ww[:, None] != 0.0, w / np.where(ww == 0.0, 1.0, ww)[:, None], w)
+    v = w * float(1 << _PRECISION_BITS)
+    kk = np.where(w < 0, (-0.5 + v), (0.5 + v)).astype(np.int64).astype(np.int32)  # C (int) cast truncates toward zero
+    bounds = np.stack([xmin, n], axis=1).astype(np.int32)
+    return bounds, kk, ksize
 
 
 @functools.lru_cache(maxsize=256)
@@ -214,4 +247,194 @@ def load_processor(pretrain_dir: str, cfg: RewardConfig, cache_dir=None, use_fas
     if tokenizer.pad_token is None:
         tokenizer.pad_token = tokenizer.eos_token
     proc = Phi3VProcessorB200(Phi3VImageProcessorB200(num_crops=cfg.num_crops, device=device), tokenizer)
+    return proc, tokenizer
+
+
+# --------------------------------------------------------------------------------------------------
+# LLaVA-v1.6 (LlavaNext) processor: reference llava branch, reward_dataset.py:334-346 via AutoProcessor
+# --------------------------------------------------------------------------------------------------
+def _patch_output_size(hw, target_hw):
+    """transformers get_patch_output_size (image_processing_utils.py:671-688)."""
+    oh, ow = hw
+    th, tw = target_hw
+    sw, sh = tw / ow, th / oh
+    if sw < sh:
+        return min(math.ceil(oh * sw), th), tw
+    return th, min(math.ceil(ow * sh), tw)
+
+
+class LlavaNextImageProcessorB200:
+    """GPU counterpart of transformers' LlavaNextImageProcessor (PIL/numpy backend) with the llava-v1.6-vicuna
+    preprocessor_config (shortest_edge 336, crop 336, BICUBIC, CLIP mean/std, anyres pinpoints): the uint8 image goes
+    to the device once; Pillow-exact bicubic resampling (`lr_resample_u8` with host-computed 22-bit taps), zero
+    padding, patch split and normalisation (`lr_patch_pack_f32`) run there. Output is bit-identical to the PIL path."""
+    model_input_names = ["pixel_values", "image_sizes"]
+
+    def __init__(self, image_grid_pinpoints=None, image_mean=None, image_std=None, size: int = 336, device="cuda",
+                 **kwargs):
+        self.image_grid_pinpoints = [list(p) for p in (image_grid_pinpoints or LlavaNextRewardConfig().image_grid_pinpoints)]
+        self.image_mean = tuple(image_mean) if image_mean is not None else OPENAI_CLIP_MEAN
+        self.image_std = tuple(image_std) if image_std is not None else OPENAI_CLIP_STD
+        self.size = int(size)
+        if self.size != 336:
+            raise ValueError("the CLIP tower of this build is ViT-L/14-336: size must be 336")
+        self.device = torch.device(device)
+        self._taps = {}
+        # uint8 -> float table with numpy's arithmetic of transformers rescale() + normalize()
+        x = (np.arange(256, dtype=np.uint8).astype(np.float64) * (1 / 255)).astype(np.float32)
+        mean = np.array(self.image_mean, dtype=np.float32)[:, None]
+        std = np.array(self.image_std, dtype=np.float32)[:, None]
+        self._lut = np.ascontiguousarray(((x[None, :] - mean) / std).astype(np.float32))
+
+    def _dev_taps(self, in_size: int, out_size: int):
+        key = (in_size, out_size)
+        if key not in self._taps:
+            b, k, ksize = _bicubic_taps(in_size, out_size)
+            self._taps[key] = (torch.from_numpy(b).to(self.device), torch.from_numpy(k).to(self.device), ksize)
+        return self._taps[key]
+
+    def _resample(self, src: torch.Tensor, out_size: int, axis: int) -> torch.Tensor:
+        h, w = src.shape[:2]
+        dh, dw = (h, out_size) if axis == 1 else (out_size, w)
+        dst = torch.empty(dh, dw, 3, dtype=torch.uint8, device=self.device)
+        b, k, ksize = self._dev_taps(w if axis == 1 else h, out_size)
+        L.call("lr_resample_u8", src.data_ptr(), h, w, dst.data_ptr(), dh, dw, axis, b.data_ptr(), k.data_ptr(), ksize,
+               torch.cuda.current_stream().cuda_stream)
+        return dst
+
+    def _resize(self, x: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
+        """PIL Image.resize order: horizontal pass, then vertical; unchanged axes are skipped."""
+        if x.shape[1] != out_w:
+            x = self._resample(x, out_w, 1)
+        if x.shape[0] != out_h:
+            x = self._resample(x, out_h, 0)
+        return x
+
+    def num_patches(self, hw) -> int:
+        return anyres_geometry(hw, self.image_grid_pinpoints, self.size)["n_patches"]
+
+    def preprocess(self, images, return_tensors=None, out=None, **kwargs):
+        if self.device.type != "cuda":
+            raise RuntimeError("LlavaNextImageProcessorB200 runs on CUDA only (no CPU fallback)")
+        images = list(images) if isinstance(images, (list, tuple)) else [images]
+        arrs = [im if torch.is_tensor(im) else _to_hwc_u8(im) for im in images]
+        sizes = [(int(a.shape[0]), int(a.shape[1])) for a in arrs]
+        n_pat = [self.num_patches(hw) for hw in sizes]
+        P = max(n_pat)
+        side = self.size
+        if out is None:
+            out = torch.empty(len(arrs), P, 3, side, side, dtype=torch.float32, device=self.device)
+        elif tuple(out.shape) != (len(arrs), P, 3, side, side) or out.dtype != torch.float32 or not out.is_cuda:
+            raise ValueError(f"out must be a CUDA float32 tensor of shape {(len(arrs), P, 3, side, side)}")
+        import ctypes
+        lut = self._lut.ctypes.data_as(ctypes.c_void_p)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            for i, a in enumerate(arrs):
+                if torch.is_tensor(a):
+                    if a.dtype != torch.uint8 or a.dim() != 3 or a.shape[2] != 3:
+                        raise ValueError("image tensors must be uint8 HxWx3")
+                    x = a.to(self.device, non_blocking=True).contiguous()
+                else:
+                    x = torch.from_numpy(a).to(self.device, non_blocking=True)
+                h, w = sizes[i]
+                bh, bw = select_best_resolution((h, w), self.image_grid_pinpoints)
+                nh, nw = _patch_output_size((h, w), (bh, bw))
+                base = self._resize(x, side, side)
+                L.call("lr_patch_pack_f32", base.data_ptr(), side, side, 0, 0, 1, 1, lut, out[i, 0].data_ptr(), stream)
+                grid = self._resize(x, nh, nw)
+                L.call("lr_patch_pack_f32", grid.data_ptr(), nh, nw, (bh - nh) // 2, (bw - nw) // 2, bh // side,
+                       bw // side, lut, out[i, 1].data_ptr(), stream)
+                if n_pat[i] < P:
+                    out[i, n_pat[i]:].zero_()   # _pad_for_batching: zero patches up to the batch maximum
+        data = {"pixel_values": out, "image_sizes": [list(s) for s in sizes]}
+        if return_tensors == "pt":
+            data["image_sizes"] = torch.tensor(data["image_sizes"], dtype=torch.int64)
+        return data
+
+    __call__ = preprocess
+
+
+class LlavaNextProcessorB200:
+    """`processor(images=..., text=..., padding=True, return_tensors="pt")` of transformers' LlavaNextProcessor
+    (processing_llava_next.py) as the reference's collate_fn calls it (reward_dataset.py:334-346): every `<image>` in
+    a prompt is expanded to the image's token count (base 576 + unpadded grid + one newline per grid row; the CLS
+    token is dropped by the 'default' feature-select strategy), then the tokenizer pads the batch. Returns a
+    transformers BatchFeature (so `.to(device)` works like the reference's caller expects)."""
+    image_token = "<image>"
+
+    def __init__(self, image_processor: LlavaNextImageProcessorB200, tokenizer):
+        self.image_processor, self.tokenizer = image_processor, tokenizer
+
+    def apply_chat_template(self, conversation, tokenize=False, add_generation_prompt=True, **kw):
+        if hasattr(self.tokenizer, "apply_chat_template") and getattr(self.tokenizer, "chat_template", None):
+            return self.tokenizer.apply_chat_template(conversation, tokenize=tokenize,
+                                                      add_generation_prompt=add_generation_prompt, **kw)
+        # Fallback when the checkpoint directory ships no chat template (restated from the llava-v1.6-vicuna
+        # chat_template.json from memory, unverified offline): "USER: <image>\n<text> ASSISTANT:", images first.
+        out = ""
+        for msg in conversation:
+            out += msg["role"].upper() + ": "
+            out += "".join("<image>\n" for c in msg["content"] if c["type"] == "image")
+            out += "".join(c["text"] + " " for c in msg["content"] if c["type"] == "text")
+        return out + ("ASSISTANT:" if add_generation_prompt else "")
+
+    def num_image_tokens(self, hw) -> int:
+        return anyres_geometry(hw, self.image_processor.image_grid_pinpoints, self.image_processor.size)["n_tokens"]
+
+    def _image_inputs(self, images):
+        return self.image_processor(images, return_tensors="pt")
+
+    def __call__(self, images=None, text=None, padding=False, truncation=None, max_length=None, return_tensors="pt",
+                 **kwargs):
+        from transformers import BatchFeature
+        if text is None:
+            raise ValueError("You have to specify at least `text`.")
+        texts = [text] if isinstance(text, str) else list(text)
+        data = {}
+        if images is not None:
+            images = list(images) if isinstance(images, (list, tuple)) else [images]
+            image_inputs = self._image_inputs(images)
+            sizes = image_inputs["image_sizes"].tolist()
+            it = iter(sizes)
+            expanded = []
+            for t in texts:
+                parts = t.split(self.image_token)
+                s = parts[0]
+                for tail in parts[1:]:
+                    try:
+                        hw = next(it)
+                    except StopIteration:
+                        raise ValueError("more <image> placeholders than images") from None
+                    s += self.image_token * self.num_image_tokens(hw) + tail
+                expanded.append(s)
+            if next(it, None) is not None:
+                raise ValueError("fewer <image> placeholders than images")
+            texts = expanded
+            data.update(image_inputs)
+        tok = self.tokenizer(texts, padding=padding, truncation=truncation, max_length=max_length,
+                             return_tensors=return_tensors)
+        data.update({"input_ids": tok["input_ids"], "attention_mask": tok["attention_mask"]})
+        return BatchFeature(data=data)
+
+
+def load_processor_llava(pretrain_dir: str, cfg: LlavaNextRewardConfig, cache_dir=None, use_fast=True, device="cuda"):
+    """(processor, tokenizer) like reference get_tokenizer_llava (llava_reward/utils/utils.py), from a LOCAL
+    llava-v1.6-vicuna checkpoint directory: tokenizer via transformers (left padding), image half on the GPU."""
+    from transformers import AutoTokenizer
+    tokenizer = AutoTokenizer.from_pretrained(pretrain_dir, use_fast=use_fast, cache_dir=cache_dir, padding_side="left")
+    if tokenizer.pad_token is None:   # reference utils.py:50-52
+        tokenizer.pad_token = tokenizer.eos_token
+        tokenizer.pad_token_id = tokenizer.eos_token_id
+    if not getattr(tokenizer, "chat_template", None):
+        import json
+        import os
+        for name in ("chat_template.jinja", "chat_template.json"):
+            path = os.path.join(pretrain_dir, name)
+            if os.path.exists(path):
+                with open(path) as f:
+                    raw = f.read()
+                tokenizer.chat_template = json.loads(raw)["chat_template"] if name.endswith(".json") else raw
+                break
+    proc = LlavaNextProcessorB200(LlavaNextImageProcessorB200(cfg.image_grid_pinpoints, device=device), tokenizer)
     return proc, tokenizer

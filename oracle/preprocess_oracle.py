@@ -37,11 +37,27 @@ def hd_geometry(width: int, height: int, hd_num: int = 16):
     return trans, new_w, new_h, tar
 
 
-def resample_coeffs(in_size: int, out_size: int):
-    """Pillow precompute_coeffs + normalize_coeffs_8bpc for the bilinear (triangle) filter, full-image box."""
+def _triangle(a: float) -> float:
+    return 1.0 - a if a < 1.0 else 0.0
+
+
+def _pil_bicubic(x: float) -> float:
+    """Pillow bicubic_filter (Resample.c, a = -0.5), argument already |x|."""
+    a = -0.5
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+def resample_coeffs(in_size: int, out_size: int, filt: str = "bilinear"):
+    """Pillow precompute_coeffs + normalize_coeffs_8bpc, full-image box; filt = 'bilinear' (triangle, support 1)
+    or 'bicubic' (a = -0.5, support 2)."""
     scale = in_size / out_size
     filterscale = max(scale, 1.0)
-    support = 1.0 * filterscale
+    fsupport, ffun = (1.0, _triangle) if filt == "bilinear" else (2.0, _pil_bicubic)
+    support = fsupport * filterscale
     ksize = int(math.ceil(support)) * 2 + 1
     bounds = np.zeros((out_size, 2), dtype=np.int32)
     kk = np.zeros((out_size, ksize), dtype=np.int32)
@@ -55,8 +71,7 @@ def resample_coeffs(in_size: int, out_size: int):
         n = xmax - xmin
         w = np.zeros(n, dtype=np.float64)
         for x in range(n):
-            a = abs((x + xmin - center + 0.5) * ss)
-            w[x] = 1.0 - a if a < 1.0 else 0.0
+            w[x] = ffun(abs((x + xmin - center + 0.5) * ss))
         ww = w.sum()  # sequential double accumulation in C; numpy pairwise sum differs only below 1e-16 relative
         ww = 0.0
         for x in range(n):
@@ -70,10 +85,10 @@ def resample_coeffs(in_size: int, out_size: int):
     return bounds, kk
 
 
-def resample_axis(img: np.ndarray, out_size: int, axis: int) -> np.ndarray:
+def resample_axis(img: np.ndarray, out_size: int, axis: int, filt: str = "bilinear") -> np.ndarray:
     """One Pillow 8bpc resample pass along `axis` (0 = vertical, 1 = horizontal) of an HxWx3 uint8 image."""
     in_size = img.shape[axis]
-    bounds, kk = resample_coeffs(in_size, out_size)
+    bounds, kk = resample_coeffs(in_size, out_size, filt)
     src = np.moveaxis(img, axis, 0).astype(np.int64)  # [in, other, 3]
     out = np.empty((out_size,) + src.shape[1:], dtype=np.uint8)
     for xx in range(out_size):

@@ -16,3 +16,8 @@ def synth_image(name: str, h: int, w: int) -> np.ndarray:
     img[..., 1] = ((yy * 255) // max(h - 1, 1) * 3 // 4 + (noise * 7 % 256) // 4) & 0xFF
     img[..., 2] = (((xx + yy) * 255) // max(h + w - 2, 1) // 2 + noise // 2) & 0xFF
     return img
+
+# LLaVA-v1.6 anyres cases: every grid pinpoint, up- and down-scaling, odd sizes, exact fits
+LLAVA_CASES = {"landscape_512x640": (512, 640), "square_768": (768, 768), "portrait_1000x300": (1000, 300),
+               "wide_300x900": (300, 900), "small_200x333": (200, 333), "exact_672x672": (672, 672),
+               "tall_1080x700": (1080, 700), "tiny_64x48": (64, 48)}

@@ -347,3 +347,71 @@ def test_value_head_wide_hidden(H):
     ops.skipca_head(None, None, None, x, None, w, out, B, H, 0, vhd, 1e-5)
     torch.cuda.synchronize()
     check_close(out, x.float() @ w.float().t(), "value head", atol=1e-2, rtol=1e-2)
+
+
+# ----------------------------------------------------------------------------------------------- preprocessing + callers
+def test_llava_gpu_preprocess_bit_exact_vs_transformers():
+    """GPU anyres preprocessing (Pillow-exact bicubic taps + lr_patch_pack_f32) against transformers' own PIL processor
+    (tests/golden/llava_preprocess.pt): SHA-1 of the float32 bytes."""
+    import hashlib
+    from preprocess_util import synth_image
+    from llava_reward_b200.processing import LlavaNextImageProcessorB200
+    fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "llava_preprocess.pt"),
+                    weights_only=False)
+    proc = LlavaNextImageProcessorB200()
+    for e in fx["cases"]:
+        h, w = e["hw"]
+        out = proc.preprocess([synth_image(e["name"], h, w)], return_tensors="pt")
+        pv = out["pixel_values"][0].cpu().contiguous()
+        assert list(pv.shape) == e["shape"] and out["image_sizes"][0].tolist() == e["image_sizes"]
+        assert torch.equal(pv[0, :, 100:104, :], e["base_rows"]), e["name"]
+        assert torch.equal(pv[1, :, 100:104, :], e["patch1_rows"]), e["name"]
+        assert hashlib.sha1(pv.numpy().tobytes()).hexdigest() == e["sha1"], e["name"]
+    b = fx["batch"]
+    from preprocess_util import LLAVA_CASES
+    out = proc.preprocess([synth_image(n, *LLAVA_CASES[n]) for n in b["names"]], return_tensors="pt")
+    assert list(out["pixel_values"].shape) == b["shape"] and out["image_sizes"].tolist() == b["image_sizes"]
+    assert hashlib.sha1(out["pixel_values"].cpu().contiguous().numpy().tobytes()).hexdigest() == b["sha1"]
+
+
+def test_llava_eval_loops_and_best_of_n(tmp_path_factory):
+    """the pairwise / single-image loops of eval/batch_inference_rm_llava.py and best-of-N over uint8 images
+    preprocessed on the GPU"""
+    from preprocess_util import synth_image
+    from llava_reward_b200.batch_eval import best_of_n, score_pairs, score_single
+    from llava_reward_b200.processing import LlavaNextImageProcessorB200
+    fx = load_fixture("llava_slim_bt")
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    bc = to_dev(llava_fixture_batch(fx, fx["batches"][0], cfg))
+    br = to_dev(llava_fixture_batch(fx, fx["batches"][1], cfg))
+    res = score_pairs(model, args, [(bc, br)])
+    ref = fx["prob"].numpy()
+    assert res["probs"].shape == (2,) and abs(res["probs"] - ref).max() < 0.05
+    single = score_single(model, args, [(bc, torch.tensor([1, 0]))], cls_based=True)
+    assert len(single["rewards"]) == 2 and 0.0 <= single["accuracy"] <= 1.0
+    # best-of-N from uint8 images: GPU preprocessing -> scoring
+    proc = LlavaNextImageProcessorB200(cfg.image_grid_pinpoints)
+    imgs = [synth_image(f"cand{i}", 400 + 40 * i, 520) for i in range(4)]
+    pp = proc.preprocess(imgs, return_tensors="pt")
+    from llava_reward_b200.config import anyres_geometry as geo
+    rows = [[1, 5, 6, 7] + [cfg.image_token_id] * geo(im.shape[:2], cfg.image_grid_pinpoints)["n_tokens"] + [2] for im in imgs]
+    S = max(len(r) for r in rows)
+    ids = torch.tensor([[0] * (S - len(r)) + r for r in rows])
+    mask = torch.tensor([[0] * (S - len(r)) + [1] * len(r) for r in rows])
+    batch = {"input_ids": ids.to(DEV), "attention_mask": mask.to(DEV), "pixel_values": pp["pixel_values"],
+             "image_sizes": pp["image_sizes"]}
+    out = best_of_n(model, [batch])
+    assert len(out["rewards"]) == 4 and 0 <= out["best"] < 4
+    # the same candidates through the oracle preprocessing + oracle forward (fp32): rewards agree within bf16 noise
+    from oracle import llava_preprocess_oracle as PO
+    pix = torch.zeros_like(pp["pixel_values"], device="cpu")
+    for i, im in enumerate(imgs):
+        pv, _ = PO.preprocess(im)
+        pix[i, : pv.shape[0]] = torch.from_numpy(pv)
+    assert torch.equal(pix, pp["pixel_values"].cpu())
+    P32 = Params(SynthProvider(cfg, seed=fx["seed_w"], device=DEV), dtype=torch.float32, device=DEV)
+    with torch.no_grad():
+        r32 = O.custom_forward(P32, cfg, {**batch, "pixel_values": pix.to(DEV)}).flatten().cpu()
+    err = (torch.tensor(out["rewards"]) - r32).abs().max().item()
+    print(f"best-of-4: engine {out['rewards']} oracle fp32 {r32.tolist()} err {err:.4g}")
+    assert err < 2e-2
