@@ -249,6 +249,9 @@ int attention_tc(const void* q, const void* k, const void* v, void* o, int ld_qk
 
 }  // namespace lr
 
+// product configuration at head_dim 128 (attention_tc variant code), chosen by tools/attn128_bench.py on the B200
+static constexpr int kHd128Product = 1;  // two tiles per CTA: 5.81 ms vs 7.80 ms (one tile) at 64 x 3057 tokens, 32 heads
+
 extern "C" int lr_attention_bf16(const void* q, const void* k, const void* v, void* o, int ld_qkv, int ld_o,
                                  int n_seq, int rows_per_seq, const int* seq_start, const int* seq_len, int n_heads,
                                  int head_dim, int causal, float scale, int impl, void* stream) {
@@ -258,9 +261,14 @@ extern "C" int lr_attention_bf16(const void* q, const void* k, const void* v, vo
                                      reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(o)) & 15)
     return LR_ERR_ALIGN;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (impl == LR_ATTN_TCGEN05 || impl == LR_ATTN_TCGEN05_SPLIT || impl == LR_ATTN_TCGEN05_2TILE)
+  if (impl == LR_ATTN_TCGEN05 || impl == LR_ATTN_TCGEN05_SPLIT || impl == LR_ATTN_TCGEN05_2TILE ||
+      impl == LR_ATTN_TCGEN05_1TILE) {
+    // attention_tc's variant code: 1 = two tiles per CTA, 2 = split softmax, 3 = one tile per CTA
+    int variant = impl == LR_ATTN_TCGEN05_SPLIT ? 2 : (impl == LR_ATTN_TCGEN05_2TILE ? 1 : 3);
+    if (impl == LR_ATTN_TCGEN05 && head_dim == 128) variant = kHd128Product;
     return attention_tc(q, k, v, o, ld_qkv, ld_o, n_seq, rows_per_seq, seq_start, seq_len, n_heads, head_dim, causal,
-                        scale, impl == LR_ATTN_TCGEN05_SPLIT ? 2 : (impl == LR_ATTN_TCGEN05 ? 3 : 1), s);
+                        scale, variant, s);
+  }
   if (impl != LR_ATTN_MMA_SYNC) return LR_ERR_BAD_ARG;
   if (head_dim == 64 && !causal)
     return launch_attn<64, false>(q, k, v, o, ld_qkv, ld_o, n_seq, rows_per_seq, seq_start, seq_len, n_heads, scale, s);

@@ -79,11 +79,15 @@ struct AttnTcCfg {
   // head_dim 128 (Llama decoder of the LLaVA-v1.6 branch): S (128) + O (128 + 16) columns exceed 256 and one CTA
   // needs 136 KB of smem, so it runs one CTA per SM with the 2-stage K/V ring and all 512 TMEM columns.
   static constexpr bool kOnePerSm = NT == 2 || HD > 96;
-  static constexpr int kStages = kOnePerSm ? 2 : 1;
+  // head_dim 128 with two tiles: S_A, S_B, O_A, O_B take all 512 TMEM columns, so there is no room for the 16 row-sum
+  // columns of the ones trick - the softmax threads keep the row sums in registers instead (fp32 sum of the un-rounded
+  // exponentials, like flash-attention 2) - and 227 KB of smem allow only a single K/V stage.
+  static constexpr bool kOnes = !(HD == 128 && NT == 2);
+  static constexpr int kStages = !kOnePerSm ? 1 : (kOnes ? 2 : 1);
   static constexpr int kTmemCols = kOnePerSm ? 512 : 256;
   static constexpr int kAtoms = HD / 32;
   static constexpr int kTileBytes = kAtoms * kAtomBytes;         // one Q / K tile, and the TMA-loaded part of a V tile
-  static constexpr int kVTileBytes = (kAtoms + 1) * kAtomBytes;  // V tile + one atom of ones (row sums via the MMA)
+  static constexpr int kVTileBytes = (kAtoms + (kOnes ? 1 : 0)) * kAtomBytes;  // V tile + one atom of ones (row sums via the MMA)
   static constexpr int kSmemBytes = NT * kTileBytes /*Q*/ + kStages * kTileBytes /*K*/ + kStages * kVTileBytes /*V*/ +
                                     NT * kPBytes + 256 /*barriers*/ + (NT == 2 ? 2048 : 0) /*row-max exchange*/;
 };
@@ -104,7 +108,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
   constexpr int NA = Cfg::kAtoms;
   constexpr int TILE = Cfg::kTileBytes;
   constexpr int VTILE = Cfg::kVTileBytes;
-  constexpr int HDX = HD + 16;  // O columns incl. the row-sum columns
+  constexpr bool ONES = Cfg::kOnes;
+  constexpr int HDX = HD + (ONES ? 16 : 0);  // O columns incl. the row-sum columns
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // the swizzled tiles need a 1024 B aligned base
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
   uint8_t* smem = smem_raw;
@@ -168,7 +173,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     tmem_relinquish();
   }
   // the ones atom of both V stages (bf16 1.0 everywhere, so the swizzle is irrelevant)
-  for (int i = threadIdx.x; i < NS * kAtomBytes / 16; i += kThreads) {
+  for (int i = threadIdx.x; ONES && i < NS * kAtomBytes / 16; i += kThreads) {
     const int st = i / (kAtomBytes / 16), o16 = i % (kAtomBytes / 16);
     *reinterpret_cast<uint4*>(sV + st * VTILE + NA * kAtomBytes + o16 * 16) =
         make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
@@ -319,6 +324,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     uint8_t* prow = sP + x * kPBytes + r * 128;
     float m_ref = -INFINITY;
+    float l_reg[4] = {0.f, 0.f, 0.f, 0.f};  // row sum kept in registers when there are no ones columns (!ONES)
     const int nx = nblk[x];
     const bool tr = (q == 0 && lane == 0 && h == 0);
     for (int j = 0; j < nx; ++j) {
@@ -373,6 +379,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         m_ref = mx;
       }
       const float msafe = (m_ref == -INFINITY) ? 0.f : m_ref;
+      if constexpr (!ONES) {
+        if (grow) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) l_reg[t] *= alpha;
+        }
+      }
       if (tr) ATTN_TRACE(1 + x, 3, j);
       // P_x buffer and O_x may be touched only after O_x += P_x(j-1) V_(j-1) has retired
       if (j > 0) {
@@ -380,7 +392,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         tc_fence_after();
         if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll 1
-          for (int c = h; c < HD / 32 + 1; c += SPLIT) {  // +1: the chunk that holds the row-sum column
+          for (int c = h; c < HD / 32 + (ONES ? 1 : 0); c += SPLIT) {  // +1: the chunk that holds the row-sum column
             uint32_t ov[32];
             tmem_ld_32x32(tm_O[x] + lane_addr + c * 32, ov);
             tmem_ld_wait();
@@ -399,9 +411,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       for (int c = 0; c < NCH; ++c) {
         uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          pk[i] = pack_bf16x2(exp2f(fmaf(__uint_as_float(sv[c][2 * i]), scale_log2, -msafe)),
-                              exp2f(fmaf(__uint_as_float(sv[c][2 * i + 1]), scale_log2, -msafe)));
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = exp2f(fmaf(__uint_as_float(sv[c][2 * i]), scale_log2, -msafe));
+          const float p1 = exp2f(fmaf(__uint_as_float(sv[c][2 * i + 1]), scale_log2, -msafe));
+          if constexpr (!ONES) {
+            l_reg[(2 * i) & 3] += p0;
+            l_reg[(2 * i + 1) & 3] += p1;
+          }
+          pk[i] = pack_bf16x2(p0, p1);
+        }
         const int cg = h * NCH + c;  // chunk index inside the 128-column row
         uint8_t* base = prow + (cg >> 1) * (kPBytes / 2);
 #pragma unroll
@@ -425,7 +443,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       mbar_wait(&o_final[x], 0);
       tc_fence_after();
       float inv;
-      {
+      if constexpr (!ONES) {
+        const float l_sum = (l_reg[0] + l_reg[1]) + (l_reg[2] + l_reg[3]);
+        inv = l_sum > 0.f ? 1.f / l_sum : 0.f;
+      } else {
         uint32_t lv[32];
         tmem_ld_32x32(tm_O[x] + lane_addr + HD, lv);  // column HD = sum_j P_ij (accumulated by the PV MMAs)
         tmem_ld_wait();
@@ -534,8 +555,11 @@ int attention_tc(const void* q, const void* k, const void* v, void* o, int ld_qk
   LR_ATTN_CASE(64, false)
   LR_ATTN_CASE(96, true)
 #undef LR_ATTN_CASE
-  if (head_dim == 128 && causal) {  // only the one-tile configuration fits (smem / TMEM, see AttnTcCfg)
-    if (split != 3) return LR_ERR_BAD_ARG;
+  if (head_dim == 128 && causal) {  // one CTA per SM either way (smem / TMEM, see AttnTcCfg); no split-softmax form
+    if (split == 2) return LR_ERR_BAD_ARG;
+    if (split == 1)  // two query tiles per CTA, row sums in registers
+      return launch_attn_tc<128, true, 1, 2>(q, total_rows, ld_qkv, 0, int(kd), int(vd), o, ld_o, n_seq, rows_per_seq,
+                                             seq_start, seq_len, n_heads, scale, s);
     return launch_attn_tc<128, true, 1, 1>(q, total_rows, ld_qkv, 0, int(kd), int(vd), o, ld_o, n_seq, rows_per_seq,
                                            seq_start, seq_len, n_heads, scale, s);
   }

@@ -29,8 +29,8 @@ _models = {}
 
 
 # ----------------------------------------------------------------------------------------------- kernels
-@pytest.mark.parametrize("impl", [L.ATTN_TCGEN05, L.ATTN_MMA_SYNC])
-@pytest.mark.parametrize("heads,T,nseq", [(4, 130, 3), (2, 2395, 2), (32, 700, 2), (1, 128, 1)])
+@pytest.mark.parametrize("impl", [L.ATTN_TCGEN05, L.ATTN_MMA_SYNC, L.ATTN_TCGEN05_2TILE, L.ATTN_TCGEN05_1TILE])
+@pytest.mark.parametrize("heads,T,nseq", [(4, 130, 3), (2, 2395, 2), (32, 700, 2), (1, 128, 1), (3, 257, 2)])
 def test_attention_hd128(heads, T, nseq, impl):
     hd = 128
     D = heads * hd
@@ -51,12 +51,12 @@ def test_attention_hd128(heads, T, nseq, impl):
         check_close(o[s * T:(s + 1) * T, :D], ref, f"attention hd128 seq {s}", atol=1e-2, rtol=2e-2)
 
 
-def test_attention_hd128_rejects_two_tile_variants():
+def test_attention_hd128_rejects_split_softmax_variant():
     qkv = rnd(256, 3 * 128, seed=1)
     o = torch.empty(256, 128, dtype=bf, device=DEV)
-    for impl in (L.ATTN_TCGEN05_SPLIT, L.ATTN_TCGEN05_2TILE):
-        with pytest.raises(RuntimeError, match="LR_ERR_BAD_ARG"):
-            ops.attention(qkv, qkv[:, 128:], qkv[:, 256:], o, 384, 128, 1, 256, None, None, 1, 128, True, 0.1, impl)
+    with pytest.raises(RuntimeError, match="LR_ERR_BAD_ARG"):
+        ops.attention(qkv, qkv[:, 128:], qkv[:, 256:], o, 384, 128, 1, 256, None, None, 1, 128, True, 0.1,
+                      L.ATTN_TCGEN05_SPLIT)
 
 
 @pytest.mark.parametrize("impl", [L.GEMM_TCGEN05, L.GEMM_SIMT])
