@@ -41,6 +41,11 @@ extern "C" {
 #define LR_EPI_BIAS_RESIDUAL 5  /* C = bf16(bf16(acc+bias) + R)                    CLIP out_proj / fc2 */
 #define LR_EPI_SWIGLU 6         /* W rows packed [gate128|up128] per 256; C[:,N/2] = up*silu(gate)  Phi3MLP (:566-572) */
 #define LR_EPI_ROPE 7           /* su-RoPE on columns [0, rope_cols) (only through lr_gemm_rope_bf16)                  */
+#define LR_EPI_BIAS_SWIGLU 8    /* as LR_EPI_SWIGLU with gate/up biases (packed like the W rows): C = bf16(up+b_u)*silu(bf16(gate+b_g))
+                                   Qwen2_5_VLMLP(bias=True) of the vision blocks (transformers modeling_qwen2_5_vl.py:77-88) */
+#define LR_EPI_BIAS_ROPE 9      /* x = bf16(acc + bias), then LR_EPI_ROPE on columns [0, rope_cols) (only lr_gemm_rope_ex_bf16) */
+#define LR_EPI_BIAS_ROPE_F32 10 /* x = bf16(acc + bias); out = bf16(x1*cos - x2*sin), bf16(x2*cos + x1*sin) in fp32 with fp32
+                                   tables: apply_rotary_pos_emb_vision (modeling_qwen2_5_vl.py:156-167) (only lr_gemm_rope_ex_bf16) */
 
 #define LR_GEMM_TCGEN05 0 /* tcgen05.mma + TMEM + TMA pipeline (product path): CTA-pair kernel when N % 256 == 0 and
                              M > 256, else the single-CTA kernel */
@@ -71,6 +76,15 @@ int lr_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int ld
 int lr_gemm_rope_bf16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
                       const int* position_ids, const void* cos_tab, const void* sin_tab, int rope_cols, int head_dim,
                       int impl, void* stream);
+
+/* lr_gemm_rope_bf16 with a linear bias (bf16 [N], packed like the W rows, added to every column before the rounding /
+ * rotation) and a table mode: epilogue = LR_EPI_BIAS_ROPE (bf16 tables, op-by-op bf16 rounding: the Qwen2 decoder's
+ * q/k/v projection + apply_multimodal_rotary_pos_emb, transformers modeling_qwen2_5_vl.py:627-669, 725-739) or
+ * LR_EPI_BIAS_ROPE_F32 (fp32 tables cos/sin[pos, head_dim/2], one rounding: the vision blocks' qkv +
+ * apply_rotary_pos_emb_vision, :156-167, 231-238). position_ids == NULL means pos = row (per-token tables). */
+int lr_gemm_rope_ex_bf16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
+                         const void* bias, const int* position_ids, const void* cos_tab, const void* sin_tab,
+                         int rope_cols, int head_dim, int epilogue, void* stream);
 
 /* y[i,:] = w * bf16(x[r,:] * rsqrt(mean(x[r,:]^2) + eps)),  r = row_index ? row_index[i] : i.
  * Replaces Phi3RMSNorm.forward (modeling_phi3_v.py:386-391). cols % 8 == 0, cols <= 8192. */
@@ -110,6 +124,18 @@ int lr_clip_embed_ln(const void* patch, const void* class_emb, const void* pos_e
 int lr_attention_bf16(const void* q, const void* k, const void* v, void* o, int ld_qkv, int ld_o, int n_seq,
                       int rows_per_seq, const int* seq_start, const int* seq_len, int n_heads, int head_dim,
                       int causal, float scale, int impl, void* stream);
+
+/* lr_attention_bf16 (tcgen05 kernels only) with grouped-query attention (query head h reads K/V head
+ * h / (n_heads / n_kv_heads); k and v are n_kv_heads*head_dim wide) and, when seq_base != NULL, PACKED variable-length
+ * sequences: sequence s owns exactly rows [seq_base[s], seq_base[s] + seq_len[s]) of the total_rows-row buffer and
+ * max_len bounds every seq_len (it sizes the grid); rows of other sequences are never written. seq_base == NULL: the
+ * slot layout of lr_attention_bf16 (total_rows = n_seq * max_len). head_dim 96 non-causal (the Qwen2.5-VL vision tower's
+ * head_dim 80 zero-padded to 96: window attention = packed sequences of <= 64 tokens, full attention = one sequence per
+ * image; replaces Qwen2_5_VLVisionAttention's varlen flash-attention call, transformers modeling_qwen2_5_vl.py:244-262)
+ * and head_dim 128 causal GQA (Qwen2_5_VLAttention, :739-753) in addition to the lr_attention_bf16 shapes. */
+int lr_attention_ex_bf16(const void* q, const void* k, const void* v, void* o, int ld_qkv, int ld_o, int total_rows,
+                         int n_seq, int max_len, const int* seq_base, const int* seq_start, const int* seq_len,
+                         int n_heads, int n_kv_heads, int head_dim, int causal, float scale, int impl, void* stream);
 
 /* In-place su/longrope rotary embedding on the q and k thirds of a fused qkv buffer [rows, 3*n_heads*head_dim]:
  * x = bf16(bf16(x*cos) + bf16(rot_half(x)*sin)) with bf16 tables cos/sin[pos, head_dim/2].
@@ -173,6 +199,12 @@ int lr_anyres_embed_scatter_bf16(const int64_t* input_ids, const int* img_ord, c
 int lr_skipca_scores(const void* q, int ldq, const void* kv, int ldkv, const int* plan, float* scores, int B, int H,
                      int max_nv, void* stream);
 
+/* lr_skipca_scores with the score written for the rows N_v(b) <= j < max_nv as a parameter: 0 reproduces the Phi-3
+ * arm (zero-padded vision rows: q.0 = 0), bf16(-1e4) = -9984 the qwen arm's masked_fill (rw_model_general_preference.py
+ * :387-392; K/V rows = hidden_states[0] at the token-id-151643 positions, :358-371, gathered by lr_compact_rows_bf16). */
+int lr_skipca_scores_ex(const void* q, int ldq, const void* kv, int ldkv, const int* plan, float* scores, int B, int H,
+                        int max_nv, float pad_score, void* stream);
+
 /* reward[b,:] = value_head( ca_ln( x_b + sum_j softmax_j(scores_b over max_nv incl. zero-padded rows) V_bj ) ).
  * scores == NULL skips the cross-attention (BT / no-SkipCA models: reward = value_head(x_b)).
  * Replaces rw_model_general_preference.py:381-386 (softmax, bmm, residual, ca_layernorm) and :407-448. */
@@ -211,6 +243,34 @@ int lr_hd_pack_f32(const uint8_t* img, int rh, int rw, int pad_top, int pad_left
  * The base view is the same call with grid 1x1 on the image resized to 336x336. */
 int lr_patch_pack_f32(const uint8_t* img, int rh, int rw, int pad_top, int pad_left, int grid_h, int grid_w,
                       const float* lut768, float* out, void* stream);
+
+/* ---- Qwen2.5-VL branch (reference model_type == 'qwen', rw_model_general_preference.py:354-371) ------------------ */
+
+/* out[i, 0:K] = bf16(pixels[src_row[i], 0:K]), out[i, K:Kpad] = 0 (src_row NULL = identity): the A operand of the
+ * patch-embedding GEMM, rows already in the vision tower's window order. pixels = the processor's flattened patches
+ * fp32 [T, 3*2*14*14]. Replaces the .to(bf16) + Conv3d im2col of Qwen2_5_VisionPatchEmbed.forward and the
+ * hidden_states[window_index] gather (transformers modeling_qwen2_5_vl.py:108-114, 484-486). K % 4 == 0, Kpad % 8 == 0. */
+int lr_patch_rows_bf16(const float* pixels, const int* src_row, void* out, int ldo, int rows, int K, int Kpad,
+                       void* stream);
+
+/* M-RoPE plan, images only: pos3[c, b*S+s] (c = temporal, height, width; int32, comp stride B*S) as
+ * Qwen2_5_VLForConditionalGeneration.get_rope_index of transformers 4.50 (the release the reference pins; called from
+ * the forward the reference invokes at rw_model_general_preference.py:357) computes them from input_ids,
+ * image_grid_thw (int32 [n_images,3], device) and the attention mask - padded positions get 0 - and the per-token rotary
+ * rows cos_out/sin_out[b*S+s, i] = cos_tab/sin_tab[pos3[sec(i)], i] (bf16 [max_pos, half] tables; sec = 0 for
+ * i < sec0, 1 for i < sec0+sec1, else 2: apply_multimodal_rotary_pos_emb, modeling_qwen2_5_vl.py:627-669).
+ * run_count: int32 [B] scratch (image runs per sample). flags |= 2 when a run of image tokens disagrees with
+ * image_grid_thw, |= 4 when a position reaches max_pos. S <= 12800. Two launches. */
+int lr_mrope_plan(const int64_t* input_ids, const int64_t* attention_mask, int B, int S, int64_t image_token_id,
+                  const int* grid_thw, int n_images, int merge, int* run_count, const void* cos_tab,
+                  const void* sin_tab, int max_pos, int half, int sec0, int sec1, int* pos3, void* cos_out,
+                  void* sin_out, int* flags, void* stream);
+
+/* dst[plan[b].ROW_BASE + ord[b,s], :] = src[b*S+s, :] for every position with ord[b,s] >= 0 (ord = the img_ord output
+ * of lr_token_plan_ex for some token id). Replaces the vision_pad gather loop of the reference's qwen SkipCA arm
+ * (rw_model_general_preference.py:362-371). cols % 8 == 0. */
+int lr_compact_rows_bf16(const void* src, int lds, const int* ord, const int* plan, void* dst, int ldd, int B, int S,
+                         int cols, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libllavareward.so")
 
 LR_OK = 0
 EPI_NONE, EPI_BIAS, EPI_BIAS_QUICKGELU, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_BIAS_RESIDUAL, EPI_SWIGLU = range(7)
+EPI_BIAS_SWIGLU, EPI_BIAS_ROPE, EPI_BIAS_ROPE_F32 = 8, 9, 10
 GEMM_TCGEN05, GEMM_SIMT, GEMM_TCGEN05_PAIR, GEMM_TCGEN05_SINGLE = 0, 1, 2, 3
 ATTN_TCGEN05, ATTN_MMA_SYNC, ATTN_TCGEN05_SPLIT, ATTN_TCGEN05_2TILE, ATTN_TCGEN05_1TILE = 0, 1, 2, 3, 4
 PLAN_STRIDE = 8
@@ -45,6 +46,12 @@ SIGNATURES = {
     "lr_resample_u8": ([p, i32, i32, p, i32, i32, i32, p, p, i32, p], i32),
     "lr_patch_pack_f32": ([p, i32, i32, i32, i32, i32, i32, p, p, p], i32),
     "lr_hd_pack_f32": ([p, i32, i32, i32, i32, i32, i32, p, p, p, i32, p], i32),
+    "lr_gemm_rope_ex_bf16": ([p, i32, p, i32, p, i32, i32, i32, i32, p, p, p, p, i32, i32, i32, p], i32),
+    "lr_attention_ex_bf16": ([p, p, p, p, i32, i32, i32, i32, i32, p, p, p, i32, i32, i32, i32, f32, i32, p], i32),
+    "lr_skipca_scores_ex": ([p, i32, p, i32, p, p, i32, i32, i32, f32, p], i32),
+    "lr_patch_rows_bf16": ([p, p, p, i32, i32, i32, i32, p], i32),
+    "lr_mrope_plan": ([p, p, i32, i32, i64, p, i32, i32, p, p, p, i32, i32, i32, i32, p, p, p, p, p], i32),
+    "lr_compact_rows_bf16": ([p, i32, p, p, p, i32, i32, i32, i32, p], i32),
 }
 
 

@@ -12,7 +12,7 @@ from typing import Callable, Dict, Optional, Tuple
 
 import torch
 
-from .config import LlavaNextRewardConfig, RewardConfig
+from .config import LlavaNextRewardConfig, QwenVLRewardConfig, RewardConfig
 
 
 def _load_file(path: str) -> Dict[str, torch.Tensor]:
@@ -148,6 +148,88 @@ def llava_checkpoint_provider(cfg: LlavaNextRewardConfig, pretrain_dir: str, pm_
                     tensors["value_head." + k.split(".")[-1]] = v
                 if ft_projector and "multi_modal_projector" in k:
                     tensors["multi_modal_projector." + ".".join(k.split(".")[-2:])] = v
+
+    def get(name: str) -> torch.Tensor:
+        if name not in tensors:
+            raise KeyError(f"checkpoint is missing parameter {name!r}")
+        return tensors[name]
+
+    return cfg, get
+
+
+def _canonical_qwen_name(k: str) -> str:
+    """Any era of transformers Qwen2.5-VL state_dict name -> the 4.50 names the reference was written against
+    (`visual.*`, `model.*` = text decoder)."""
+    if k.startswith("model.visual."):
+        return k[len("model."):]
+    if k.startswith("model.language_model."):
+        return "model." + k[len("model.language_model."):]
+    return k
+
+
+def qwen_checkpoint_provider(cfg: QwenVLRewardConfig, pretrain_dir: str, pm_path: Optional[str],
+                             ft_projector: bool = False):
+    """HF Qwen2.5-VL checkpoint directory + the reference's save_model_lora layout for the qwen branch (key selection
+    of reference eval/reward_adaptor_loader.py:80-105, incl. the `merger` remap of :93-103) -> provider with
+    synth.qwen_param_specs names."""
+    if not os.path.isdir(pretrain_dir):
+        raise FileNotFoundError(f"args.pretrain={pretrain_dir!r} is not a local directory (no network access: "
+                                "hub ids cannot be resolved) - use 'synthetic' for random-init weights")
+    with open(os.path.join(pretrain_dir, "config.json")) as f:
+        hf = json.load(f)
+    t = hf.get("text_config", hf)      # 4.50-era config.json keeps the text fields at top level
+    v = hf.get("vision_config", {})
+    cfg.vocab_size = t.get("vocab_size", cfg.vocab_size)
+    cfg.hidden_size = t.get("hidden_size", cfg.hidden_size)
+    cfg.intermediate_size = t.get("intermediate_size", cfg.intermediate_size)
+    cfg.num_layers = t.get("num_hidden_layers", cfg.num_layers)
+    cfg.num_heads = t.get("num_attention_heads", cfg.num_heads)
+    cfg.num_kv_heads = t.get("num_key_value_heads", cfg.num_kv_heads)
+    cfg.rms_eps = t.get("rms_norm_eps", cfg.rms_eps)
+    rp = t.get("rope_parameters") or t.get("rope_scaling") or {}
+    cfg.rope_theta = rp.get("rope_theta", t.get("rope_theta", cfg.rope_theta))
+    cfg.mrope_section = list(rp.get("mrope_section", cfg.mrope_section))
+    cfg.image_token_id = hf.get("image_token_id", cfg.image_token_id)
+    cfg.vit_depth = v.get("depth", cfg.vit_depth)
+    cfg.vit_hidden = v.get("hidden_size", cfg.vit_hidden)
+    cfg.vit_intermediate = v.get("intermediate_size", cfg.vit_intermediate)
+    cfg.vit_heads = v.get("num_heads", cfg.vit_heads)
+    cfg.vit_window = v.get("window_size", cfg.vit_window)
+    cfg.vit_fullatt = list(v.get("fullatt_block_indexes", cfg.vit_fullatt))
+    tensors: Dict[str, torch.Tensor] = {}
+    files = sorted(glob.glob(os.path.join(pretrain_dir, "*.safetensors"))) or \
+        sorted(glob.glob(os.path.join(pretrain_dir, "pytorch_model*.bin")))
+    if not files:
+        raise FileNotFoundError(f"no *.safetensors / pytorch_model*.bin under {pretrain_dir}")
+    for fpath in files:
+        tensors.update({_canonical_qwen_name(k): val for k, val in _load_file(fpath).items()})
+    cfg.use_lora = False
+    if pm_path:
+        for cand in ("adapter_model.safetensors", "adapter_model.bin"):
+            p = os.path.join(pm_path, "lora", cand)
+            if os.path.exists(p):
+                for k, val in _load_file(p).items():
+                    k = _canonical_qwen_name(k.replace("base_model.model.", "", 1).replace(".default", ""))
+                    tensors[k] = val
+                cfg.use_lora = True
+                acfg = os.path.join(pm_path, "lora", "adapter_config.json")
+                if os.path.exists(acfg):
+                    with open(acfg) as f:
+                        a = json.load(f)
+                    cfg.lora_rank, cfg.lora_alpha = int(a.get("r", cfg.lora_rank)), float(a.get("lora_alpha", cfg.lora_alpha))
+                break
+        heads = os.path.join(pm_path, "pytorch_model.bin")
+        if os.path.exists(heads):
+            sd = torch.load(heads, map_location="cpu", weights_only=True)
+            for k, val in sd.items():
+                leaf = k.split(".")[-1]
+                for mod in ("value_head", "W_q", "W_k", "W_v", "ca_layernorm"):
+                    if mod in k:
+                        tensors[f"{mod}.{leaf}"] = val
+                if ft_projector and "merger" in k:
+                    # reference :93-103: keys are cut to their last two components ('ln_q.weight', '0.weight', ...)
+                    tail = ".".join(k.split(".")[-2:])
+                    tensors["visual.merger." + (tail if tail.startswith("ln_q") else "mlp." + tail)] = val
 
     def get(name: str) -> torch.Tensor:
         if name not in tensors:

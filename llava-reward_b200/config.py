@@ -195,3 +195,111 @@ def anyres_geometry(original_hw, pinpoints, image_size: int = 336, patch: int = 
     keep_h, keep_w = cur_h - 2 * top, cur_w - 2 * left
     return dict(grid_h=gh, grid_w=gw, n_patches=gh * gw + 1, top=top, left=left, keep_h=keep_h, keep_w=keep_w,
                 n_tokens=side * side + keep_h * (keep_w + 1))
+
+
+# --------------------------------------------------------------------------------------
+# Qwen2.5-VL backbone: reference branch model_type == 'qwen'
+# (rw_model_general_preference.py:354-371, 387-397; eval/reward_adaptor_loader.py:64-109)
+# --------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class QwenVLRewardConfig:
+    """Qwen2.5-VL reward model (BASELINE.json configs[3]): window-attention ViT (RMSNorm, SwiGLU MLP with biases, 2D
+    rotary, 2x2 patch merger) -> Qwen2 decoder (GQA, q/k/v biases, M-RoPE sections [16,24,24]) with LoRA on
+    q/k/v/o/gate/up/down (create_lora_config_qwen, llava_reward/utils/utils.py:223-242) -> final norm -> optional SkipCA
+    (qwen arm, :387-397) -> value head on the last valid token. Defaults = Qwen/Qwen2.5-VL-7B-Instruct."""
+    vocab_size: int = 152064
+    hidden_size: int = 3584
+    intermediate_size: int = 18944
+    num_layers: int = 28
+    num_heads: int = 28
+    num_kv_heads: int = 4
+    rms_eps: float = 1e-6
+    rope_theta: float = 1000000.0
+    mrope_section: List[int] = dataclasses.field(default_factory=lambda: [16, 24, 24])
+    image_token_id: int = 151655
+    video_token_id: int = 151656
+    vision_start_token_id: int = 151652
+    vision_end_token_id: int = 151653
+    pad_token_id: int = 151643     # also the token id the reference's SkipCA arm keys its "vision" rows on (:358)
+    # vision tower
+    vit_depth: int = 32
+    vit_hidden: int = 1280
+    vit_intermediate: int = 3420
+    vit_heads: int = 16
+    vit_patch: int = 14
+    vit_temporal_patch: int = 2
+    vit_merge: int = 2
+    vit_window: int = 112
+    vit_fullatt: List[int] = dataclasses.field(default_factory=lambda: [7, 15, 23, 31])
+    vit_eps: float = 1e-6
+    # LoRA + heads
+    lora_rank: int = 128
+    lora_alpha: float = 256.0
+    use_lora: bool = True
+    is_general_preference: bool = False
+    value_head_dim: int = 2
+    general_preference_tau: float = 0.1
+    add_cross_attention: bool = False
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden_size // self.num_heads
+
+    @property
+    def vit_head_dim(self) -> int:
+        return self.vit_hidden // self.vit_heads
+
+    @property
+    def patch_dim(self) -> int:
+        return 3 * self.vit_temporal_patch * self.vit_patch * self.vit_patch
+
+    @property
+    def lora_scale(self) -> float:
+        return self.lora_alpha / self.lora_rank
+
+    @property
+    def vhd(self) -> int:
+        return self.value_head_dim if self.is_general_preference else 1
+
+
+def qwen_window_plan(grid_thw, merge: int = 2, window: int = 112, patch: int = 14):
+    """Host-side index plan of the Qwen2.5-VL vision tower for a list of (t, h, w) patch grids
+    (transformers modeling_qwen2_5_vl.py: rot_pos_emb :382-409, get_window_index :411-453, forward :470-500):
+      window_index [T/4]  merged-unit order after the window permutation (new unit j = old unit window_index[j])
+      src_row [T]         patch row of window-ordered token i
+      pos_hw [T, 2]       (h, w) patch coordinates of window-ordered token i (rotary)
+      win_cu              cumulative token counts of the non-empty windows (cu_window_seqlens after unique_consecutive)
+      img_cu              cumulative token counts per frame (cu_seqlens of the full-attention blocks)."""
+    import numpy as np
+
+    unit = merge * merge
+    wsz = window // merge // patch
+    widx, win_cu, img_cu, pos = [], [0], [0], []
+    base = 0
+    for t, h, w in grid_thw:
+        t, h, w = int(t), int(h), int(w)
+        lh, lw = h // merge, w // merge
+        hp = np.broadcast_to(np.arange(h)[:, None], (h, w)).reshape(lh, merge, lw, merge).transpose(0, 2, 1, 3).reshape(-1)
+        wp = np.broadcast_to(np.arange(w)[None, :], (h, w)).reshape(lh, merge, lw, merge).transpose(0, 2, 1, 3).reshape(-1)
+        pos.append(np.tile(np.stack([hp, wp], -1), (t, 1)))
+        idx = np.arange(t * lh * lw).reshape(t, lh, lw)
+        ph, pw_ = wsz - lh % wsz, wsz - lw % wsz
+        nh, nw = (lh + ph) // wsz, (lw + pw_) // wsz
+        pad = np.full((t, lh + ph, lw + pw_), -100, dtype=np.int64)
+        pad[:, :lh, :lw] = idx
+        pad = pad.reshape(t, nh, wsz, nw, wsz).transpose(0, 1, 3, 2, 4).reshape(t, nh * nw, wsz, wsz)
+        lens = (pad != -100).sum((2, 3)).reshape(-1)
+        flat = pad.reshape(-1)
+        widx.append(flat[flat != -100] + base)
+        for n in lens:
+            if n > 0:
+                win_cu.append(win_cu[-1] + int(n) * unit)
+        for _ in range(t):
+            img_cu.append(img_cu[-1] + h * w)
+        base += t * lh * lw
+    widx = np.concatenate(widx)
+    pos = np.concatenate(pos, 0)
+    src_row = (widx[:, None] * unit + np.arange(unit)[None, :]).reshape(-1)
+    return dict(window_index=widx.astype(np.int32), src_row=src_row.astype(np.int32),
+                pos_hw=pos[src_row].astype(np.int32), win_cu=np.asarray(win_cu, dtype=np.int32),
+                img_cu=np.asarray(img_cu, dtype=np.int32))

@@ -243,9 +243,9 @@ static int launch_attn(const void* q, const void* k, const void* v, void* o, int
   return lr_launch_status();
 }
 
-int attention_tc(const void* q, const void* k, const void* v, void* o, int ld_qkv, int ld_o, int n_seq,
-                 int rows_per_seq, const int* seq_start, const int* seq_len, int n_heads, int head_dim, int causal,
-                 float scale, int split, cudaStream_t s);
+int attention_tc(const void* q, const void* k, const void* v, void* o, int ld_qkv, int ld_o, int total_rows, int n_seq,
+                 int rows_per_seq, const int* seq_base, const int* seq_start, const int* seq_len, int n_heads,
+                 int n_kv_heads, int head_dim, int causal, float scale, int split, cudaStream_t s);
 
 }  // namespace lr
 
@@ -266,8 +266,8 @@ extern "C" int lr_attention_bf16(const void* q, const void* k, const void* v, vo
     // attention_tc's variant code: 1 = two tiles per CTA, 2 = split softmax, 3 = one tile per CTA
     int variant = impl == LR_ATTN_TCGEN05_SPLIT ? 2 : (impl == LR_ATTN_TCGEN05_2TILE ? 1 : 3);
     if (impl == LR_ATTN_TCGEN05 && head_dim == 128) variant = kHd128Product;
-    return attention_tc(q, k, v, o, ld_qkv, ld_o, n_seq, rows_per_seq, seq_start, seq_len, n_heads, head_dim, causal,
-                        scale, variant, s);
+    return attention_tc(q, k, v, o, ld_qkv, ld_o, n_seq * rows_per_seq, n_seq, rows_per_seq, nullptr, seq_start, seq_len,
+                        n_heads, n_heads, head_dim, causal, scale, variant, s);
   }
   if (impl != LR_ATTN_MMA_SYNC) return LR_ERR_BAD_ARG;
   if (head_dim == 64 && !causal)
@@ -281,4 +281,25 @@ extern "C" int lr_attention_bf16(const void* q, const void* k, const void* v, vo
   if (head_dim == 128 && causal)  // Llama decoder of the LLaVA-v1.6 branch
     return launch_attn<128, true>(q, k, v, o, ld_qkv, ld_o, n_seq, rows_per_seq, seq_start, seq_len, n_heads, scale, s);
   return LR_ERR_BAD_ARG;
+}
+
+
+extern "C" int lr_attention_ex_bf16(const void* q, const void* k, const void* v, void* o, int ld_qkv, int ld_o,
+                                    int total_rows, int n_seq, int max_len, const int* seq_base, const int* seq_start,
+                                    const int* seq_len, int n_heads, int n_kv_heads, int head_dim, int causal,
+                                    float scale, int impl, void* stream) {
+  using namespace lr;
+  LR_CHECK_ARG(q && k && v && o && n_seq > 0 && max_len > 0 && n_heads > 0 && n_kv_heads > 0 && total_rows > 0);
+  if (seq_base) LR_CHECK_ARG(seq_len != nullptr);
+  else LR_CHECK_ARG(total_rows == n_seq * max_len);
+  if ((ld_qkv % 8) || (ld_o % 8) || (reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
+                                     reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(o)) & 15)
+    return LR_ERR_ALIGN;
+  int variant = impl == LR_ATTN_TCGEN05_SPLIT ? 2 : (impl == LR_ATTN_TCGEN05_2TILE ? 1 : 3);
+  if (impl == LR_ATTN_TCGEN05 && head_dim == 128) variant = kHd128Product;
+  if (impl != LR_ATTN_TCGEN05 && impl != LR_ATTN_TCGEN05_SPLIT && impl != LR_ATTN_TCGEN05_2TILE &&
+      impl != LR_ATTN_TCGEN05_1TILE)
+    return LR_ERR_BAD_ARG;
+  return attention_tc(q, k, v, o, ld_qkv, ld_o, total_rows, n_seq, max_len, seq_base, seq_start, seq_len, n_heads,
+                      n_kv_heads, head_dim, causal, scale, variant, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -101,8 +101,8 @@ struct AttnTcCfg {
 template <int HD, bool CAUSAL, int SPLIT, int NT>
 __global__ void __launch_bounds__(128 + 128 * NT * SPLIT, AttnTcCfg<HD, NT>::kOnePerSm ? 1 : 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o, int ld_o, int rows_per_seq,
-               const int* __restrict__ seq_start, const int* __restrict__ seq_len, int q_col0, int k_col0, int v_col0,
-               float scale_log2) {
+               const int* __restrict__ seq_base, const int* __restrict__ seq_start, const int* __restrict__ seq_len,
+               int q_col0, int k_col0, int v_col0, int kv_group, float scale_log2) {
   using Cfg = AttnTcCfg<HD, NT>;
   constexpr int NS = Cfg::kStages;
   constexpr int NA = Cfg::kAtoms;
@@ -134,12 +134,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int seq = blockIdx.z, head = blockIdx.y;
+  const int kv_head = head / kv_group;  // grouped-query attention: kv_group query heads share one K/V head
   const int qt = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
   const int m0 = qt * 128 * NT;
-  const int start = seq_start ? seq_start[seq] : 0;
+  // slot layout: sequence s owns rows [s*rows_per_seq, +rows_per_seq), valid run [start, start+len);
+  // packed layout (seq_base != NULL): sequence s owns exactly rows [seq_base[s], +seq_len[s]), rows_per_seq = max len
+  const int start = (seq_start && !seq_base) ? seq_start[seq] : 0;
   const int len = seq_len ? seq_len[seq] : rows_per_seq;
   const int end = start + len;
-  const int slot_row0 = seq * rows_per_seq;
+  const int slot_row0 = seq_base ? seq_base[seq] : seq * rows_per_seq;
 
   int lo[2], hi[2], nblk[2], kv_end[2];
 #pragma unroll
@@ -212,7 +215,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
           const int s = kj % NS;
           mbar_arrive_expect_tx(&k_full[s], TILE);
           for (int a = 0; a < NA; ++a)
-            tma_load_2d(sK + s * TILE + a * kAtomBytes, &tm_qkv, &k_full[s], k_col0 + head * HD + a * 32,
+            tma_load_2d(sK + s * TILE + a * kAtomBytes, &tm_qkv, &k_full[s], k_col0 + kv_head * HD + a * 32,
                         slot_row0 + start + kj * 128);
           ++kj;
         }
@@ -220,7 +223,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
           const int s = vj % NS;
           mbar_arrive_expect_tx(&v_full[s], TILE);
           for (int a = 0; a < NA; ++a)
-            tma_load_2d(sV + s * VTILE + a * kAtomBytes, &tm_qkv, &v_full[s], v_col0 + head * HD + a * 32,
+            tma_load_2d(sV + s * VTILE + a * kAtomBytes, &tm_qkv, &v_full[s], v_col0 + kv_head * HD + a * 32,
                         slot_row0 + start + vj * 128);
           ++vj;
         }
@@ -436,7 +439,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       if (tr) ATTN_TRACE(1 + x, 6, j);
     }
     // epilogue: O / l -> bf16 -> global; rows outside the valid run are zero-filled
-    const bool row_in_slot = row_abs < rows_per_seq;
+    const bool row_in_slot = row_abs < (seq_base ? end : rows_per_seq);  // packed: the next rows are another sequence
     const bool row_valid = row_abs >= lo[x] && row_abs < hi[x];
     bf16* orow = o + size_t(slot_row0 + row_abs) * ld_o + head * HD;
     if (nx > 0) {
@@ -507,8 +510,8 @@ static EncodeTiledFn attn_encode_fn() {
 
 template <int HD, bool CAUSAL, int SPLIT, int NT>
 static int launch_attn_tc(const void* base, int total_rows, int ld_qkv, int q_col0, int k_col0, int v_col0, void* o,
-                          int ld_o, int n_seq, int rows_per_seq, const int* seq_start, const int* seq_len, int n_heads,
-                          float scale, cudaStream_t stream) {
+                          int ld_o, int n_seq, int rows_per_seq, const int* seq_base, const int* seq_start,
+                          const int* seq_len, int n_heads, int kv_group, float scale, cudaStream_t stream) {
   using Cfg = AttnTcCfg<HD, NT>;
   EncodeTiledFn fn = attn_encode_fn();
   if (!fn) return LR_ERR_NO_DRIVER;
@@ -527,44 +530,43 @@ static int launch_attn_tc(const void* base, int total_rows, int ld_qkv, int q_co
     if (e != cudaSuccess) return static_cast<int>(e);
   }
   dim3 grid((rows_per_seq + 128 * NT - 1) / (128 * NT), n_heads, n_seq);
-  kern<<<grid, 128 + 128 * NT * SPLIT, Cfg::kSmemBytes, stream>>>(tm, reinterpret_cast<bf16*>(o), ld_o, rows_per_seq, seq_start,
-                                                      seq_len, q_col0, k_col0, v_col0, scale * 1.4426950408889634f);
+  kern<<<grid, 128 + 128 * NT * SPLIT, Cfg::kSmemBytes, stream>>>(tm, reinterpret_cast<bf16*>(o), ld_o, rows_per_seq, seq_base,
+                                                      seq_start, seq_len, q_col0, k_col0, v_col0, kv_group,
+                                                      scale * 1.4426950408889634f);
   return lr_launch_status();
 }
 
 // q, k, v must be column offsets into ONE row-major buffer (the fused qkv projection): base = q.
-int attention_tc(const void* q, const void* k, const void* v, void* o, int ld_qkv, int ld_o, int n_seq,
-                 int rows_per_seq, const int* seq_start, const int* seq_len, int n_heads, int head_dim, int causal,
-                 float scale, int split, cudaStream_t s) {
+// seq_base == NULL: slot layout (total_rows = n_seq * rows_per_seq); else packed sequences (rows_per_seq = max length).
+int attention_tc(const void* q, const void* k, const void* v, void* o, int ld_qkv, int ld_o, int total_rows, int n_seq,
+                 int rows_per_seq, const int* seq_base, const int* seq_start, const int* seq_len, int n_heads,
+                 int n_kv_heads, int head_dim, int causal, float scale, int split, cudaStream_t s) {
   const ptrdiff_t kd = (reinterpret_cast<const char*>(k) - reinterpret_cast<const char*>(q)) / 2;
   const ptrdiff_t vd = (reinterpret_cast<const char*>(v) - reinterpret_cast<const char*>(q)) / 2;
-  const int width = n_heads * head_dim;
-  if (kd < 0 || vd < 0 || kd + width > ld_qkv || vd + width > ld_qkv) return LR_ERR_BAD_ARG;
-  const int total_rows = n_seq * rows_per_seq;
-#define LR_ATTN_CASE(HD_, CAUSAL_)                                                                                  \
-  if (head_dim == HD_ && bool(causal) == CAUSAL_) {                                                                 \
-    if (split == 2)                                                                                                 \
-      return launch_attn_tc<HD_, CAUSAL_, 2, 2>(q, total_rows, ld_qkv, 0, int(kd), int(vd), o, ld_o, n_seq,          \
-                                                rows_per_seq, seq_start, seq_len, n_heads, scale, s);               \
-    if (split == 3)                                                                                                 \
-      return launch_attn_tc<HD_, CAUSAL_, 1, 1>(q, total_rows, ld_qkv, 0, int(kd), int(vd), o, ld_o, n_seq,          \
-                                                rows_per_seq, seq_start, seq_len, n_heads, scale, s);               \
-    return launch_attn_tc<HD_, CAUSAL_, 1, 2>(q, total_rows, ld_qkv, 0, int(kd), int(vd), o, ld_o, n_seq,            \
-                                              rows_per_seq, seq_start, seq_len, n_heads, scale, s);                 \
+  if (n_kv_heads <= 0 || n_heads % n_kv_heads) return LR_ERR_BAD_ARG;
+  const int kvw = n_kv_heads * head_dim, g = n_heads / n_kv_heads;
+  if (kd < 0 || vd < 0 || kd + kvw > ld_qkv || vd + kvw > ld_qkv || n_heads * head_dim > ld_qkv) return LR_ERR_BAD_ARG;
+#define LR_ATTN_ARGS q, total_rows, ld_qkv, 0, int(kd), int(vd), o, ld_o, n_seq, rows_per_seq, seq_base, seq_start, seq_len, n_heads, g, scale, s
+#define LR_ATTN_CASE(HD_, CAUSAL_)                                                     \
+  if (head_dim == HD_ && bool(causal) == CAUSAL_) {                                    \
+    if (split == 2) return launch_attn_tc<HD_, CAUSAL_, 2, 2>(LR_ATTN_ARGS);           \
+    if (split == 3) return launch_attn_tc<HD_, CAUSAL_, 1, 1>(LR_ATTN_ARGS);           \
+    return launch_attn_tc<HD_, CAUSAL_, 1, 2>(LR_ATTN_ARGS);                           \
   }
   LR_ATTN_CASE(64, false)
   LR_ATTN_CASE(96, true)
 #undef LR_ATTN_CASE
+  if (head_dim == 96 && !causal) {  // Qwen2.5-VL vision tower (head_dim 80 zero-padded to 96): one tile per CTA only
+    if (split == 2 || split == 1) return LR_ERR_BAD_ARG;
+    return launch_attn_tc<96, false, 1, 1>(LR_ATTN_ARGS);
+  }
   if (head_dim == 128 && causal) {  // one CTA per SM either way (smem / TMEM, see AttnTcCfg); no split-softmax form
     if (split == 2) return LR_ERR_BAD_ARG;
     if (split == 1)  // two query tiles per CTA, row sums in registers
-      return launch_attn_tc<128, true, 1, 2>(q, total_rows, ld_qkv, 0, int(kd), int(vd), o, ld_o, n_seq, rows_per_seq,
-                                             seq_start, seq_len, n_heads, scale, s);
-    return launch_attn_tc<128, true, 1, 1>(q, total_rows, ld_qkv, 0, int(kd), int(vd), o, ld_o, n_seq, rows_per_seq,
-                                           seq_start, seq_len, n_heads, scale, s);
+      return launch_attn_tc<128, true, 1, 2>(LR_ATTN_ARGS);
+    return launch_attn_tc<128, true, 1, 1>(LR_ATTN_ARGS);
   }
-#define LR_ATTN_CASE(a, b)
-#undef LR_ATTN_CASE
+#undef LR_ATTN_ARGS
   return LR_ERR_BAD_ARG;
 }
 

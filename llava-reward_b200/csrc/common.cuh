@@ -97,6 +97,10 @@ __device__ __forceinline__ float epi_swiglu(float gate_acc, float up_acc) {
   return bf16_round(up_acc) * bf16_round(epi_silu(bf16_round(gate_acc)));
 }
 
+__host__ __device__ constexpr bool epi_is_swiglu(int e) { return e == LR_EPI_SWIGLU || e == LR_EPI_BIAS_SWIGLU; }
+__host__ __device__ constexpr bool epi_is_rope(int e) {
+  return e == LR_EPI_ROPE || e == LR_EPI_BIAS_ROPE || e == LR_EPI_BIAS_ROPE_F32;
+}
 __host__ __device__ constexpr bool epi_has_bias(int e) {
   return e == LR_EPI_BIAS || e == LR_EPI_BIAS_QUICKGELU || e == LR_EPI_BIAS_GELU || e == LR_EPI_BIAS_RESIDUAL;
 }

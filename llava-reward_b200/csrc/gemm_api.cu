@@ -11,6 +11,10 @@ int gemm_tcgen05_pair(const void* A, int lda, const void* W, int ldw, void* C, i
 int gemm_rope_pair(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K, const int* pos,
                    const void* cos_tab, const void* sin_tab, int rope_cols, int head_dim, cudaStream_t s);
 
+int gemm_rope_ex_pair(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
+                      const void* lin_bias, const int* pos, const void* cos_tab, const void* sin_tab, int rope_cols,
+                      int head_dim, int epi, cudaStream_t s);
+
 // Verification-only kernel: 32x32 output tile per CTA, fp32 accumulation on CUDA cores, same epilogue math.
 // It exists so tests can tell a tcgen05/TMA descriptor bug from an epilogue/packing bug; the engine never
 // selects it on its own.
@@ -127,19 +131,38 @@ extern "C" int lr_gemm_rope_bf16(const void* A, int lda, const void* W, int ldw,
   return gemm_rope_pair(A, lda, W, ldw, C, ldc, M, N, K, position_ids, cos_tab, sin_tab, rope_cols, head_dim, s);
 }
 
+extern "C" int lr_gemm_rope_ex_bf16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N,
+                                    int K, const void* bias, const int* position_ids, const void* cos_tab,
+                                    const void* sin_tab, int rope_cols, int head_dim, int epilogue, void* stream) {
+  LR_CHECK_ARG(A && W && C && bias && cos_tab && sin_tab && M > 0 && N > 0 && K > 0 && K % 64 == 0);
+  LR_CHECK_ARG(epilogue == LR_EPI_BIAS_ROPE || epilogue == LR_EPI_BIAS_ROPE_F32);
+  LR_CHECK_ARG(N % 256 == 0 && rope_cols % 256 == 0 && rope_cols >= 0 && rope_cols <= N && head_dim > 0 &&
+               head_dim % 32 == 0 && lda >= K && ldw >= K && ldc >= N);
+  auto mis = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; };
+  if (mis(A) || mis(W) || mis(C) || mis(bias) || mis(cos_tab) || mis(sin_tab) || (lda % 8) || (ldw % 8) || (ldc % 8))
+    return LR_ERR_ALIGN;
+  return gemm_rope_ex_pair(A, lda, W, ldw, C, ldc, M, N, K, bias, position_ids, cos_tab, sin_tab, rope_cols, head_dim,
+                           epilogue, reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int lr_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
                             int epilogue, const void* bias, const void* R, int ldr, int impl, void* stream) {
   LR_CHECK_ARG(A && W && C && M > 0 && N > 0 && K > 0 && K % 64 == 0 && N % 128 == 0);
-  LR_CHECK_ARG(epilogue >= LR_EPI_NONE && epilogue <= LR_EPI_SWIGLU);  // LR_EPI_ROPE: lr_gemm_rope_bf16 only
-  if (epi_has_bias(epilogue)) LR_CHECK_ARG(bias != nullptr);
+  // the RoPE epilogues: lr_gemm_rope_bf16 / lr_gemm_rope_ex_bf16 only
+  LR_CHECK_ARG((epilogue >= LR_EPI_NONE && epilogue <= LR_EPI_SWIGLU) || epilogue == LR_EPI_BIAS_SWIGLU);
+  if (epi_has_bias(epilogue) || epilogue == LR_EPI_BIAS_SWIGLU) LR_CHECK_ARG(bias != nullptr);
   if (epi_has_res(epilogue)) LR_CHECK_ARG(R != nullptr && ldr >= N);
-  if (epilogue == LR_EPI_SWIGLU) LR_CHECK_ARG(N % 256 == 0);
-  LR_CHECK_ARG(lda >= K && ldw >= K && ldc >= (epilogue == LR_EPI_SWIGLU ? N / 2 : N));
+  if (epi_is_swiglu(epilogue)) LR_CHECK_ARG(N % 256 == 0);
+  LR_CHECK_ARG(lda >= K && ldw >= K && ldc >= (epi_is_swiglu(epilogue) ? N / 2 : N));
   auto mis = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; };
   if (mis(A) || mis(W) || mis(C) || (bias && mis(bias)) || (R && mis(R)) || (lda % 8) || (ldw % 8) || (ldc % 8) ||
       (R && (ldr % 8)))
     return LR_ERR_ALIGN;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (epilogue == LR_EPI_BIAS_SWIGLU) {  // CTA-pair kernel only (any M)
+    if (impl == LR_GEMM_SIMT || impl == LR_GEMM_TCGEN05_SINGLE) return LR_ERR_BAD_ARG;
+    return gemm_tcgen05_pair(A, lda, W, ldw, C, ldc, M, N, K, epilogue, bias, R, ldr, s);
+  }
   if (impl == LR_GEMM_SIMT) return gemm_simt(A, lda, W, ldw, C, ldc, M, N, K, epilogue, bias, R, ldr, s);
   if (impl == LR_GEMM_TCGEN05_PAIR || (impl == LR_GEMM_TCGEN05 && N % 256 == 0 && M > 256)) {
     if (N % 256) return LR_ERR_BAD_ARG;

@@ -105,8 +105,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const __grid_constant__ CUtensorMap tma_c, int M, int N, int K,
                     const bf16* __restrict__ bias, const bf16* __restrict__ R, int ldr, int group_m,
-                    const int* __restrict__ pos, int rope_hd) {
-  // LR_EPI_ROPE reuses the generic slots: bias = cos table, R = sin table, ldr = number of rotated columns
+                    const int* __restrict__ pos, int rope_hd, const bf16* __restrict__ lin_bias) {
+  // the RoPE epilogues reuse the generic slots: bias = cos table, R = sin table (bf16, or fp32 for
+  // LR_EPI_BIAS_ROPE_F32), ldr = number of rotated columns; lin_bias = the nn.Linear bias (LR_EPI_BIAS_ROPE*), pos may
+  // be NULL (table row = output row)
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -217,7 +219,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int ew = warp - 4;
     const int q = warp & 3;      // TMEM lane quarter this warp may access (hardware rule: warp_id % 4)
     const int half = ew >> 2;    // which half of the tile's output columns
-    constexpr int kOutN = (EPI == LR_EPI_SWIGLU) ? BN / 2 : BN;
+    constexpr int kOutN = epi_is_swiglu(EPI) ? BN / 2 : BN;
     constexpr int kChunks = kOutN / 2 / 64;  // 64-column chunks per warp
     static_assert(kChunks >= 1, "tile too narrow for 8 epilogue warps");
     uint8_t* stg = smem_c + ew * kStagingBytes;
@@ -243,31 +245,73 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           uint32_t acc[32];
           float v[32];
           tmem_ld_32x32(taddr + col_t + hh * 32, acc);
-          if constexpr (EPI == LR_EPI_SWIGLU) {
+          if constexpr (epi_is_swiglu(EPI)) {
             uint32_t up[32];
             tmem_ld_32x32(taddr + BN / 2 + col_t + hh * 32, up);
+            float bg[32], bu[32];
+            if constexpr (EPI == LR_EPI_BIAS_SWIGLU) {  // bias packed like the W rows: [gate 128 | up 128] per n-tile
+              const uint4* gp = reinterpret_cast<const uint4*>(bias + n_blk * BN + col_t + hh * 32);
+              const uint4* up_ = reinterpret_cast<const uint4*>(bias + n_blk * BN + BN / 2 + col_t + hh * 32);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                unpack8_bf16(__ldg(gp + j), bg + j * 8);
+                unpack8_bf16(__ldg(up_ + j), bu + j * 8);
+              }
+            }
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = epi_swiglu(__uint_as_float(acc[j]), __uint_as_float(up[j]));
-          } else if constexpr (EPI == LR_EPI_ROPE) {
-            tmem_ld_wait();
+            for (int j = 0; j < 32; ++j) {
+              if constexpr (EPI == LR_EPI_BIAS_SWIGLU)
+                v[j] = epi_swiglu(__uint_as_float(acc[j]) + bg[j], __uint_as_float(up[j]) + bu[j]);
+              else
+                v[j] = epi_swiglu(__uint_as_float(acc[j]), __uint_as_float(up[j]));
+            }
+          } else if constexpr (epi_is_rope(EPI)) {
             const int cg = col_g + hh * 32;
+            float lb[32];
+            if constexpr (EPI != LR_EPI_ROPE) {
+              const uint4* bp = reinterpret_cast<const uint4*>(lin_bias + cg);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) unpack8_bf16(__ldg(bp + j), lb + j * 8);
+            }
+            tmem_ld_wait();
+            if constexpr (EPI != LR_EPI_ROPE) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + lb[j]);
+            }
             if (cg < ldr) {
               const int half = rope_hd >> 1;
-              const int p = row_ok ? pos[row] : 0;
+              const int p = row_ok ? (pos ? pos[row] : row) : 0;
               const int i0 = (cg % rope_hd) >> 1;  // 16 consecutive rotation pairs start here (cg % 32 == 0)
               float cs[16], sn[16];
-              const uint4* cp = reinterpret_cast<const uint4*>(bias + size_t(p) * half + i0);
-              const uint4* sp = reinterpret_cast<const uint4*>(R + size_t(p) * half + i0);
-              unpack8_bf16(__ldg(cp), cs);
-              unpack8_bf16(__ldg(cp + 1), cs + 8);
-              unpack8_bf16(__ldg(sp), sn);
-              unpack8_bf16(__ldg(sp + 1), sn + 8);
+              if constexpr (EPI == LR_EPI_BIAS_ROPE_F32) {
+                const float4* cp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(bias) + size_t(p) * half + i0);
+                const float4* sp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(R) + size_t(p) * half + i0);
 #pragma unroll
-              for (int k = 0; k < 16; ++k) {
-                const float x1 = bf16_round(__uint_as_float(acc[2 * k])), x2 = bf16_round(__uint_as_float(acc[2 * k + 1]));
-                v[2 * k] = bf16_round(x1 * cs[k]) + bf16_round(-x2 * sn[k]);
-                v[2 * k + 1] = bf16_round(x2 * cs[k]) + bf16_round(x1 * sn[k]);
+                for (int j = 0; j < 4; ++j) {
+                  const float4 c4 = __ldg(cp + j), s4 = __ldg(sp + j);
+                  cs[4 * j] = c4.x, cs[4 * j + 1] = c4.y, cs[4 * j + 2] = c4.z, cs[4 * j + 3] = c4.w;
+                  sn[4 * j] = s4.x, sn[4 * j + 1] = s4.y, sn[4 * j + 2] = s4.z, sn[4 * j + 3] = s4.w;
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {  // fp32 rotation, one rounding (apply_rotary_pos_emb_vision)
+                  const float x1 = bf16_round(__uint_as_float(acc[2 * k])), x2 = bf16_round(__uint_as_float(acc[2 * k + 1]));
+                  v[2 * k] = __fadd_rn(__fmul_rn(x1, cs[k]), __fmul_rn(-x2, sn[k]));
+                  v[2 * k + 1] = __fadd_rn(__fmul_rn(x2, cs[k]), __fmul_rn(x1, sn[k]));
+                }
+              } else {
+                const uint4* cp = reinterpret_cast<const uint4*>(bias + size_t(p) * half + i0);
+                const uint4* sp = reinterpret_cast<const uint4*>(R + size_t(p) * half + i0);
+                unpack8_bf16(__ldg(cp), cs);
+                unpack8_bf16(__ldg(cp + 1), cs + 8);
+                unpack8_bf16(__ldg(sp), sn);
+                unpack8_bf16(__ldg(sp + 1), sn + 8);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                  const float x1 = bf16_round(__uint_as_float(acc[2 * k])), x2 = bf16_round(__uint_as_float(acc[2 * k + 1]));
+                  v[2 * k] = bf16_round(x1 * cs[k]) + bf16_round(-x2 * sn[k]);
+                  v[2 * k + 1] = bf16_round(x2 * cs[k]) + bf16_round(x1 * sn[k]);
+                }
               }
             } else {
 #pragma unroll
@@ -380,14 +424,14 @@ static int sm_count() {
 template <int BN, int EPI>
 static int launch_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
                        const void* bias, const void* R, int ldr, cudaStream_t stream, const int* pos = nullptr,
-                       int rope_hd = 0) {
+                       int rope_hd = 0, const void* lin_bias = nullptr) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap ta, tb, tc;
   int st = make_tmap(&ta, A, M, K, lda, kBM);
   if (st != LR_OK) return st;
   st = make_tmap(&tb, W, N, K, ldw, BN / 2);
   if (st != LR_OK) return st;
-  st = make_tmap(&tc, C, M, EPI == LR_EPI_SWIGLU ? N / 2 : N, ldc, 32);
+  st = make_tmap(&tc, C, M, epi_is_swiglu(EPI) ? N / 2 : N, ldc, 32);
   if (st != LR_OK) return st;
   auto kern = gemm_pair_kernel<BN, EPI>;
   {  // per-device attribute; setting it on every launch keeps multi-device processes correct
@@ -402,7 +446,8 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, void* C, 
   int group_m = int((32ll << 20) / (int64_t(2 * kBM) * K * 2));
   group_m = group_m < 4 ? 4 : (group_m > 32 ? 32 : group_m);
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, M, N, K, reinterpret_cast<const bf16*>(bias),
-                                                        reinterpret_cast<const bf16*>(R), ldr, group_m, pos, rope_hd);
+                                                        reinterpret_cast<const bf16*>(R), ldr, group_m, pos, rope_hd,
+                                                        reinterpret_cast<const bf16*>(lin_bias));
   return lr_launch_status();
 }
 
@@ -429,10 +474,24 @@ int gemm_rope_pair(const void* A, int lda, const void* W, int ldw, void* C, int 
   return pair::launch_gemm<256, LR_EPI_ROPE>(A, lda, W, ldw, C, ldc, M, N, K, cos_tab, sin_tab, rope_cols, s, pos, head_dim);
 }
 
+int gemm_rope_ex_pair(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
+                      const void* lin_bias, const int* pos, const void* cos_tab, const void* sin_tab, int rope_cols,
+                      int head_dim, int epi, cudaStream_t s) {
+  if (epi == LR_EPI_BIAS_ROPE)
+    return pair::launch_gemm<256, LR_EPI_BIAS_ROPE>(A, lda, W, ldw, C, ldc, M, N, K, cos_tab, sin_tab, rope_cols, s, pos,
+                                                    head_dim, lin_bias);
+  if (epi == LR_EPI_BIAS_ROPE_F32)
+    return pair::launch_gemm<256, LR_EPI_BIAS_ROPE_F32>(A, lda, W, ldw, C, ldc, M, N, K, cos_tab, sin_tab, rope_cols, s,
+                                                        pos, head_dim, lin_bias);
+  return LR_ERR_BAD_ARG;
+}
+
 int gemm_tcgen05_pair(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K, int epi,
                       const void* bias, const void* R, int ldr, cudaStream_t s) {
   if (N % 256) return LR_ERR_BAD_ARG;
   if (epi == LR_EPI_SWIGLU) return pair::launch_gemm<256, LR_EPI_SWIGLU>(A, lda, W, ldw, C, ldc, M, N, K, bias, R, ldr, s);
+  if (epi == LR_EPI_BIAS_SWIGLU)
+    return pair::launch_gemm<256, LR_EPI_BIAS_SWIGLU>(A, lda, W, ldw, C, ldc, M, N, K, bias, R, ldr, s);
   return pair::dispatch_epi<256>(epi, A, lda, W, ldw, C, ldc, M, N, K, bias, R, ldr, s);
 }
 

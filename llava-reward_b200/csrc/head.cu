@@ -9,7 +9,8 @@ namespace lr {
 // (rows the reference zero-pads: K row = 0 -> score 0). grid (ceil(max_nv/8), B), one warp per K row.
 __global__ void __launch_bounds__(256)
 skipca_scores_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ kv, int ldkv,
-                     const int* __restrict__ plan, float* __restrict__ scores, int H, int max_nv, float inv_sqrt_d) {
+                     const int* __restrict__ plan, float* __restrict__ scores, int H, int max_nv, float inv_sqrt_d,
+                     float pad_score) {
   extern __shared__ __align__(16) uint8_t sc_smem[];
   bf16* sq = reinterpret_cast<bf16*>(sc_smem);
   const int b = blockIdx.y;
@@ -31,11 +32,11 @@ skipca_scores_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict
     }
     acc = warp_sum(acc);
   }
-  if (lane == 0) scores[size_t(b) * max_nv + j] = (j < nv) ? bf16_round(bf16_round(acc) * inv_sqrt_d) : 0.f;
+  if (lane == 0) scores[size_t(b) * max_nv + j] = (j < nv) ? bf16_round(bf16_round(acc) * inv_sqrt_d) : pad_score;
 }
 
 // One CTA (768 threads) per sample: softmax over max_nv scores, out = P V, y = x + out, RMSNorm, value head.
-constexpr int kHeadThreads = 768;
+constexpr int kHeadThreads = 1024;  // two groups of H/8 threads split the P.V rows: H <= 4096 with SkipCA
 constexpr int kHeadMaxNv = 4096;
 
 __global__ void __launch_bounds__(kHeadThreads)
@@ -157,21 +158,26 @@ __global__ void preference_kernel(const bf16* __restrict__ c, const bf16* __rest
 using namespace lr;
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-extern "C" int lr_skipca_scores(const void* q, int ldq, const void* kv, int ldkv, const int* plan, float* scores,
-                                int B, int H, int max_nv, void* stream) {
+extern "C" int lr_skipca_scores_ex(const void* q, int ldq, const void* kv, int ldkv, const int* plan, float* scores,
+                                   int B, int H, int max_nv, float pad_score, void* stream) {
   LR_CHECK_ARG(q && kv && plan && scores && B > 0 && H > 0 && H % 256 == 0 && max_nv > 0);
   if ((ldq % 8) || (ldkv % 8) || !aligned16(q) || !aligned16(kv)) return LR_ERR_ALIGN;
   skipca_scores_kernel<<<dim3((max_nv + 7) / 8, B), 256, H * 2, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(q), ldq, reinterpret_cast<const bf16*>(kv), ldkv, plan, scores, H, max_nv,
-      1.0f / sqrtf(float(H)));
+      1.0f / sqrtf(float(H)), pad_score);
   return lr_launch_status();
+}
+
+extern "C" int lr_skipca_scores(const void* q, int ldq, const void* kv, int ldkv, const int* plan, float* scores,
+                                int B, int H, int max_nv, void* stream) {
+  return lr_skipca_scores_ex(q, ldq, kv, ldkv, plan, scores, B, H, max_nv, 0.f, stream);
 }
 
 extern "C" int lr_skipca_head(const float* scores, const void* kv, int ldkv, const int* plan, const void* x, int ldx,
                               const void* ca_ln_w, const void* value_head_w, void* reward, int B, int H, int max_nv,
                               int vhd, float eps, void* stream) {
-  // with cross-attention two thread groups split the P.V rows (H <= 3072); the value-head-only form needs one
-  // thread per 8 columns (H <= 6144: the 4096 / 5120 wide Vicuna decoders of the LLaVA-v1.6 branch)
+  // with cross-attention two thread groups split the P.V rows (H <= 4096); the value-head-only form needs one
+  // thread per 8 columns (H <= 8192: the 4096 / 5120 wide Vicuna decoders of the LLaVA-v1.6 branch)
   LR_CHECK_ARG(x && value_head_w && reward && B > 0 && H > 0 && H % 8 == 0 && vhd > 0 &&
                (H / 8) * (scores ? 2 : 1) <= kHeadThreads);
   if (scores) LR_CHECK_ARG(kv && plan && ca_ln_w && max_nv > 0 && max_nv <= kHeadMaxNv);

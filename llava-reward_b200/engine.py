@@ -15,7 +15,7 @@ import torch
 
 from . import _lib as L
 from . import ops
-from .config import RewardConfig, num_image_tokens
+from .config import RewardConfig, num_image_tokens, qwen_window_plan
 from .weights import PackedWeights
 
 
@@ -107,20 +107,31 @@ class RewardEngine:
         lw0 = w.layers[0] if w.layers else {}
         rq, ro, rg, rd = (lw0[k].shape[0] if k in lw0 else 0 for k in ("qkv_a", "o_a", "gu_a", "dn_a"))
         xn = self.buf("dec_xn", (M, H + max(rq, rg)))
-        dqkv = self.buf("dec_qkv", (M, 3 * H))
+        nh, hd = cfg.num_heads, cfg.head_dim
+        nkv = getattr(cfg, "num_kv_heads", nh)      # grouped-query attention (Qwen2 decoder): k/v are nkv*hd wide
+        kvw = nkv * hd
+        QW = H + 2 * kvw
+        dqkv = self.buf("dec_qkv", (M, QW))
         dao = self.buf("dec_ao", (M, H + ro))
         gg = self.buf("dec_g", (M, I + rd))
         att_scale = 1.0 / math.sqrt(cfg.head_dim)
-        nh, hd = cfg.num_heads, cfg.head_dim
         for li, lw in enumerate(w.layers):
             ops.rmsnorm(hid, lw["in_ln"], xn, M, H, cfg.rms_eps)
             if rq:
                 self._gemm(xn, lw["qkv_a"], xn[:, H:], M, rq, H)
             # qkv projection with RoPE in the epilogue (q/k rows are head-interleaved, see weights.py)
-            ops.gemm_rope(xn, lw["qkv_w"], dqkv, M, 3 * H, H + rq, pos, cos_tab, sin_tab, 2 * H, hd,
-                          L.GEMM_SIMT if self.gemm_impl == L.GEMM_SIMT else L.GEMM_TCGEN05)
-            ops.attention(dqkv, dqkv[:, H:], dqkv[:, 2 * H:], dao, 3 * H, H + ro, B, S, seq_start, seq_len, nh, hd,
-                          True, att_scale, self.attn_impl)
+            if "qkv_b" in lw:   # q/k/v biases (Qwen2): bias + RoPE epilogue, per-token tables when pos is None
+                ops.gemm_rope_ex(xn, lw["qkv_w"], dqkv, M, QW, H + rq, lw["qkv_b"], pos, cos_tab, sin_tab, H + kvw, hd,
+                                 L.EPI_BIAS_ROPE)
+            else:
+                ops.gemm_rope(xn, lw["qkv_w"], dqkv, M, QW, H + rq, pos, cos_tab, sin_tab, H + kvw, hd,
+                              L.GEMM_SIMT if self.gemm_impl == L.GEMM_SIMT else L.GEMM_TCGEN05)
+            if nkv != nh:
+                ops.attention_ex(dqkv, dqkv[:, H:], dqkv[:, H + kvw:], dao, QW, H + ro, M, B, S, None, seq_start,
+                                 seq_len, nh, nkv, hd, True, att_scale, self.attn_impl)
+            else:
+                ops.attention(dqkv, dqkv[:, H:], dqkv[:, 2 * H:], dao, 3 * H, H + ro, B, S, seq_start, seq_len, nh, hd,
+                              True, att_scale, self.attn_impl)
             if ro:
                 self._gemm(dao, lw["o_a"], dao[:, H:], M, ro, H)
             self._gemm(dao, lw["o_w"], hid, M, H, H + ro, L.EPI_RESIDUAL, None, hid)
@@ -345,5 +356,233 @@ class LlavaNextRewardEngine(RewardEngine):
         self._tap("last_hidden_eos", xe)
         reward = torch.empty(B, cfg.vhd, dtype=torch.bfloat16, device=dev)
         ops.skipca_head(None, None, None, xe, None, w.head["vh"], reward, B, H, 0, cfg.vhd, cfg.rms_eps)
+        self.launches = L.launch_count() - launches0
+        return reward
+
+
+class QwenVLRewardEngine(RewardEngine):
+    """The reference's qwen branch (rw_model_general_preference.py:354-371 forward, :387-397 SkipCA, :407-448 head) as
+    C-ABI launches: [patch rows -> bf16, window order] -> patch-embed GEMM -> 32 vision blocks (RMSNorm, qkv GEMM with
+    bias + fp32 2D rotary in the epilogue, packed varlen tcgen05 attention over windows / whole images, proj GEMM,
+    RMSNorm, gate|up GEMM with bias + SwiGLU epilogue, down GEMM) -> merger (RMSNorm that also undoes the window
+    permutation, 2 GEMMs) -> embedding gather + image scatter -> Qwen2 decoder (GQA, q/k/v bias + M-RoPE in the qkv
+    epilogue, LoRA K-extension) -> final RMSNorm on the last valid row -> optional SkipCA over the token-id-151643
+    rows of hidden_states[0] -> value head. Not executed (output-identical): the reference's extra `self.visual(...)`
+    pass (:356) and the 152064-wide lm_head."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self._vplans: Dict[tuple, dict] = {}
+
+    def rope_tables(self, n_pos: int, long: bool = False):
+        """cos/sin [n_pos, head_dim/2] bf16 by position (Qwen2_5_VLRotaryEmbedding.forward, default rope,
+        transformers modeling_qwen2_5_vl.py:595-608): fp32 angles -> cos/sin -> bf16."""
+        key = (n_pos, False)
+        if key not in self._rope:
+            cfg = self.cfg
+            expo = torch.arange(0, cfg.head_dim, 2, dtype=torch.int64, device=self.device).float() / cfg.head_dim
+            inv_freq = 1.0 / (cfg.rope_theta ** expo)
+            ang = torch.arange(n_pos, dtype=torch.int64, device=self.device).float()[:, None] * inv_freq[None, :]
+            self._rope = {key: (ang.cos().to(torch.bfloat16).contiguous(), ang.sin().to(torch.bfloat16).contiguous())}
+        return self._rope[key]
+
+    def vision_plan(self, grids) -> dict:
+        """Device copies of the host index plan for a tuple of (t, h, w) grids (cached: eval batches repeat shapes)."""
+        key = tuple(grids)
+        vp = self._vplans.get(key)
+        if vp is None:
+            cfg, dev = self.cfg, self.device
+            from .weights import qwen_vit_padded_head_dim
+            hp = qwen_window_plan(grids, cfg.vit_merge, cfg.vit_window, cfg.vit_patch)
+            unit = cfg.vit_merge ** 2
+            T = int(hp["src_row"].shape[0])
+            # rotary rows per window-ordered token: [h-frequencies | w-frequencies] (rot_pos_emb, :382-409), fp32,
+            # padded with cos = 1 / sin = 0 up to the padded head_dim / 2
+            hd = cfg.vit_head_dim
+            hdp = qwen_vit_padded_head_dim(hd)
+            dim = hd // 2
+            inv_freq = 1.0 / (10000.0 ** (torch.arange(0, dim, 2, dtype=torch.float) / dim))
+            pos = torch.from_numpy(hp["pos_hw"].astype(np.int64))
+            freqs = torch.outer(torch.arange(int(pos.max()) + 1, dtype=torch.float), inv_freq)
+            rot = freqs[pos].flatten(1)                                            # [T, hd/2]
+            cos = torch.ones(T, hdp // 2, dtype=torch.float32)
+            sin = torch.zeros(T, hdp // 2, dtype=torch.float32)
+            cos[:, : hd // 2], sin[:, : hd // 2] = rot.cos(), rot.sin()
+            # merger rows in the ORIGINAL order: merged unit g sits at window slot inv[g] (reverse_indices, :515-517)
+            inv = np.argsort(hp["window_index"], kind="stable")
+            unwin = (inv[:, None] * unit + np.arange(unit)[None, :]).reshape(-1).astype(np.int32)
+            win_cu, img_cu = hp["win_cu"], hp["img_cu"]
+
+            def d(a):
+                return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+            vp = dict(T=T, src_row=d(hp["src_row"]), cos=cos.to(dev), sin=sin.to(dev), unwin=d(unwin),
+                      win_base=d(win_cu[:-1]), win_len=d(np.diff(win_cu).astype(np.int32)), n_win=len(win_cu) - 1,
+                      win_max=int(np.diff(win_cu).max()),
+                      img_base=d(img_cu[:-1]), img_len=d(np.diff(img_cu).astype(np.int32)), n_img=len(img_cu) - 1,
+                      img_max=int(np.diff(img_cu).max()))
+            if len(self._vplans) > 64:
+                self._vplans.clear()
+            self._vplans[key] = vp
+        return vp
+
+    def _vision_tower(self, pix: torch.Tensor, vp: dict) -> torch.Tensor:
+        """-> merged image embeddings [T/4, H] in the original patch order."""
+        from .weights import qwen_vit_padded_head_dim
+        cfg, w = self.cfg, self.w
+        T, D = vp["T"], cfg.vit_hidden
+        nh, hd = cfg.vit_heads, cfg.vit_head_dim
+        hdp = qwen_vit_padded_head_dim(hd)
+        QW, AW = 3 * nh * hdp, nh * hdp
+        K0, K0p = cfg.patch_dim, w.vit["patch_w"].shape[1]
+        Ip = w.vit_layers[0]["dn_w"].shape[1] if w.vit_layers else 128
+        a0 = self.buf("vit_a0", (T, K0p))
+        ops.patch_rows(pix, vp["src_row"], a0, T, K0, K0p)
+        x = self.buf("vit_x", (T, D))
+        self._gemm(a0, w.vit["patch_w"], x, T, D, K0p)
+        self._tap("vit_embed", x)
+        hn = self.buf("vit_hn", (T, D))
+        qkv = self.buf("vit_qkv", (T, QW))
+        ao = self.buf("vit_ao", (T, AW))
+        ff = self.buf("vit_ff", (T, Ip))
+        scale = hd ** -0.5
+        for li, lw in enumerate(w.vit_layers):
+            ops.rmsnorm(x, lw["n1"], hn, T, D, cfg.vit_eps)
+            ops.gemm_rope_ex(hn, lw["qkv_w"], qkv, T, QW, D, lw["qkv_b"], None, vp["cos"], vp["sin"], 2 * AW, hdp,
+                             L.EPI_BIAS_ROPE_F32)
+            if li in cfg.vit_fullatt:
+                base, ln, n, mx = vp["img_base"], vp["img_len"], vp["n_img"], vp["img_max"]
+            else:
+                base, ln, n, mx = vp["win_base"], vp["win_len"], vp["n_win"], vp["win_max"]
+            ops.attention_ex(qkv, qkv[:, AW:], qkv[:, 2 * AW:], ao, QW, AW, T, n, mx, base, None, ln, nh, nh, hdp, False,
+                             scale, L.ATTN_TCGEN05)
+            self._gemm(ao, lw["proj_w"], x, T, D, AW, L.EPI_BIAS_RESIDUAL, lw["proj_b"], x)
+            ops.rmsnorm(x, lw["n2"], hn, T, D, cfg.vit_eps)
+            self._gemm(hn, lw["gu_w"], ff, T, 2 * Ip, D, L.EPI_BIAS_SWIGLU, lw["gu_b"])
+            self._gemm(ff, lw["dn_w"], x, T, D, Ip, L.EPI_BIAS_RESIDUAL, lw["dn_b"], x)
+            if li == 0:
+                self._tap("vit_layer0", x)
+        self._tap("vit_out", x)
+        unit = cfg.vit_merge ** 2
+        y = self.buf("vit_merge_in", (T, D))
+        ops.rmsnorm(x, w.proj["ln_q"], y, T, D, 1e-6, row_index=vp["unwin"])
+        Tm, D4, H = T // unit, D * unit, cfg.hidden_size
+        y4 = y.view(Tm, D4)
+        m1 = self.buf("vit_m1", (Tm, D4))
+        self._gemm(y4, w.proj["m0_w"], m1, Tm, D4, D4, L.EPI_BIAS_GELU, w.proj["m0_b"])
+        img = self.buf("img_proj", (Tm, H))
+        self._gemm(m1, w.proj["m2_w"], img, Tm, H, D4, L.EPI_BIAS, w.proj["m2_b"])
+        self._tap("image_embeds", img)
+        return img
+
+    @torch.no_grad()
+    def forward(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, pixel_values: torch.Tensor,
+                image_grid_thw) -> torch.Tensor:
+        cfg, w, dev = self.cfg, self.w, self.device
+        launches0 = L.launch_count()
+        B, S = input_ids.shape
+        H, M = cfg.hidden_size, B * S
+        ids = input_ids.to(dev, torch.int64).contiguous()
+        mask = attention_mask.to(dev, torch.int64).contiguous()
+        pix = pixel_values.to(dev, torch.float32).contiguous()
+        if pix.dim() != 2 or pix.shape[1] != cfg.patch_dim:
+            raise ValueError(f"pixel_values of shape {tuple(pix.shape)}, expect [patches, {cfg.patch_dim}]")
+        grid_dev = torch.as_tensor(image_grid_thw).to(dev, torch.int32).reshape(-1, 3).contiguous()
+        n_images = grid_dev.shape[0]
+        ca = cfg.add_cross_attention
+
+        # 1. token plans (image positions; for SkipCA also the token-id-151643 positions) + M-RoPE plan, ONE D2H read
+        pos = self.buf("pos", (M,), torch.int32)
+        img_ord = self.buf("img_ord", (M,), torch.int32)
+        nmeta = 4 * B + 1
+        meta = self.buf("meta", (2 * nmeta + B + 3 * n_images,), torch.int32)
+        seq_start, seq_len, eos_row, n_img, flags = (meta[:B], meta[B:2 * B], meta[2 * B:3 * B], meta[3 * B:4 * B],
+                                                     meta[4 * B:nmeta])
+        meta[4 * B:nmeta].zero_()
+        ops.token_plan_ex(ids, mask, B, S, cfg.image_token_id, L.POS_ARANGE, pos, img_ord, seq_start, seq_len, eos_row,
+                          n_img, flags)
+        m2 = meta[nmeta:2 * nmeta]
+        pad_ord = self.buf("pad_ord", (M,), torch.int32)
+        if ca:
+            m2[4 * B:].zero_()
+            # the reference's mask is `input_ids == 151643` over ALL positions, padded ones included (:358)
+            ops.token_plan_ex(ids, mask, B, S, cfg.pad_token_id, L.POS_ARANGE, pos, pad_ord, m2[:B], m2[B:2 * B],
+                              m2[2 * B:3 * B], m2[3 * B:4 * B], m2[4 * B:])
+        run_count = meta[2 * nmeta:2 * nmeta + B]
+        meta[2 * nmeta + B:].copy_(grid_dev.reshape(-1))
+        n_pos = S + 8
+        cos_pos, sin_pos = self.rope_tables(n_pos)
+        half = cfg.head_dim // 2
+        pos3 = self.buf("pos3", (3, M), torch.int32)
+        cos_tok = self.buf("cos_tok", (M, half))
+        sin_tok = self.buf("sin_tok", (M, half))
+        ops.mrope_plan(ids, mask, B, S, cfg.image_token_id, grid_dev, n_images, cfg.vit_merge, run_count, cos_pos, sin_pos,
+                       n_pos, half, cfg.mrope_section[0], cfg.mrope_section[1], pos3, cos_tok, sin_tok, flags)
+        meta_h = meta.cpu().numpy()
+        if self.taps is not None:
+            self.taps["pos3"] = pos3.clone()
+        if meta_h[4 * B] & 1:
+            raise ValueError("attention_mask rows must be one contiguous run of ones (left/right padding)")
+        grids = [tuple(int(v) for v in meta_h[2 * nmeta + B + 3 * i: 2 * nmeta + B + 3 * i + 3]) for i in range(n_images)]
+        unit = cfg.vit_merge ** 2
+        n_tok = int(meta_h[3 * B:4 * B].sum())
+        n_feat = sum(t * h * w for t, h, w in grids) // unit
+        if (meta_h[4 * B] & 2) or n_tok != n_feat:
+            # get_placeholder_mask (transformers modeling_qwen2_5_vl.py:1204-1208) checks the batch total; a per-image
+            # mismatch would shift features across images and is an error here
+            raise ValueError(f"Image features and image tokens do not match, tokens: {n_tok}, features: {n_feat}")
+        if sum(t * h * w for t, h, w in grids) != pix.shape[0]:
+            raise ValueError(f"pixel_values has {pix.shape[0]} patches but image_grid_thw implies "
+                             f"{sum(t * h * w for t, h, w in grids)}")
+        for t, h, w in grids:
+            if h % cfg.vit_merge or w % cfg.vit_merge:
+                raise ValueError(f"image grid {(t, h, w)} is not a multiple of the merge size {cfg.vit_merge}")
+        plan_h = np.zeros((2 * B, L.PLAN_STRIDE), dtype=np.int32)
+        plan_h[:B, L.PLAN_NV] = meta_h[3 * B:4 * B]
+        plan_h[:B, L.PLAN_ROW_BASE] = np.concatenate([[0], np.cumsum(meta_h[3 * B:4 * B])[:-1]])
+        n_pad = meta_h[nmeta + 3 * B: nmeta + 4 * B] if ca else np.zeros(B, dtype=np.int32)
+        plan_h[B:, L.PLAN_NV] = n_pad
+        plan_h[B:, L.PLAN_ROW_BASE] = np.concatenate([[0], np.cumsum(n_pad)[:-1]])
+        sum_pad, max_pad = int(n_pad.sum()), int(n_pad.max()) if B else 0
+        host = torch.from_numpy(plan_h.reshape(-1))
+        dev_plan = self.buf("plan", (host.numel(),), torch.int32)
+        dev_plan.copy_(host.pin_memory() if dev.type == "cuda" else host, non_blocking=True)
+        plan, pad_plan = dev_plan[: B * L.PLAN_STRIDE], dev_plan[B * L.PLAN_STRIDE:]
+
+        # 2. vision tower + merger, 3. embeddings
+        vp = self.vision_plan(grids)
+        img = self._vision_tower(pix, vp)
+        hid = self.buf("hidden", (M, H))
+        ops.embed_scatter(ids, img_ord, plan, w.embed, img, hid, B, S, H, cfg.vocab_size)
+        self._tap("inputs_embeds", hid)
+        kv_src = None
+        if ca and sum_pad > 0:
+            kv_src = self.buf("ca_src", (sum_pad, H))
+            ops.compact_rows(hid, pad_ord, pad_plan, kv_src, B, S, H)
+
+        # 4. decoder (per-token M-RoPE rows: position_ids = None)
+        self._decoder(hid, B, S, None, seq_start, seq_len, cos_tok, sin_tok)
+
+        # 5. final norm on the last valid row, SkipCA (qwen arm), value head
+        xe = self.buf("x_eos", (max(B, 1), H))
+        ops.rmsnorm(hid, w.head["norm"], xe, B, H, cfg.rms_eps, row_index=eos_row)
+        self._tap("last_hidden_eos", xe)
+        vhd = cfg.vhd
+        reward = torch.empty(B, vhd, dtype=torch.bfloat16, device=dev)
+        if ca and sum_pad > 0:
+            q = self.buf("ca_q", (B, H))
+            self._gemm(xe, w.head["wq"], q, B, H, H)
+            kv = self.buf("ca_kv", (sum_pad, 2 * H))
+            self._gemm(kv_src, w.head["wkv"], kv, sum_pad, 2 * H, H)
+            scores = self.buf("ca_scores", (B, max_pad), torch.float32)
+            ops.skipca_scores_ex(q, kv, pad_plan, scores, B, H, max_pad, -9984.0)   # bf16(-1e4), masked_fill at :391
+            ops.skipca_head(scores, kv, pad_plan, xe, w.head["ca_ln"], w.head["vh"], reward, B, H, max_pad, vhd, 1e-6)
+        elif ca:
+            # no token-id-151643 position in the batch: vision_pad is [B, 0, H], attn_o = 0, ca_layernorm(last + 0)
+            xc = self.buf("x_ca", (max(B, 1), H))
+            ops.rmsnorm(xe, w.head["ca_ln"], xc, B, H, 1e-6)
+            ops.skipca_head(None, None, None, xc, None, w.head["vh"], reward, B, H, 0, vhd, cfg.rms_eps)
+        else:
+            ops.skipca_head(None, None, None, xe, None, w.head["vh"], reward, B, H, 0, vhd, cfg.rms_eps)
         self.launches = L.launch_count() - launches0
         return reward

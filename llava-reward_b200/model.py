@@ -11,9 +11,9 @@ from typing import Callable, Optional
 import torch
 
 from . import _lib as L
-from .config import LlavaNextRewardConfig, RewardConfig
-from .engine import LlavaNextRewardEngine, RewardEngine
-from .weights import pack_weights, pack_weights_llava
+from .config import LlavaNextRewardConfig, QwenVLRewardConfig, RewardConfig
+from .engine import LlavaNextRewardEngine, QwenVLRewardEngine, RewardEngine
+from .weights import pack_weights, pack_weights_llava, pack_weights_qwen
 
 
 class B200RewardModel:
@@ -128,6 +128,45 @@ class B200LlavaNextRewardModel(B200RewardModel):
         with torch.cuda.device(self.device):
             reward = self.engine.forward(inputs_batch["input_ids"], inputs_batch["attention_mask"],
                                          inputs_batch["pixel_values"], inputs_batch["image_sizes"])
+        return reward, None
+
+    __call__ = custom_forward
+
+
+class B200QwenRewardModel(B200RewardModel):
+    """model_type 'qwen' (Qwen2.5-VL): the caller passes the processor's BatchFeature as `inputs_batch`
+    (reference eval/batch_inference_rm_qwen.py:91-92, rw_model_general_preference.py:354-371, 387-397)."""
+    model_type = "qwen"
+
+    def __init__(self, cfg: QwenVLRewardConfig, provider: Callable[[str], torch.Tensor]):
+        super().__init__(cfg, provider)
+        self.layer_id = cfg.num_layers
+
+    def _build_engine(self, device):
+        return QwenVLRewardEngine(self.config, pack_weights_qwen(self.config, self._provider, device=device),
+                                  device=device)
+
+    def custom_forward(self, input_ids=None, attention_mask=None, pixel_values=None, image_sizes=None,
+                       return_output=False, inputs_batch=None):
+        if self.engine is None:
+            raise RuntimeError("call .to('cuda') before custom_forward (weights are packed on the device)")
+        if inputs_batch is None:
+            # the reference reads inputs_batch['attention_mask'] unconditionally in this branch (:355)
+            raise TypeError("model_type 'qwen' is called as custom_forward(inputs_batch=processor_output)")
+        if return_output:
+            raise NotImplementedError("return_output=True (HF Qwen2_5_VLCausalLMOutputWithPast) is not produced by the fused path")
+        if self.mean_hidden_state:
+            raise NotImplementedError("mean_hidden_state pooling is off in all shipped reference configs")
+        if self.training:
+            raise NotImplementedError("training-mode gather (values[:, -1]) is not part of the scoring path")
+        for k in ("input_ids", "attention_mask", "pixel_values", "image_grid_thw"):
+            if k not in inputs_batch:
+                raise KeyError(k)
+        if inputs_batch.get("pixel_values_videos") is not None:
+            raise NotImplementedError("video inputs: the reference's reward datasets are image-only")
+        with torch.cuda.device(self.device):
+            reward = self.engine.forward(inputs_batch["input_ids"], inputs_batch["attention_mask"],
+                                         inputs_batch["pixel_values"], inputs_batch["image_grid_thw"])
         return reward, None
 
     __call__ = custom_forward

@@ -117,3 +117,44 @@ def skipca_head(scores, kv, plan, x, ca_ln_w, vh_w, reward, B, H, max_nv, vhd, e
 def preference(chosen, reject, prob, n, vhd, is_gpm, tau):
     _need_cuda(chosen, reject, prob)
     L.call("lr_preference", _ptr(chosen), _ptr(reject), _ptr(prob), n, vhd, int(is_gpm), float(tau), _stream())
+
+
+# ---- Qwen2.5-VL branch -------------------------------------------------------------------------------------------
+def gemm_rope_ex(A, W, C, M, N, K, bias, position_ids, cos_tab, sin_tab, rope_cols, head_dim, epilogue):
+    """C = A W^T + bias with the rotary embedding fused on columns [0, rope_cols); position_ids None = per-token tables."""
+    _need_cuda(A, W, C, bias, position_ids, cos_tab, sin_tab)
+    L.call("lr_gemm_rope_ex_bf16", _ptr(A), A.stride(0), _ptr(W), W.stride(0), _ptr(C), C.stride(0), M, N, K, _ptr(bias),
+           _ptr(position_ids), _ptr(cos_tab), _ptr(sin_tab), rope_cols, head_dim, epilogue, _stream())
+
+
+def attention_ex(q, k, v, o, ld_qkv, ld_o, total_rows, n_seq, max_len, seq_base, seq_start, seq_len, n_heads,
+                 n_kv_heads, head_dim, causal, scale, impl: int = L.ATTN_TCGEN05):
+    _need_cuda(q, k, v, o, seq_base, seq_start, seq_len)
+    L.call("lr_attention_ex_bf16", _ptr(q), _ptr(k), _ptr(v), _ptr(o), ld_qkv, ld_o, total_rows, n_seq, max_len,
+           _ptr(seq_base), _ptr(seq_start), _ptr(seq_len), n_heads, n_kv_heads, head_dim, int(causal), scale, impl,
+           _stream())
+
+
+def skipca_scores_ex(q, kv, plan, scores, B, H, max_nv, pad_score):
+    _need_cuda(q, kv, plan, scores)
+    L.call("lr_skipca_scores_ex", _ptr(q), q.stride(0), _ptr(kv), kv.stride(0), _ptr(plan), _ptr(scores), B, H, max_nv,
+           float(pad_score), _stream())
+
+
+def patch_rows(pixels, src_row, out, rows, K, Kpad):
+    _need_cuda(pixels, src_row, out)
+    L.call("lr_patch_rows_bf16", _ptr(pixels), _ptr(src_row), _ptr(out), out.stride(0), rows, K, Kpad, _stream())
+
+
+def mrope_plan(ids, mask, B, S, image_token_id, grid_thw, n_images, merge, run_count, cos_tab, sin_tab, max_pos, half,
+               sec0, sec1, pos3, cos_out, sin_out, flags):
+    _need_cuda(ids, mask, grid_thw, run_count, cos_tab, sin_tab, pos3, cos_out, sin_out, flags)
+    L.call("lr_mrope_plan", _ptr(ids), _ptr(mask), B, S, int(image_token_id), _ptr(grid_thw), n_images, merge,
+           _ptr(run_count), _ptr(cos_tab), _ptr(sin_tab), max_pos, half, sec0, sec1, _ptr(pos3), _ptr(cos_out),
+           _ptr(sin_out), _ptr(flags), _stream())
+
+
+def compact_rows(src, ord_, plan, dst, B, S, cols):
+    _need_cuda(src, ord_, plan, dst)
+    L.call("lr_compact_rows_bf16", _ptr(src), src.stride(0), _ptr(ord_), _ptr(plan), _ptr(dst), dst.stride(0), B, S,
+           cols, _stream())

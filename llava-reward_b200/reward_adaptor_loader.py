@@ -11,9 +11,9 @@ import numpy as np
 import torch
 import yaml
 
-from .checkpoint import checkpoint_provider, llava_checkpoint_provider
-from .config import LlavaNextRewardConfig, RewardConfig
-from .model import B200LlavaNextRewardModel, B200RewardModel
+from .checkpoint import checkpoint_provider, llava_checkpoint_provider, qwen_checkpoint_provider
+from .config import LlavaNextRewardConfig, QwenVLRewardConfig, RewardConfig
+from .model import B200LlavaNextRewardModel, B200QwenRewardModel, B200RewardModel
 from .synth import SynthProvider
 
 
@@ -31,12 +31,34 @@ def load_reward_adaptor(args, model_type, reward_config_path, load_tokenizer=Fal
     args.add_cross_attention = reward_cfg['add_cross_attention']
     args.value_head_dim = reward_cfg['value_head_dim']
     args.general_preference_tau = reward_cfg['general_preference_tau']
-    if model_type not in ('phi3v', 'llava'):
-        raise NotImplementedError(f"model_type={model_type!r}: this build covers the phi3v and llava (v1.6 Vicuna) "
-                                  "backbones (qwen is the next row of SURVEY.md 8f)")
+    if model_type not in ('phi3v', 'llava', 'qwen'):
+        raise NotImplementedError(f"model_type={model_type!r}: the reference knows 'phi3v', 'qwen' and 'llava'")
     overrides = dict(getattr(args, "config_overrides", None) or {})
     pretrain = str(args.pretrain)
     synthetic = pretrain.startswith("synthetic")
+    if model_type == 'qwen':
+        # reference :64-109 (Qwen2.5-VL-7B-Instruct + LoRA on the seven decoder linears, optional SkipCA and merger)
+        qcfg = QwenVLRewardConfig(is_general_preference=bool(args.is_general_preference),
+                                  add_cross_attention=bool(args.add_cross_attention),
+                                  value_head_dim=int(args.value_head_dim),
+                                  general_preference_tau=float(args.general_preference_tau), **overrides)
+        if synthetic:
+            parts = [x for x in pretrain.split(":")[1:] if x.isdigit()]
+            qprov: Callable[[str], torch.Tensor] = SynthProvider(qcfg, seed=int(parts[0]) if parts else 1234)
+        else:
+            qcfg, qprov = qwen_checkpoint_provider(qcfg, pretrain, getattr(args, "pm_path", None),
+                                                   ft_projector=bool(getattr(args, "ft_projector", False)))
+        qmodel = B200QwenRewardModel(qcfg, qprov)
+        if load_tokenizer:
+            # get_tokenizer_qwen (llava_reward/utils/utils.py) = AutoProcessor + its tokenizer, left padding
+            from transformers import AutoProcessor
+            processor = AutoProcessor.from_pretrained(pretrain, cache_dir=getattr(args, "cache_dir", None),
+                                                      min_pixels=256 * 28 * 28, max_pixels=1280 * 28 * 28)
+            tokenizer = processor.tokenizer
+            tokenizer.padding_side = "left"
+            tokenizer.truncation_side = "right"
+            return args, qmodel, processor, tokenizer
+        return args, qmodel
     if model_type == 'llava':
         # reference :110-151. add_cross_attention is read from the yaml but the llava branch of custom_forward never
         # applies SkipCA (rw_model_general_preference.py:376-397), so it does not change the forward.

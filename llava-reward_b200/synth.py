@@ -17,7 +17,7 @@ from typing import Callable, Dict, Iterator, List, Optional, Tuple
 
 import torch
 
-from .config import LlavaNextRewardConfig, RewardConfig, anyres_geometry, num_image_tokens
+from .config import LlavaNextRewardConfig, QwenVLRewardConfig, RewardConfig, anyres_geometry, num_image_tokens
 
 _M32 = 0xFFFFFFFF
 _IH_STD = 65536.0 / (3.0 ** 0.5)  # std of the sum of four U{0..65535} (Irwin-Hall, n=4)
@@ -177,13 +177,64 @@ def llava_param_specs(cfg: LlavaNextRewardConfig) -> Iterator[Tuple[str, Tuple[i
     yield "value_head.weight", (cfg.vhd, H), "w"
 
 
+def qwen_param_specs(cfg: QwenVLRewardConfig) -> Iterator[Tuple[str, Tuple[int, ...], str]]:
+    """Parameters of the Qwen2.5-VL reward model under the state_dict names of the transformers release the reference
+    pins (4.50: `visual.*`, `model.*` = the text decoder - the names create_lora_config_qwen targets,
+    llava_reward/utils/utils.py:223-231) + the reward heads (rw_model_general_preference.py:314-326)."""
+    H, I, V = cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size
+    D, DI = cfg.vit_hidden, cfg.vit_intermediate
+    kv = cfg.num_kv_heads * cfg.head_dim
+    yield "model.embed_tokens.weight", (V, H), "w"
+    yield "visual.patch_embed.proj.weight", (D, 3, cfg.vit_temporal_patch, cfg.vit_patch, cfg.vit_patch), "w"
+    for i in range(cfg.vit_depth):
+        p = f"visual.blocks.{i}."
+        yield p + "norm1.weight", (D,), "n"
+        yield p + "norm2.weight", (D,), "n"
+        yield p + "attn.qkv.weight", (3 * D, D), "w"
+        yield p + "attn.qkv.bias", (3 * D,), "w"
+        yield p + "attn.proj.weight", (D, D), "w"
+        yield p + "attn.proj.bias", (D,), "w"
+        for nm, o, k in (("gate_proj", DI, D), ("up_proj", DI, D), ("down_proj", D, DI)):
+            yield p + f"mlp.{nm}.weight", (o, k), "w"
+            yield p + f"mlp.{nm}.bias", (o,), "w"
+    M4 = D * cfg.vit_merge ** 2
+    yield "visual.merger.ln_q.weight", (D,), "n"
+    yield "visual.merger.mlp.0.weight", (M4, M4), "w"
+    yield "visual.merger.mlp.0.bias", (M4,), "w"
+    yield "visual.merger.mlp.2.weight", (H, M4), "w"
+    yield "visual.merger.mlp.2.bias", (H,), "w"
+    r = cfg.lora_rank
+    for i in range(cfg.num_layers):
+        p = f"model.layers.{i}."
+        lin = [("self_attn.q_proj", H, H, True), ("self_attn.k_proj", kv, H, True), ("self_attn.v_proj", kv, H, True),
+               ("self_attn.o_proj", H, H, False), ("mlp.gate_proj", I, H, False), ("mlp.up_proj", I, H, False),
+               ("mlp.down_proj", H, I, False)]
+        for nm, o, k, bias in lin:
+            yield p + nm + ".weight", (o, k), "w"
+            if bias:
+                yield p + nm + ".bias", (o,), "w"
+            if cfg.use_lora:
+                yield p + nm + ".lora_A.weight", (r, k), "w"
+                yield p + nm + ".lora_B.weight", (o, r), "w"
+        yield p + "input_layernorm.weight", (H,), "n"
+        yield p + "post_attention_layernorm.weight", (H,), "n"
+    yield "model.norm.weight", (H,), "n"
+    yield "value_head.weight", (cfg.vhd, H), "w"
+    if cfg.add_cross_attention:
+        yield "W_q.weight", (H, H), "w"
+        yield "W_k.weight", (H, H), "w"
+        yield "W_v.weight", (H, H), "w"
+        yield "ca_layernorm.weight", (H,), "n"
+
+
 class SynthProvider:
     """Callable ``name -> tensor`` producing synthetic parameters on demand."""
 
     def __init__(self, cfg: RewardConfig, seed: int = 1234, std: float = 0.02, device="cpu",
                  dtype=torch.float32):
         self.cfg, self.seed, self.std, self.device, self.dtype = cfg, seed, std, device, dtype
-        gen = llava_param_specs if isinstance(cfg, LlavaNextRewardConfig) else param_specs
+        gen = (llava_param_specs if isinstance(cfg, LlavaNextRewardConfig) else
+               qwen_param_specs if isinstance(cfg, QwenVLRewardConfig) else param_specs)
         self.specs: Dict[str, Tuple[Tuple[int, ...], str]] = {n: (s, k) for n, s, k in gen(cfg)}
 
     def names(self) -> List[str]:
@@ -274,3 +325,37 @@ def synth_batch_llava(cfg: LlavaNextRewardConfig, batch: int, orig_hw_list, seq_
             mask[b, : len(row)] = 1
     return {"input_ids": ids.to(device), "attention_mask": mask.to(device), "pixel_values": pix,
             "image_sizes": sizes.to(device)}
+
+
+def synth_batch_qwen(cfg: QwenVLRewardConfig, grid_hw_list, seq_len: Optional[int], seed: int = 7, device="cpu",
+                     text_len_range: Tuple[int, int] = (40, 128), tag: str = "c", padding_side: str = "left"):
+    """The `inputs_batch` Qwen2_5_VLProcessor(text, images, padding=True) hands to custom_forward
+    (reference reward_dataset.py:466-489): input_ids [B,S] = [pad..., <|im_start|>, user, \n, <|vision_start|>,
+    <|image_pad|> x (h/2 * w/2), <|vision_end|>, text..., <|im_end|>] (the chat template cut at :417), attention_mask,
+    pixel_values [sum h*w, 1176] fp32 (flattened (c, t, ph, pw) patches in 2x2-merge order), image_grid_thw [B,3],
+    mm_token_type_ids (1 at image positions; what the installed processor adds). grid_hw_list: (h, w) in patches."""
+    B = len(grid_hw_list)
+    tl = hash_randint(f"textlen.{tag}", B, text_len_range[0], text_len_range[1], seed).tolist()
+    rows, pix = [], []
+    for b, (h, w) in enumerate(grid_hw_list):
+        assert h % cfg.vit_merge == 0 and w % cfg.vit_merge == 0
+        pix.append(hash_normal(f"pixels.{tag}.{b}", (h * w, cfg.patch_dim), 1.0, seed, device=device))
+        text = hash_randint(f"text.{tag}.{b}", tl[b], 3, 151000, seed).tolist()
+        n_img = (h // cfg.vit_merge) * (w // cfg.vit_merge)
+        rows.append([151644, 872, 198, cfg.vision_start_token_id] + [cfg.image_token_id] * n_img +
+                    [cfg.vision_end_token_id] + text + [151645])
+    S = max(len(r) for r in rows) if seq_len is None else seq_len
+    ids = torch.full((B, S), cfg.pad_token_id, dtype=torch.int64)
+    mask = torch.zeros((B, S), dtype=torch.int64)
+    for b, row in enumerate(rows):
+        if len(row) > S:
+            raise ValueError(f"sample {b} needs {len(row)} tokens > seq_len {S}")
+        if padding_side == "left":
+            ids[b, S - len(row):] = torch.tensor(row, dtype=torch.int64)
+            mask[b, S - len(row):] = 1
+        else:
+            ids[b, : len(row)] = torch.tensor(row, dtype=torch.int64)
+            mask[b, : len(row)] = 1
+    grid = torch.tensor([[1, h, w] for h, w in grid_hw_list], dtype=torch.int64)
+    return {"input_ids": ids.to(device), "attention_mask": mask.to(device), "pixel_values": torch.cat(pix, 0),
+            "image_grid_thw": grid.to(device), "mm_token_type_ids": (ids == cfg.image_token_id).int().to(device)}

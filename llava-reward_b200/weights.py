@@ -19,7 +19,7 @@ from typing import Callable, Dict, List
 
 import torch
 
-from .config import LlavaNextRewardConfig, RewardConfig
+from .config import LlavaNextRewardConfig, QwenVLRewardConfig, RewardConfig
 from .synth import CLIP_PREFIX, LLAVA_CLIP_PREFIX, LLAVA_LM_PREFIX
 
 VE = "model.vision_embed_tokens."
@@ -33,10 +33,12 @@ class PackedWeights:
         self.layers: List[Dict[str, torch.Tensor]] = []
         self.head: Dict[str, torch.Tensor] = {}
         self.embed: torch.Tensor = None
+        self.vit: Dict[str, torch.Tensor] = {}                 # Qwen2.5-VL vision tower
+        self.vit_layers: List[Dict[str, torch.Tensor]] = []
 
     def nbytes(self) -> int:
         tot = 0
-        for d in [self.clip, self.proj, self.head, *self.clip_layers, *self.layers]:
+        for d in [self.clip, self.proj, self.head, self.vit, *self.clip_layers, *self.layers, *self.vit_layers]:
             tot += sum(t.numel() * t.element_size() for t in d.values())
         return tot + self.embed.numel() * self.embed.element_size()
 
@@ -185,4 +187,122 @@ def pack_weights_llava(cfg: LlavaNextRewardConfig, get: Callable[[str], torch.Te
             d.update({"qkv_a": qkv_a, "o_a": o_a, "gu_a": gu_a, "dn_a": dn_a})
         pw.layers.append(d)
     pw.head = {"norm": g(lm + "norm.weight"), "vh": g("value_head.weight")}
+    return pw
+
+
+def qwen_vit_padded_head_dim(head_dim: int) -> int:
+    """head_dim of the vision tower as the attention kernel sees it: 80 is zero-padded to 96 (three 32-column TMA atoms)."""
+    assert head_dim % 2 == 0 and head_dim <= 96
+    return 64 if head_dim <= 64 else 96
+
+
+def pack_weights_qwen(cfg: QwenVLRewardConfig, get: Callable[[str], torch.Tensor], device="cuda") -> PackedWeights:
+    """Qwen2.5-VL (reference-era names, see synth.qwen_param_specs) -> kernel layouts.
+    Vision tower (transformers modeling_qwen2_5_vl.py:207-322):
+      * patch_embed Conv3d weight flattened to [D, 1176 -> 1216] (K padded to a multiple of 64)
+      * attn.qkv [3D, D] (+bias): every head padded from head_dim 80 to 96 rows (zero rows, zero bias), q/k rows inside a
+        head interleaved so that rotation pair (i, i + 40) is two adjacent output columns (lr_gemm_rope_ex_bf16,
+        LR_EPI_BIAS_ROPE_F32); attn.proj [D, D] gets the matching zero COLUMNS
+      * mlp gate/up (+biases) zero-padded from 3420 to 3456 rows each and interleaved in blocks of 128 for the
+        SwiGLU epilogue (LR_EPI_BIAS_SWIGLU); down_proj gets the matching zero columns
+    Decoder (same per-layer dict as the Phi-3 / LLaVA loop): q/k/v stacked into one [H + 2 kv, H + 3r] weight with the
+    three LoRA-B blocks on the block diagonal of the K-extension, q/k rows head-interleaved, `qkv_b` the stacked bias;
+    gate/up stacked [2I, H + 2r] and interleaved in blocks of 128."""
+    bf = torch.bfloat16
+
+    def g(name):
+        return get(name).to(device=device, dtype=bf).contiguous()
+
+    def rows(t: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        """t[idx] with idx == -1 -> zero row"""
+        out = t[idx.clamp(min=0)]
+        out[idx < 0] = 0
+        return out.contiguous()
+
+    pw = PackedWeights()
+    D, DI, nh, hd = cfg.vit_hidden, cfg.vit_intermediate, cfg.vit_heads, cfg.vit_head_dim
+    hdp = qwen_vit_padded_head_dim(hd)
+    K0 = cfg.patch_dim
+    K0p = (K0 + 63) // 64 * 64
+    pe = g("visual.patch_embed.proj.weight").reshape(D, -1)
+    patch_w = torch.zeros(D, K0p, dtype=bf, device=device)
+    patch_w[:, :K0] = pe
+    pw.vit = {"patch_w": patch_w}
+    # row index maps
+    half = hd // 2
+    inter = torch.stack([torch.arange(half), torch.arange(half) + half], 1).reshape(-1)          # 0,40,1,41,..
+    qk_head = torch.cat([inter, torch.full((hdp - hd,), -1, dtype=torch.long)])                  # [hdp]
+    v_head = torch.cat([torch.arange(hd), torch.full((hdp - hd,), -1, dtype=torch.long)])
+    heads = torch.arange(nh)[:, None] * hd
+
+    def head_map(per_head, base):
+        m = heads + per_head[None, :]
+        m = torch.where(per_head[None, :] < 0, torch.full_like(m, -1), m + base)
+        return m.reshape(-1)
+
+    qkv_idx = torch.cat([head_map(qk_head, 0), head_map(qk_head, D), head_map(v_head, 2 * D)]).to(device)
+    proj_cols = head_map(v_head, 0).to(device)                                                    # [nh*hdp]
+    Ip = (DI + 127) // 128 * 128
+    pad_i = torch.cat([torch.arange(DI), torch.full((Ip - DI,), -1, dtype=torch.long)])
+    gu_idx = torch.cat([pad_i, torch.where(pad_i < 0, pad_i, pad_i + DI)])
+    gu_idx = gu_idx.view(2, Ip // 128, 128).permute(1, 0, 2).reshape(-1).to(device)
+    dn_cols = pad_i.to(device)
+    for i in range(cfg.vit_depth):
+        p = f"visual.blocks.{i}."
+        gu_w = torch.cat([g(p + "mlp.gate_proj.weight"), g(p + "mlp.up_proj.weight")], 0)
+        gu_b = torch.cat([g(p + "mlp.gate_proj.bias"), g(p + "mlp.up_proj.bias")], 0)
+        pw.vit_layers.append({
+            "n1": g(p + "norm1.weight"), "n2": g(p + "norm2.weight"),
+            "qkv_w": rows(g(p + "attn.qkv.weight"), qkv_idx), "qkv_b": rows(g(p + "attn.qkv.bias"), qkv_idx),
+            "proj_w": rows(g(p + "attn.proj.weight").t().contiguous(), proj_cols).t().contiguous(),
+            "proj_b": g(p + "attn.proj.bias"),
+            "gu_w": rows(gu_w, gu_idx), "gu_b": rows(gu_b, gu_idx),
+            "dn_w": rows(g(p + "mlp.down_proj.weight").t().contiguous(), dn_cols).t().contiguous(),
+            "dn_b": g(p + "mlp.down_proj.bias"),
+        })
+    pw.proj = {"ln_q": g("visual.merger.ln_q.weight"),
+               "m0_w": g("visual.merger.mlp.0.weight"), "m0_b": g("visual.merger.mlp.0.bias"),
+               "m2_w": g("visual.merger.mlp.2.weight"), "m2_b": g("visual.merger.mlp.2.bias")}
+    pw.embed = g("model.embed_tokens.weight")
+    H, I, r = cfg.hidden_size, cfg.intermediate_size, cfg.lora_rank
+    kvw = cfg.num_kv_heads * cfg.head_dim
+    assert I % 128 == 0 and (H + 2 * kvw) % 256 == 0 and (H + kvw) % 256 == 0
+    gu_perm = torch.arange(2 * I, device=device).view(2, I // 128, 128).permute(1, 0, 2).reshape(-1)
+    qkv_perm = torch.cat([_qk_interleave_perm(cfg.num_heads, cfg.head_dim, device),
+                          H + _qk_interleave_perm(cfg.num_kv_heads, cfg.head_dim, device),
+                          torch.arange(H + kvw, H + 2 * kvw, device=device)])
+
+    def stacked(names):
+        Ws = [g(n + ".weight") for n in names]
+        if not cfg.use_lora:
+            return torch.cat(Ws, 0).contiguous(), None
+        k = len(names)
+        blocks = []
+        for j, n in enumerate(names):
+            B = (get(n + ".lora_B.weight").to(device=device, dtype=torch.float32) * cfg.lora_scale).to(bf)
+            ext = torch.zeros(B.shape[0], k * r, dtype=bf, device=device)
+            ext[:, j * r:(j + 1) * r] = B
+            blocks.append(torch.cat([Ws[j], ext], dim=1))
+        A = torch.cat([g(n + ".lora_A.weight") for n in names], 0).contiguous()
+        return torch.cat(blocks, 0).contiguous(), A
+
+    for i in range(cfg.num_layers):
+        p = f"model.layers.{i}."
+        names = [p + f"self_attn.{n}_proj" for n in "qkv"]
+        qkv_w, qkv_a = stacked(names)
+        qkv_b = torch.cat([g(n + ".bias") for n in names], 0)
+        o_w, o_a = stacked([p + "self_attn.o_proj"])
+        gu_w, gu_a = stacked([p + "mlp.gate_proj", p + "mlp.up_proj"])
+        dn_w, dn_a = stacked([p + "mlp.down_proj"])
+        d = {"in_ln": g(p + "input_layernorm.weight"), "post_ln": g(p + "post_attention_layernorm.weight"),
+             "qkv_w": qkv_w[qkv_perm].contiguous(), "qkv_b": qkv_b[qkv_perm].contiguous(), "o_w": o_w,
+             "gu_w": gu_w[gu_perm].contiguous(), "dn_w": dn_w}
+        if cfg.use_lora:
+            d.update({"qkv_a": qkv_a, "o_a": o_a, "gu_a": gu_a, "dn_a": dn_a})
+        pw.layers.append(d)
+    pw.head = {"norm": g("model.norm.weight"), "vh": g("value_head.weight")}
+    if cfg.add_cross_attention:
+        pw.head.update({"wq": g("W_q.weight"),
+                        "wkv": torch.cat([g("W_k.weight"), g("W_v.weight")], 0).contiguous(),
+                        "ca_ln": g("ca_layernorm.weight")})
     return pw

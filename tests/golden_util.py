@@ -37,3 +37,15 @@ def llava_fixture_batch(fx, entry, cfg, device="cpu"):
     hw = [tuple(x) for x in entry["image_hw"]]
     return synth_batch_llava(cfg, len(hw), hw, entry["seq_len"], seed=fx["seed_x"], tag=entry["tag"],
                              padding_side=entry["padding_side"], device=device)
+
+
+def qwen_fixture_cfg(fx):
+    from llava_reward_b200.config import QwenVLRewardConfig
+    return QwenVLRewardConfig(**fx["cfg_overrides"])
+
+
+def qwen_fixture_batch(fx, entry, cfg, device="cpu"):
+    from llava_reward_b200.synth import synth_batch_qwen
+    grids = [tuple(x) for x in entry["grids"]]
+    return synth_batch_qwen(cfg, grids, entry["seq_len"], seed=fx["seed_x"], tag=entry["tag"],
+                            padding_side=entry["padding_side"], device=device)
