@@ -526,17 +526,17 @@ class QwenVLRewardEngine(RewardEngine):
         grids = [tuple(int(v) for v in meta_h[2 * nmeta + B + 3 * i: 2 * nmeta + B + 3 * i + 3]) for i in range(n_images)]
         unit = cfg.vit_merge ** 2
         n_tok = int(meta_h[3 * B:4 * B].sum())
-        n_feat = sum(t * h * w for t, h, w in grids) // unit
+        n_patch = sum(gt * gh * gw for gt, gh, gw in grids)
+        n_feat = n_patch // unit
         if (meta_h[4 * B] & 2) or n_tok != n_feat:
             # get_placeholder_mask (transformers modeling_qwen2_5_vl.py:1204-1208) checks the batch total; a per-image
             # mismatch would shift features across images and is an error here
             raise ValueError(f"Image features and image tokens do not match, tokens: {n_tok}, features: {n_feat}")
-        if sum(t * h * w for t, h, w in grids) != pix.shape[0]:
-            raise ValueError(f"pixel_values has {pix.shape[0]} patches but image_grid_thw implies "
-                             f"{sum(t * h * w for t, h, w in grids)}")
-        for t, h, w in grids:
-            if h % cfg.vit_merge or w % cfg.vit_merge:
-                raise ValueError(f"image grid {(t, h, w)} is not a multiple of the merge size {cfg.vit_merge}")
+        if n_patch != pix.shape[0]:
+            raise ValueError(f"pixel_values has {pix.shape[0]} patches but image_grid_thw implies {n_patch}")
+        for gt, gh, gw in grids:
+            if gh % cfg.vit_merge or gw % cfg.vit_merge:
+                raise ValueError(f"image grid {(gt, gh, gw)} is not a multiple of the merge size {cfg.vit_merge}")
         plan_h = np.zeros((2 * B, L.PLAN_STRIDE), dtype=np.int32)
         plan_h[:B, L.PLAN_NV] = meta_h[3 * B:4 * B]
         plan_h[:B, L.PLAN_ROW_BASE] = np.concatenate([[0], np.cumsum(meta_h[3 * B:4 * B])[:-1]])
