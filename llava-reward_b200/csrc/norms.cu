@@ -60,6 +60,48 @@ rmsnorm_kernel(const bf16* __restrict__ x, int ldx, const int* __restrict__ row_
   }
 }
 
+// Warp-per-row RMSNorm for narrow rows (cols <= 2048: the Qwen2.5-VL vision tower's 1280): a 2.5 KB row does not fill a
+// CTA, and one CTA per row made launch/scheduling overhead the bound (3.1 TB/s measured). NCH x 16 B per lane, shuffle
+// reduction only, 8 rows per CTA.
+template <int NCH>
+__global__ void __launch_bounds__(256)
+rmsnorm_warp_kernel(const bf16* __restrict__ x, int ldx, const int* __restrict__ row_index, const bf16* __restrict__ w,
+                    bf16* __restrict__ y, int ldy, int rows, int cols, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const size_t src_row = row_index ? size_t(row_index[row]) : size_t(row);
+  const bf16* xr = x + src_row * ldx;
+  bf16* yr = y + size_t(row) * ldy;
+  const int nchunk = cols >> 3;
+  uint4 v[NCH];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = lane + i * 32;
+    if (c < nchunk) {
+      v[i] = ldg128(xr + c * 8);
+      float f[8];
+      unpack8(v[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+    }
+  }
+  ss = warp_sum(ss);
+  const float rstd = rsqrtf(ss / float(cols) + eps);
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = lane + i * 32;
+    if (c < nchunk) {
+      float f[8], g[8];
+      unpack8(v[i], f);
+      unpack8(ldg128(w + c * 8), g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = g[j] * bf16_round(f[j] * rstd);
+      stg128(yr + c * 8, pack8(f));
+    }
+  }
+}
+
 // Shared LayerNorm body: v[] holds this thread's chunks of the (already assembled) row.
 __device__ __forceinline__ void layernorm_row(uint4 (&v)[kMaxChunks], int nchunk, int cols, const bf16* w,
                                               const bf16* b, bf16* yr, float eps, float* red) {
@@ -220,7 +262,17 @@ extern "C" int lr_rmsnorm_bf16(const void* x, int ldx, const int* row_index, con
                                int rows, int cols, float eps, void* stream) {
   LR_CHECK_ARG(x && w && y && rows > 0 && cols > 0 && cols % 8 == 0 && cols <= kRowThreads * kMaxChunks * 8);
   if ((ldx % 8) || (ldy % 8) || !aligned16(x) || !aligned16(w) || !aligned16(y)) return LR_ERR_ALIGN;
-  rmsnorm_kernel<<<rows, kRowThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (cols <= 2048 && rows >= 1024) {  // narrow rows, many of them: one warp per row
+    const bf16 *xb = reinterpret_cast<const bf16*>(x), *wb = reinterpret_cast<const bf16*>(w);
+    bf16* yb = reinterpret_cast<bf16*>(y);
+    if (cols <= 1024)
+      rmsnorm_warp_kernel<4><<<(rows + 7) / 8, 256, 0, s>>>(xb, ldx, row_index, wb, yb, ldy, rows, cols, eps);
+    else
+      rmsnorm_warp_kernel<8><<<(rows + 7) / 8, 256, 0, s>>>(xb, ldx, row_index, wb, yb, ldy, rows, cols, eps);
+    return lr_launch_status();
+  }
+  rmsnorm_kernel<<<rows, kRowThreads, 0, s>>>(
       reinterpret_cast<const bf16*>(x), ldx, row_index, reinterpret_cast<const bf16*>(w), reinterpret_cast<bf16*>(y),
       ldy, cols, eps);
   return lr_launch_status();

@@ -153,7 +153,8 @@ def test_gemm_bad_args():
         ops.gemm(A, W, C, 128, 256, 64, L.EPI_BIAS, None)
 
 
-@pytest.mark.parametrize("rows,cols", [(1, 3072), (1000, 3072), (333, 1024), (17, 8192)])
+@pytest.mark.parametrize("rows,cols", [(1, 3072), (1000, 3072), (333, 1024), (17, 8192), (5003, 1280), (2050, 640),
+                                       (4100, 2048), (1024, 512)])
 def test_rmsnorm(rows, cols):
     x, w = rnd(rows, cols, std=2.0, seed=1), (1 + rnd(cols, std=0.1, seed=2).float()).to(bf)
     y = torch.empty_like(x)
