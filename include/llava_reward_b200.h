@@ -137,6 +137,14 @@ int lr_attention_ex_bf16(const void* q, const void* k, const void* v, void* o, i
                          int n_seq, int max_len, const int* seq_base, const int* seq_start, const int* seq_len,
                          int n_heads, int n_kv_heads, int head_dim, int causal, float scale, int impl, void* stream);
 
+/* Non-causal attention over SHORT SEGMENTS of one packed buffer (tcgen05 kernel): row r attends to the key rows
+ * [row_lo[r], row_hi[r]) (int32 per row, device; segments are contiguous, row_lo[r] <= r < row_hi[r], and at most 128
+ * rows long so that a 128-row query tile needs at most ~256 key rows). One CTA per 128 consecutive rows and head:
+ * full tiles for the <= 64-token windows of the Qwen2.5-VL vision blocks (window attention through cu_window_seqlens,
+ * transformers modeling_qwen2_5_vl.py:500-505, 244-262) instead of one half-empty tile per window. head_dim 64 or 96. */
+int lr_attention_seg_bf16(const void* q, const void* k, const void* v, void* o, int ld_qkv, int ld_o, int total_rows,
+                          const int* row_lo, const int* row_hi, int n_heads, int head_dim, float scale, void* stream);
+
 /* In-place su/longrope rotary embedding on the q and k thirds of a fused qkv buffer [rows, 3*n_heads*head_dim]:
  * x = bf16(bf16(x*cos) + bf16(rot_half(x)*sin)) with bf16 tables cos/sin[pos, head_dim/2].
  * Replaces Phi3SuScaledRotaryEmbedding + apply_rotary_pos_emb (modeling_phi3_v.py:438-476, 529-553). */

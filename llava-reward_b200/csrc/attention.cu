@@ -247,6 +247,9 @@ int attention_tc(const void* q, const void* k, const void* v, void* o, int ld_qk
                  int rows_per_seq, const int* seq_base, const int* seq_start, const int* seq_len, int n_heads,
                  int n_kv_heads, int head_dim, int causal, float scale, int split, cudaStream_t s);
 
+int attention_tc_seg(const void* q, const void* k, const void* v, void* o, int ld_qkv, int ld_o, int total_rows,
+                     const int* row_lo, const int* row_hi, int n_heads, int head_dim, float scale, cudaStream_t s);
+
 }  // namespace lr
 
 // product configuration at head_dim 128 (attention_tc variant code), chosen by tools/attn128_bench.py on the B200
@@ -302,4 +305,17 @@ extern "C" int lr_attention_ex_bf16(const void* q, const void* k, const void* v,
     return LR_ERR_BAD_ARG;
   return attention_tc(q, k, v, o, ld_qkv, ld_o, total_rows, n_seq, max_len, seq_base, seq_start, seq_len, n_heads,
                       n_kv_heads, head_dim, causal, scale, variant, reinterpret_cast<cudaStream_t>(stream));
+}
+
+
+extern "C" int lr_attention_seg_bf16(const void* q, const void* k, const void* v, void* o, int ld_qkv, int ld_o,
+                                     int total_rows, const int* row_lo, const int* row_hi, int n_heads, int head_dim,
+                                     float scale, void* stream) {
+  using namespace lr;
+  LR_CHECK_ARG(q && k && v && o && row_lo && row_hi && total_rows > 0 && n_heads > 0);
+  if ((ld_qkv % 8) || (ld_o % 8) || (reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
+                                     reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(o)) & 15)
+    return LR_ERR_ALIGN;
+  return attention_tc_seg(q, k, v, o, ld_qkv, ld_o, total_rows, row_lo, row_hi, n_heads, head_dim, scale,
+                          reinterpret_cast<cudaStream_t>(stream));
 }

@@ -102,7 +102,8 @@ template <int HD, bool CAUSAL, int SPLIT, int NT>
 __global__ void __launch_bounds__(128 + 128 * NT * SPLIT, AttnTcCfg<HD, NT>::kOnePerSm ? 1 : 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o, int ld_o, int rows_per_seq,
                const int* __restrict__ seq_base, const int* __restrict__ seq_start, const int* __restrict__ seq_len,
-               int q_col0, int k_col0, int v_col0, int kv_group, float scale_log2) {
+               int q_col0, int k_col0, int v_col0, int kv_group, float scale_log2,
+               const int* __restrict__ row_lo, const int* __restrict__ row_hi) {
   using Cfg = AttnTcCfg<HD, NT>;
   constexpr int NS = Cfg::kStages;
   constexpr int NA = Cfg::kAtoms;
@@ -139,10 +140,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
   const int m0 = qt * 128 * NT;
   // slot layout: sequence s owns rows [s*rows_per_seq, +rows_per_seq), valid run [start, start+len);
   // packed layout (seq_base != NULL): sequence s owns exactly rows [seq_base[s], +seq_len[s]), rows_per_seq = max len
-  const int start = (seq_start && !seq_base) ? seq_start[seq] : 0;
+  // segment layout (row_lo != NULL; non-causal, NT == 1): ONE buffer of rows_per_seq rows cut into short segments (the
+  // <= 64-token windows of the Qwen2.5-VL vision tower); row r attends to keys [row_lo[r], row_hi[r]). A CTA takes 128
+  // consecutive rows - several segments - and the K/V rows from the first row's segment start to the last row's
+  // segment end (<= 2 blocks of 128), masking per row: full 128-row tiles instead of one half-empty tile per window.
+  const bool seg = row_lo != nullptr;
+  int start = (seq_start && !seq_base) ? seq_start[seq] : 0;
   const int len = seq_len ? seq_len[seq] : rows_per_seq;
-  const int end = start + len;
+  int end = start + len;
   const int slot_row0 = seq_base ? seq_base[seq] : seq * rows_per_seq;
+  if (seg) {
+    start = row_lo[m0];
+    end = row_hi[min(m0 + 128 * NT, rows_per_seq) - 1];
+  }
 
   int lo[2], hi[2], nblk[2], kv_end[2];
 #pragma unroll
@@ -330,13 +340,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     float l_reg[4] = {0.f, 0.f, 0.f, 0.f};  // row sum kept in registers when there are no ones columns (!ONES)
     const int nx = nblk[x];
     const bool tr = (q == 0 && lane == 0 && h == 0);
+    int my_lo = 0, my_hi = 0;  // segment layout: this row's key range (absolute rows)
+    if (seg && row_abs < rows_per_seq) {
+      my_lo = row_lo[row_abs];
+      my_hi = row_hi[row_abs];
+    }
     for (int j = 0; j < nx; ++j) {
       if (tr) ATTN_TRACE(1 + x, 0, j);
       mbar_wait(&s_full[x], j & 1);
       tc_fence_after();
       if (tr) ATTN_TRACE(1 + x, 1, j);
       const int kv0 = start + j * 128;
-      const bool need_mask = (kv0 + 128 > kv_end[x]) || (CAUSAL && kv0 + 127 > m0 + x * 128);
+      const bool need_mask = seg || (kv0 + 128 > kv_end[x]) || (CAUSAL && kv0 + 127 > m0 + x * 128);
       // whole S row -> registers, then give the TMEM buffer back to the MMA warp
       uint32_t sv[NCH][32];
 #pragma unroll
@@ -349,7 +364,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int col = kv0 + (h * NCH + c) * 32 + i;
-            const bool ok = col < kv_end[x] && (!CAUSAL || col <= row_abs);
+            const bool ok = seg ? (col >= my_lo && col < my_hi) : (col < kv_end[x] && (!CAUSAL || col <= row_abs));
             sv[c][i] = ok ? sv[c][i] : 0xff800000u;  // -inf
           }
       }
@@ -511,7 +526,8 @@ static EncodeTiledFn attn_encode_fn() {
 template <int HD, bool CAUSAL, int SPLIT, int NT>
 static int launch_attn_tc(const void* base, int total_rows, int ld_qkv, int q_col0, int k_col0, int v_col0, void* o,
                           int ld_o, int n_seq, int rows_per_seq, const int* seq_base, const int* seq_start,
-                          const int* seq_len, int n_heads, int kv_group, float scale, cudaStream_t stream) {
+                          const int* seq_len, int n_heads, int kv_group, float scale, cudaStream_t stream,
+                          const int* row_lo = nullptr, const int* row_hi = nullptr) {
   using Cfg = AttnTcCfg<HD, NT>;
   EncodeTiledFn fn = attn_encode_fn();
   if (!fn) return LR_ERR_NO_DRIVER;
@@ -532,7 +548,7 @@ static int launch_attn_tc(const void* base, int total_rows, int ld_qkv, int q_co
   dim3 grid((rows_per_seq + 128 * NT - 1) / (128 * NT), n_heads, n_seq);
   kern<<<grid, 128 + 128 * NT * SPLIT, Cfg::kSmemBytes, stream>>>(tm, reinterpret_cast<bf16*>(o), ld_o, rows_per_seq, seq_base,
                                                       seq_start, seq_len, q_col0, k_col0, v_col0, kv_group,
-                                                      scale * 1.4426950408889634f);
+                                                      scale * 1.4426950408889634f, row_lo, row_hi);
   return lr_launch_status();
 }
 
@@ -567,6 +583,22 @@ int attention_tc(const void* q, const void* k, const void* v, void* o, int ld_qk
     return launch_attn_tc<128, true, 1, 1>(LR_ATTN_ARGS);
   }
 #undef LR_ATTN_ARGS
+  return LR_ERR_BAD_ARG;
+}
+
+// Segment layout (see the kernel): non-causal, head_dim 64 or 96, one query tile per CTA.
+int attention_tc_seg(const void* q, const void* k, const void* v, void* o, int ld_qkv, int ld_o, int total_rows,
+                     const int* row_lo, const int* row_hi, int n_heads, int head_dim, float scale, cudaStream_t s) {
+  const ptrdiff_t kd = (reinterpret_cast<const char*>(k) - reinterpret_cast<const char*>(q)) / 2;
+  const ptrdiff_t vd = (reinterpret_cast<const char*>(v) - reinterpret_cast<const char*>(q)) / 2;
+  const int w = n_heads * head_dim;
+  if (kd < 0 || vd < 0 || kd + w > ld_qkv || vd + w > ld_qkv) return LR_ERR_BAD_ARG;
+  if (head_dim == 96)
+    return launch_attn_tc<96, false, 1, 1>(q, total_rows, ld_qkv, 0, int(kd), int(vd), o, ld_o, 1, total_rows, nullptr,
+                                           nullptr, nullptr, n_heads, 1, scale, s, row_lo, row_hi);
+  if (head_dim == 64)
+    return launch_attn_tc<64, false, 1, 1>(q, total_rows, ld_qkv, 0, int(kd), int(vd), o, ld_o, 1, total_rows, nullptr,
+                                           nullptr, nullptr, n_heads, 1, scale, s, row_lo, row_hi);
   return LR_ERR_BAD_ARG;
 }
 

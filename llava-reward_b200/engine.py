@@ -373,6 +373,7 @@ class QwenVLRewardEngine(RewardEngine):
     def __init__(self, *a, **k):
         super().__init__(*a, **k)
         self._vplans: Dict[tuple, dict] = {}
+        self.window_attn = "seg"   # "seg" (product) | "packed" (one tile per window; kept for comparison / tests)
 
     def rope_tables(self, n_pos: int, long: bool = False):
         """cos/sin [n_pos, head_dim/2] bf16 by position (Qwen2_5_VLRotaryEmbedding.forward, default rope,
@@ -416,7 +417,11 @@ class QwenVLRewardEngine(RewardEngine):
             def d(a):
                 return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
+            wlen = np.diff(win_cu)
+            row_lo = np.repeat(win_cu[:-1], wlen).astype(np.int32)     # per-token window bounds (lr_attention_seg_bf16)
+            row_hi = np.repeat(win_cu[1:], wlen).astype(np.int32)
             vp = dict(T=T, src_row=d(hp["src_row"]), cos=cos.to(dev), sin=sin.to(dev), unwin=d(unwin),
+                      row_lo=d(row_lo), row_hi=d(row_hi),
                       win_base=d(win_cu[:-1]), win_len=d(np.diff(win_cu).astype(np.int32)), n_win=len(win_cu) - 1,
                       win_max=int(np.diff(win_cu).max()),
                       img_base=d(img_cu[:-1]), img_len=d(np.diff(img_cu).astype(np.int32)), n_img=len(img_cu) - 1,
@@ -450,12 +455,15 @@ class QwenVLRewardEngine(RewardEngine):
             ops.rmsnorm(x, lw["n1"], hn, T, D, cfg.vit_eps)
             ops.gemm_rope_ex(hn, lw["qkv_w"], qkv, T, QW, D, lw["qkv_b"], None, vp["cos"], vp["sin"], 2 * AW, hdp,
                              L.EPI_BIAS_ROPE_F32)
-            if li in cfg.vit_fullatt:
-                base, ln, n, mx = vp["img_base"], vp["img_len"], vp["n_img"], vp["img_max"]
-            else:
-                base, ln, n, mx = vp["win_base"], vp["win_len"], vp["n_win"], vp["win_max"]
-            ops.attention_ex(qkv, qkv[:, AW:], qkv[:, 2 * AW:], ao, QW, AW, T, n, mx, base, None, ln, nh, nh, hdp, False,
-                             scale, L.ATTN_TCGEN05)
+            if li in cfg.vit_fullatt:     # one packed sequence per image
+                ops.attention_ex(qkv, qkv[:, AW:], qkv[:, 2 * AW:], ao, QW, AW, T, vp["n_img"], vp["img_max"],
+                                 vp["img_base"], None, vp["img_len"], nh, nh, hdp, False, scale, L.ATTN_TCGEN05)
+            elif self.window_attn == "seg":   # full 128-row tiles spanning several windows, per-row key ranges
+                ops.attention_seg(qkv, qkv[:, AW:], qkv[:, 2 * AW:], ao, QW, AW, T, vp["row_lo"], vp["row_hi"], nh, hdp,
+                                  scale)
+            else:                         # one packed sequence (one 128-row tile) per window
+                ops.attention_ex(qkv, qkv[:, AW:], qkv[:, 2 * AW:], ao, QW, AW, T, vp["n_win"], vp["win_max"],
+                                 vp["win_base"], None, vp["win_len"], nh, nh, hdp, False, scale, L.ATTN_TCGEN05)
             self._gemm(ao, lw["proj_w"], x, T, D, AW, L.EPI_BIAS_RESIDUAL, lw["proj_b"], x)
             ops.rmsnorm(x, lw["n2"], hn, T, D, cfg.vit_eps)
             self._gemm(hn, lw["gu_w"], ff, T, 2 * Ip, D, L.EPI_BIAS_SWIGLU, lw["gu_b"])

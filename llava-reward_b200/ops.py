@@ -135,6 +135,12 @@ def attention_ex(q, k, v, o, ld_qkv, ld_o, total_rows, n_seq, max_len, seq_base,
            _stream())
 
 
+def attention_seg(q, k, v, o, ld_qkv, ld_o, total_rows, row_lo, row_hi, n_heads, head_dim, scale):
+    _need_cuda(q, k, v, o, row_lo, row_hi)
+    L.call("lr_attention_seg_bf16", _ptr(q), _ptr(k), _ptr(v), _ptr(o), ld_qkv, ld_o, total_rows, _ptr(row_lo),
+           _ptr(row_hi), n_heads, head_dim, scale, _stream())
+
+
 def skipca_scores_ex(q, kv, plan, scores, B, H, max_nv, pad_score):
     _need_cuda(q, kv, plan, scores)
     L.call("lr_skipca_scores_ex", _ptr(q), q.stride(0), _ptr(kv), kv.stride(0), _ptr(plan), _ptr(scores), B, H, max_nv,

@@ -58,6 +58,39 @@ def test_attention_packed_hd96_noncausal(lens):
     assert (o[:T].view(T, heads, hdp)[..., hd:] == 0).all()   # padded head columns stay exactly zero
 
 
+@pytest.mark.parametrize("lens", [[64, 64, 16, 64, 8, 4, 48], [64] * 9 + [48] * 3 + [36], [4], [128, 64, 1, 127, 64],
+                                  [48, 36] * 40 + [64] * 33])
+def test_attention_segments_hd96(lens):
+    """segment layout: 128-row tiles spanning several windows, every row attends to its own window only - same
+    results as the one-sequence-per-window packed launch (bit-identical inputs, same per-row arithmetic up to the
+    order of the masked-out zero terms) and as the fp32 reference"""
+    heads, hd, hdp = 3, 80, 96
+    T = sum(lens)
+    AW = heads * hdp
+    qkv = rnd(T, 3 * AW, seed=9)
+    qkv.view(T, 3, heads, hdp)[..., hd:] = 0
+    cu = np.concatenate([[0], np.cumsum(lens)])
+    lo = torch.tensor(np.repeat(cu[:-1], lens), dtype=torch.int32, device=DEV)
+    hi = torch.tensor(np.repeat(cu[1:], lens), dtype=torch.int32, device=DEV)
+    o = torch.full((T + 128, AW), float("nan"), dtype=bf, device=DEV)
+    scale = hd ** -0.5
+    ops.attention_seg(qkv, qkv[:, AW:], qkv[:, 2 * AW:], o, 3 * AW, AW, T, lo, hi, heads, hdp, scale)
+    o2 = torch.full((T, AW), float("nan"), dtype=bf, device=DEV)
+    base = torch.tensor(cu[:-1], dtype=torch.int32, device=DEV)
+    ln = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    ops.attention_ex(qkv, qkv[:, AW:], qkv[:, 2 * AW:], o2, 3 * AW, AW, T, len(lens), max(lens), base, None, ln, heads,
+                     heads, hdp, False, scale)
+    torch.cuda.synchronize()
+    assert torch.isnan(o[T:].float()).all()
+    f = qkv.float().view(T, 3, heads, hdp)
+    b0 = 0
+    for n in lens:
+        ref = attn_ref(f[b0:b0 + n, 0], f[b0:b0 + n, 1], f[b0:b0 + n, 2], False, scale).reshape(n, AW)
+        check_close(o[b0:b0 + n], ref, f"segment attention at {b0}", atol=1e-2, rtol=2e-2)
+        b0 += n
+    assert (o[:T].float() - o2.float()).abs().max().item() < 8e-3
+
+
 @pytest.mark.parametrize("heads,kvh,T,nseq", [(4, 2, 130, 3), (28, 4, 700, 2), (8, 1, 257, 2), (4, 4, 300, 1)])
 def test_attention_gqa_hd128(heads, kvh, T, nseq):
     hd = 128
@@ -416,6 +449,22 @@ def test_qwen_stages_vs_oracle(case, tmp_path_factory):
     # image rows of inputs_embeds are bit-exact copies of the merger output (original order)
     sel = ids == cfg.image_token_id
     assert torch.equal(te["inputs_embeds"].view(B, S, -1)[sel], te["image_embeds"])
+
+
+def test_qwen_window_attention_layouts_agree(tmp_path_factory):
+    """engine with the segment-layout window attention (product) vs one packed sequence per window"""
+    fx = load_fixture("qwen_slim_bt")
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    batch = to_dev(qwen_fixture_batch(fx, fx["batches"][1], cfg))
+    assert model.engine.window_attn == "seg"
+    r_seg, _ = model.custom_forward(inputs_batch=batch)
+    model.engine.window_attn = "packed"
+    try:
+        r_pk, _ = model.custom_forward(inputs_batch=batch)
+    finally:
+        model.engine.window_attn = "seg"
+    print(f"window attention: seg {r_seg.flatten().tolist()} packed {r_pk.flatten().tolist()}")
+    assert (r_seg.float() - r_pk.float()).abs().max().item() < 1e-2
 
 
 def test_qwen_validation_errors(tmp_path_factory):
