@@ -261,6 +261,16 @@ int lr_patch_pack_f32(const uint8_t* img, int rh, int rw, int pad_top, int pad_l
 int lr_patch_rows_bf16(const float* pixels, const int* src_row, void* out, int ldo, int rows, int K, int Kpad,
                        void* stream);
 
+/* Qwen2-VL image -> flattened patches: uint8 HWC image [H, W, 3] (device; already resized by smart_resize, H and W
+ * multiples of patch*merge) -> out fp32 [(H/patch)*(W/patch), 3*2*patch*patch]: rescale + normalise through lut768
+ * (HOST pointer, [3][256] floats, built by the caller with the processor's own arithmetic so the result is
+ * bit-identical), the still image repeated over the temporal_patch_size = 2 axis, rows in 2x2-merge order and columns
+ * in (channel, t, py, px) order. Replaces rescale / normalize / the reshape-transpose of transformers'
+ * Qwen2VLImageProcessor._preprocess (image_processing_pil_qwen2_vl.py:186-217) used by the reference through
+ * AutoProcessor (llava_reward/datasets/reward_dataset.py:472-487). patch even. */
+int lr_qwen_patchify_f32(const uint8_t* img, int H, int W, int patch, int merge, const float* lut768, float* out,
+                         void* stream);
+
 /* M-RoPE plan, images only: pos3[c, b*S+s] (c = temporal, height, width; int32, comp stride B*S) as
  * Qwen2_5_VLForConditionalGeneration.get_rope_index of transformers 4.50 (the release the reference pins; called from
  * the forward the reference invokes at rw_model_general_preference.py:357) computes them from input_ids,

@@ -51,6 +51,7 @@ SIGNATURES = {
     "lr_attention_seg_bf16": ([p, p, p, p, i32, i32, i32, p, p, i32, i32, f32, p], i32),
     "lr_skipca_scores_ex": ([p, i32, p, i32, p, p, i32, i32, i32, f32, p], i32),
     "lr_patch_rows_bf16": ([p, p, p, i32, i32, i32, i32, p], i32),
+    "lr_qwen_patchify_f32": ([p, i32, i32, i32, i32, p, p, p], i32),
     "lr_mrope_plan": ([p, p, i32, i32, i64, p, i32, i32, p, p, p, i32, i32, i32, i32, p, p, p, p, p], i32),
     "lr_compact_rows_bf16": ([p, i32, p, p, p, i32, i32, i32, i32, p], i32),
 }

@@ -1,8 +1,8 @@
 """Batch evaluation callers around the hot path: the collate step of
 `GeneralRewardDataset.collate_fn` (reference llava_reward/datasets/reward_dataset.py:137-202, left padding via
 `zero_pad_sequences`, datasets/utils.py:5-13) and the two loops of `batch_rm_inference`
-(reference eval/batch_inference_rm_phi.py:70-152, eval/batch_inference_rm_llava.py:70-152 - the same loops with the
-`inputs_batch=` calling convention): pairwise preference accuracy and single-image (BT / cls) scoring.
+(reference eval/batch_inference_rm_phi.py:70-152, eval/batch_inference_rm_llava.py:70-152 and
+eval/batch_inference_rm_qwen.py:75-146 - the same loops with the `inputs_batch=` calling convention): pairwise preference accuracy and single-image (BT / cls) scoring.
 Inputs are per-sample dicts as produced by `inference_process_phi3v` / the processor; everything stays on the GPU
 until the final numpy conversion.
 """
@@ -40,8 +40,8 @@ def collate_samples(items: Sequence[Dict[str, torch.Tensor]], pad_token_id: int)
 def _forward(model, batch):
     """One scoring call in the backbone's own convention: positional tensors for phi3v
     (eval/batch_inference_rm_phi.py:93), the processor's BatchFeature as `inputs_batch` for llava
-    (eval/batch_inference_rm_llava.py:86-87)."""
-    if getattr(model, "model_type", "phi3v") == "llava":
+    (eval/batch_inference_rm_llava.py:86-87) and qwen (eval/batch_inference_rm_qwen.py:91-92)."""
+    if getattr(model, "model_type", "phi3v") in ("llava", "qwen"):
         return model.custom_forward(inputs_batch=batch)[0]
     return model.custom_forward(batch["input_ids"], batch["attention_mask"], batch["pixel_values"],
                                 batch["image_sizes"])[0]

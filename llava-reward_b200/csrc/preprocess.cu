@@ -133,6 +133,27 @@ patch_pack_kernel(const uint8_t* __restrict__ img, int rh, int rw, int pad_top, 
   *reinterpret_cast<float4*>(out + i) = o;
 }
 
+// Qwen2-VL patchify: out[row, c*2*P*P + t*P*P + py*P + px] = lut[c][img[gy*P+py, gx*P+px, c]] for t = 0, 1 (a still image is
+// repeated along the temporal axis), row = ((gy/m)*(gw/m) + gx/m)*m*m + (gy%m)*m + gx%m (2x2-merge order).
+// One thread = 2 consecutive px of one (row, c, py) line (P = 14 is not a multiple of 4): float2 stores, both t copies.
+__global__ void __launch_bounds__(256)
+qwen_patchify_kernel(const uint8_t* __restrict__ img, int W, int gh, int gw, int P, int m, float* __restrict__ out,
+                     const __grid_constant__ PatchLut lut) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int hp = P / 2;
+  const size_t total = size_t(gh) * gw * 3 * P * hp;
+  if (i >= total) return;
+  const int px = int(i % hp) * 2, py = int((i / hp) % P), c = int((i / (size_t(hp) * P)) % 3);
+  const int row = int(i / (size_t(hp) * P * 3));
+  const int mm = m * m, blk = row / mm, in = row % mm;
+  const int gy = (blk / (gw / m)) * m + in / m, gx = (blk % (gw / m)) * m + in % m;
+  const uint8_t* src = img + (size_t(gy * P + py) * W + gx * P + px) * 3 + c;
+  const float2 v = make_float2(lut.v[c][src[0]], lut.v[c][src[3]]);
+  float* o = out + size_t(row) * (3 * 2 * P * P) + size_t(c) * 2 * P * P + py * P + px;
+  *reinterpret_cast<float2*>(o) = v;
+  *reinterpret_cast<float2*>(o + P * P) = v;
+}
+
 }  // namespace lr
 
 using namespace lr;
@@ -174,5 +195,21 @@ extern "C" int lr_patch_pack_f32(const uint8_t* img, int rh, int rw, int pad_top
   const size_t n4 = size_t(grid_h) * grid_w * 3 * 336 * 336 / 4;
   patch_pack_kernel<<<unsigned((n4 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       img, rh, rw, pad_top, pad_left, grid_h, grid_w, out, lut);
+  return lr_launch_status();
+}
+
+
+extern "C" int lr_qwen_patchify_f32(const uint8_t* img, int H, int W, int patch, int merge, const float* lut768,
+                                    float* out, void* stream) {
+  LR_CHECK_ARG(img && out && lut768 && H > 0 && W > 0 && patch > 0 && patch % 2 == 0 && merge > 0);
+  LR_CHECK_ARG(H % (patch * merge) == 0 && W % (patch * merge) == 0);
+  if (reinterpret_cast<uintptr_t>(out) & 7) return LR_ERR_ALIGN;
+  PatchLut lut;
+  for (int c = 0; c < 3; ++c)
+    for (int u = 0; u < 256; ++u) lut.v[c][u] = lut768[c * 256 + u];  // host pointer
+  const int gh = H / patch, gw = W / patch;
+  const size_t n = size_t(gh) * gw * 3 * patch * (patch / 2);
+  qwen_patchify_kernel<<<unsigned((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      img, W, gh, gw, patch, merge, out, lut);
   return lr_launch_status();
 }

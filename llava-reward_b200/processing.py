@@ -438,3 +438,173 @@ def load_processor_llava(pretrain_dir: str, cfg: LlavaNextRewardConfig, cache_di
                 break
     proc = LlavaNextProcessorB200(LlavaNextImageProcessorB200(cfg.image_grid_pinpoints, device=device), tokenizer)
     return proc, tokenizer
+
+
+# --------------------------------------------------------------------------------------
+# Qwen2.5-VL: reference get_tokenizer_qwen (llava_reward/utils/utils.py:34-44) -> AutoProcessor with
+# min_pixels = 256*28*28, max_pixels = 1280*28*28; image side of transformers' Qwen2VLImageProcessor
+# --------------------------------------------------------------------------------------
+def smart_resize(height: int, width: int, factor: int = 28, min_pixels: int = 256 * 28 * 28,
+                 max_pixels: int = 1280 * 28 * 28) -> Tuple[int, int]:
+    """transformers image_processing_pil_qwen2_vl.smart_resize (:56-84): both sides multiples of `factor`, pixel count
+    inside [min_pixels, max_pixels], aspect ratio kept as closely as possible."""
+    import math
+    if max(height, width) / min(height, width) > 200:
+        raise ValueError(f"absolute aspect ratio must be smaller than 200, got {max(height, width) / min(height, width)}")
+    h_bar = round(height / factor) * factor
+    w_bar = round(width / factor) * factor
+    if h_bar * w_bar > max_pixels:
+        beta = math.sqrt((height * width) / max_pixels)
+        h_bar = max(factor, math.floor(height / beta / factor) * factor)
+        w_bar = max(factor, math.floor(width / beta / factor) * factor)
+    elif h_bar * w_bar < min_pixels:
+        beta = math.sqrt(min_pixels / (height * width))
+        h_bar = math.ceil(height * beta / factor) * factor
+        w_bar = math.ceil(width * beta / factor) * factor
+    return h_bar, w_bar
+
+
+class Qwen2VLImageProcessorB200:
+    """GPU counterpart of transformers' Qwen2VLImageProcessor (PIL backend) as the reference configures it
+    (BICUBIC, CLIP mean/std, patch 14, temporal 2, merge 2, min/max_pixels of get_tokenizer_qwen): the uint8 image goes
+    to the device once; Pillow-exact bicubic resampling (`lr_resample_u8`), rescale + normalise + patch flattening
+    (`lr_qwen_patchify_f32`) run there. Output is bit-identical to the PIL path (tests/golden/qwen_preprocess.pt)."""
+    model_input_names = ["pixel_values", "image_grid_thw"]
+
+    def __init__(self, min_pixels: int = 256 * 28 * 28, max_pixels: int = 1280 * 28 * 28, patch_size: int = 14,
+                 merge_size: int = 2, temporal_patch_size: int = 2, image_mean=None, image_std=None, device="cuda",
+                 **kwargs):
+        if temporal_patch_size != 2:
+            raise ValueError("temporal_patch_size must be 2 (Qwen2-VL / Qwen2.5-VL)")
+        self.min_pixels, self.max_pixels = int(min_pixels), int(max_pixels)
+        self.patch_size, self.merge_size, self.temporal_patch_size = int(patch_size), int(merge_size), 2
+        self.image_mean = tuple(image_mean) if image_mean is not None else OPENAI_CLIP_MEAN
+        self.image_std = tuple(image_std) if image_std is not None else OPENAI_CLIP_STD
+        self.device = torch.device(device)
+        self._taps = {}
+        x = (np.arange(256, dtype=np.uint8).astype(np.float64) * (1 / 255)).astype(np.float32)
+        mean = np.array(self.image_mean, dtype=np.float32)[:, None]
+        std = np.array(self.image_std, dtype=np.float32)[:, None]
+        self._lut = np.ascontiguousarray(((x[None, :] - mean) / std).astype(np.float32))
+
+    _dev_taps = LlavaNextImageProcessorB200._dev_taps
+    _resample = LlavaNextImageProcessorB200._resample
+    _resize = LlavaNextImageProcessorB200._resize
+
+    def grid(self, hw) -> Tuple[int, int]:
+        rh, rw = smart_resize(int(hw[0]), int(hw[1]), self.patch_size * self.merge_size, self.min_pixels, self.max_pixels)
+        return rh // self.patch_size, rw // self.patch_size
+
+    def get_number_of_image_patches(self, height: int, width: int, images_kwargs=None) -> int:
+        gh, gw = self.grid((height, width))
+        return gh * gw
+
+    def preprocess(self, images, return_tensors=None, out=None, **kwargs):
+        if self.device.type != "cuda":
+            raise RuntimeError("Qwen2VLImageProcessorB200 runs on CUDA only (no CPU fallback)")
+        images = list(images) if isinstance(images, (list, tuple)) else [images]
+        arrs = [im if torch.is_tensor(im) else _to_hwc_u8(im) for im in images]
+        grids = [self.grid(a.shape[:2]) for a in arrs]
+        K = 3 * 2 * self.patch_size * self.patch_size
+        T = sum(gh * gw for gh, gw in grids)
+        if out is None:
+            out = torch.empty(T, K, dtype=torch.float32, device=self.device)
+        elif tuple(out.shape) != (T, K) or out.dtype != torch.float32 or not out.is_cuda:
+            raise ValueError(f"out must be a CUDA float32 tensor of shape {(T, K)}")
+        import ctypes
+        lut = self._lut.ctypes.data_as(ctypes.c_void_p)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            row = 0
+            for a, (gh, gw) in zip(arrs, grids):
+                if torch.is_tensor(a):
+                    if a.dtype != torch.uint8 or a.dim() != 3 or a.shape[2] != 3:
+                        raise ValueError("image tensors must be uint8 HxWx3")
+                    x = a.to(self.device, non_blocking=True).contiguous()
+                else:
+                    x = torch.from_numpy(a).to(self.device, non_blocking=True)
+                x = self._resize(x, gh * self.patch_size, gw * self.patch_size)
+                L.call("lr_qwen_patchify_f32", x.data_ptr(), gh * self.patch_size, gw * self.patch_size, self.patch_size,
+                       self.merge_size, lut, out[row].data_ptr(), stream)
+                row += gh * gw
+        thw = [[1, gh, gw] for gh, gw in grids]
+        data = {"pixel_values": out, "image_grid_thw": thw}
+        if return_tensors == "pt":
+            data["image_grid_thw"] = torch.tensor(thw, dtype=torch.int64)
+        return data
+
+    __call__ = preprocess
+
+
+class Qwen2_5_VLProcessorB200:
+    """`processor(text=..., images=..., padding=True, return_tensors="pt")` of transformers' Qwen2_5_VLProcessor
+    (processing_qwen2_5_vl.py) as the reference's collate_fn calls it (reward_dataset.py:472-487): every
+    `<|image_pad|>` in a prompt is expanded to the image's merged-token count (grid_h * grid_w / merge^2), then the
+    tokenizer pads the batch. Image preprocessing runs on the GPU. Returns a transformers BatchFeature."""
+    image_token = "<|image_pad|>"
+
+    def __init__(self, image_processor: Qwen2VLImageProcessorB200, tokenizer):
+        self.image_processor, self.tokenizer = image_processor, tokenizer
+
+    def apply_chat_template(self, conversation, tokenize=False, add_generation_prompt=True, **kw):
+        if hasattr(self.tokenizer, "apply_chat_template") and getattr(self.tokenizer, "chat_template", None):
+            return self.tokenizer.apply_chat_template(conversation, tokenize=tokenize,
+                                                      add_generation_prompt=add_generation_prompt, **kw)
+        # Fallback when the checkpoint directory ships no chat template: the Qwen2.5-VL-Instruct template restated
+        # (default system prompt; an image is <|vision_start|><|image_pad|><|vision_end|>). The reference slices this
+        # string with [58:-23] (reward_dataset.py:417), which removes exactly the system turn and the generation prompt.
+        out = "<|im_start|>system\nYou are a helpful assistant.<|im_end|>\n"
+        for msg in conversation:
+            out += f"<|im_start|>{msg['role']}\n"
+            content = msg["content"] if isinstance(msg["content"], list) else [{"type": "text", "text": msg["content"]}]
+            for c in content:
+                out += "<|vision_start|><|image_pad|><|vision_end|>" if c["type"] == "image" else c.get("text", "")
+            out += "<|im_end|>\n"
+        return out + ("<|im_start|>assistant\n" if add_generation_prompt else "")
+
+    def __call__(self, text=None, images=None, videos=None, padding=False, truncation=None, max_length=None,
+                 return_tensors="pt", **kwargs):
+        from transformers import BatchFeature
+        if text is None:
+            raise ValueError("You have to specify at least `text`.")
+        if videos:
+            raise NotImplementedError("video inputs: the reference's reward datasets are image-only")
+        texts = [text] if isinstance(text, str) else list(text)
+        data = {}
+        if images is not None:
+            images = list(images) if isinstance(images, (list, tuple)) else [images]
+            image_inputs = self.image_processor(images, return_tensors="pt")
+            m2 = self.image_processor.merge_size ** 2
+            it = iter(image_inputs["image_grid_thw"].tolist())
+            expanded = []
+            for t in texts:
+                parts = t.split(self.image_token)
+                s = parts[0]
+                for tail in parts[1:]:
+                    try:
+                        g = next(it)
+                    except StopIteration:
+                        raise ValueError("more <|image_pad|> placeholders than images") from None
+                    s += self.image_token * (g[0] * g[1] * g[2] // m2) + tail
+                expanded.append(s)
+            if next(it, None) is not None:
+                raise ValueError("fewer <|image_pad|> placeholders than images")
+            texts = expanded
+            data.update(image_inputs)
+        tok = self.tokenizer(texts, padding=padding, truncation=truncation, max_length=max_length,
+                             return_tensors=return_tensors)
+        data.update({"input_ids": tok["input_ids"], "attention_mask": tok["attention_mask"]})
+        return BatchFeature(data=data)
+
+
+def load_processor_qwen(pretrain_dir: str, cache_dir=None, use_fast=True, device="cuda"):
+    """(processor, tokenizer) like reference get_tokenizer_qwen (llava_reward/utils/utils.py:34-44), from a LOCAL
+    Qwen2.5-VL checkpoint directory: tokenizer via transformers (left padding), image half on the GPU with the
+    reference's pixel budget."""
+    from transformers import AutoTokenizer
+    tokenizer = AutoTokenizer.from_pretrained(pretrain_dir, use_fast=use_fast, cache_dir=cache_dir, padding_side="left")
+    if tokenizer.pad_token is None:   # reference utils.py:40-42
+        tokenizer.pad_token = tokenizer.eos_token
+        tokenizer.pad_token_id = tokenizer.eos_token_id
+    proc = Qwen2_5_VLProcessorB200(Qwen2VLImageProcessorB200(256 * 28 * 28, 1280 * 28 * 28, device=device), tokenizer)
+    return proc, tokenizer

@@ -50,12 +50,11 @@ def load_reward_adaptor(args, model_type, reward_config_path, load_tokenizer=Fal
                                                    ft_projector=bool(getattr(args, "ft_projector", False)))
         qmodel = B200QwenRewardModel(qcfg, qprov)
         if load_tokenizer:
-            # get_tokenizer_qwen (llava_reward/utils/utils.py) = AutoProcessor + its tokenizer, left padding
-            from transformers import AutoProcessor
-            processor = AutoProcessor.from_pretrained(pretrain, cache_dir=getattr(args, "cache_dir", None),
-                                                      min_pixels=256 * 28 * 28, max_pixels=1280 * 28 * 28)
-            tokenizer = processor.tokenizer
-            tokenizer.padding_side = "left"
+            # get_tokenizer_qwen (llava_reward/utils/utils.py:34-44): tokenizer with left padding + the image processor
+            # with min_pixels = 256*28*28, max_pixels = 1280*28*28 (here: GPU preprocessing, bit-identical output)
+            from .processing import load_processor_qwen
+            processor, tokenizer = load_processor_qwen(pretrain, cache_dir=getattr(args, "cache_dir", None),
+                                                       use_fast=not getattr(args, "disable_fast_tokenizer", False))
             tokenizer.truncation_side = "right"
             return args, qmodel, processor, tokenizer
         return args, qmodel

@@ -21,3 +21,8 @@ def synth_image(name: str, h: int, w: int) -> np.ndarray:
 LLAVA_CASES = {"landscape_512x640": (512, 640), "square_768": (768, 768), "portrait_1000x300": (1000, 300),
                "wide_300x900": (300, 900), "small_200x333": (200, 333), "exact_672x672": (672, 672),
                "tall_1080x700": (1080, 700), "tiny_64x48": (64, 48)}
+
+# Qwen2.5-VL cases: inside the pixel budget, above max_pixels (downscale), below min_pixels (upscale), odd sizes
+QWEN_CASES = {"landscape_512x640": (512, 640), "square_1024": (1024, 1024), "portrait_1000x300": (1000, 300),
+              "wide_1080x1920": (1080, 1920), "small_200x333": (200, 333), "tiny_64x48": (64, 48),
+              "exact_448x448": (448, 448)}

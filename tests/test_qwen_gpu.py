@@ -519,3 +519,58 @@ def test_qwen_skipca_without_any_pad_token(tmp_path_factory):
     err = (r.float() - o32).abs().max().item()
     print(f"no-pad SkipCA: engine {r.flatten().tolist()} fp32 {o32.flatten().tolist()} err {err:.4g} floor {floor:.4g}")
     assert err < REWARD_TOL + 3 * floor
+
+
+# ----------------------------------------------------------------------------------------------- preprocessing + callers
+def test_qwen_gpu_preprocess_bit_exact_vs_transformers():
+    """GPU preprocessing (smart_resize + Pillow-exact bicubic taps + lr_qwen_patchify_f32) against transformers' own PIL
+    processor (tests/golden/qwen_preprocess.pt): SHA-1 of the float32 bytes."""
+    import hashlib
+    from preprocess_util import QWEN_CASES, synth_image
+    from llava_reward_b200.processing import Qwen2VLImageProcessorB200
+    fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "qwen_preprocess.pt"),
+                    weights_only=False)
+    proc = Qwen2VLImageProcessorB200()
+    for e in fx["cases"]:
+        h, w = e["hw"]
+        out = proc.preprocess([synth_image(e["name"], h, w)], return_tensors="pt")
+        pv = out["pixel_values"].cpu().contiguous()
+        assert list(pv.shape) == e["shape"] and out["image_grid_thw"][0].tolist() == e["grid"], e["name"]
+        assert torch.equal(pv[5:9], e["rows"]), e["name"]
+        assert hashlib.sha1(pv.numpy().tobytes()).hexdigest() == e["sha1"], e["name"]
+    b = fx["batch"]
+    out = proc.preprocess([synth_image(n, *QWEN_CASES[n]) for n in b["names"]], return_tensors="pt")
+    assert list(out["pixel_values"].shape) == b["shape"] and out["image_grid_thw"].tolist() == b["grid"]
+    assert hashlib.sha1(out["pixel_values"].cpu().contiguous().numpy().tobytes()).hexdigest() == b["sha1"]
+
+
+def test_qwen_eval_loops_from_uint8_images(tmp_path_factory):
+    """the pairwise / single-image loops of eval/batch_inference_rm_qwen.py on uint8 images preprocessed on the GPU by
+    the processor wrapper; rewards agree with the oracle preprocessing + oracle forward in fp32"""
+    from preprocess_util import synth_image
+    from test_qwen_processor_cpu import FakeTok
+    from llava_reward_b200.batch_eval import score_pairs, score_single
+    from llava_reward_b200.processing import Qwen2_5_VLProcessorB200, Qwen2VLImageProcessorB200
+    from oracle import qwen_preprocess_oracle as PO
+    fx = load_fixture("qwen_slim_bt")
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    # a small pixel budget keeps the test fast; same code path as the reference's 256..1280 token budget
+    proc = Qwen2_5_VLProcessorB200(Qwen2VLImageProcessorB200(min_pixels=16 * 28 * 28, max_pixels=96 * 28 * 28), FakeTok())
+    imgs_c = [synth_image("qc0", 300, 420), synth_image("qc1", 500, 260)]
+    imgs_r = [synth_image("qr0", 333, 200), synth_image("qr1", 64, 48)]
+    text = "<|vision_start|><|image_pad|><|vision_end|>a photo"
+    bc = proc(text=[text, text], images=imgs_c, padding=True, return_tensors="pt").to(DEV)
+    br = proc(text=[text, text + " of a dog"], images=imgs_r, padding=True, return_tensors="pt").to(DEV)
+    res = score_pairs(model, args, [(bc, br)])
+    assert res["probs"].shape == (2,) and len(res["chosen_rewards"]) == 2
+    single = score_single(model, args, [(bc, torch.tensor([1, 0]))], cls_based=True)
+    assert len(single["rewards"]) == 2 and 0.0 <= single["accuracy"] <= 1.0
+    # oracle: numpy preprocessing (bit-identical pixels) + fp32 forward
+    pix = np.concatenate([PO.preprocess(im, min_pixels=16 * 28 * 28, max_pixels=96 * 28 * 28)[0] for im in imgs_c], 0)
+    assert torch.equal(torch.from_numpy(pix), bc["pixel_values"].cpu())
+    P32 = Params(SynthProvider(cfg, seed=fx["seed_w"], device=DEV), dtype=torch.float32, device=DEV)
+    with torch.no_grad():
+        r32 = O.custom_forward(P32, cfg, dict(bc)).flatten().cpu()
+    err = (torch.tensor(res["chosen_rewards"]) - r32).abs().max().item()
+    print(f"eval loop: engine {res['chosen_rewards']} oracle fp32 {r32.tolist()} err {err:.4g}")
+    assert err < 2e-2
