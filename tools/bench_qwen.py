@@ -144,6 +144,45 @@ def main():
     step(True)
     ms_e2e = timed(True, a.steps)
 
+    # third arm: uint8 1024x1024 images in pinned host memory -> GPU preprocessing (smart_resize -> 980x980) -> scoring
+    from llava_reward_b200.processing import Qwen2VLImageProcessorB200
+    from llava_reward_b200.synth import hash_randint
+    proc = Qwen2VLImageProcessorB200(device=dev)
+    ORIG = (1024, 1024)
+    assert proc.grid(ORIG) == GRID
+    u8 = [hash_randint(f"img.{rank}.{i}", ORIG[0] * ORIG[1] * 3, 0, 256, 7).to(torch.uint8)
+          .view(ORIG[0], ORIG[1], 3).pin_memory() for i in range(B)]
+    pix_slot = torch.empty_like(resident["pixel_values"])
+
+    def step_u8():
+        ib = {k: host[k].to(dev, non_blocking=True) for k in ("input_ids", "attention_mask")}
+        pp = proc.preprocess(u8, return_tensors="pt", out=pix_slot)
+        ib["pixel_values"], ib["image_grid_thw"] = pp["pixel_values"], pp["image_grid_thw"]
+        r, _ = model.custom_forward(inputs_batch=ib)
+        rc, rr = r[0::2].contiguous(), r[1::2].contiguous()
+        res = torch.cat([rc.float(), rr.float(), eng.preference(rc, rr)[:, None]], dim=1)
+        if world > 1:
+            dist.all_gather_into_tensor(gather, res)
+            res = gather
+        return res.cpu()
+
+    step_u8()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step_u8()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_u8 = ms_t.item()
+    h2d_u8 = B * ORIG[0] * ORIG[1] * 3 + sum(host[k].numel() * host[k].element_size()
+                                             for k in ("input_ids", "attention_mask"))
+
     if rank == 0:
         peaks = load_peaks()
         n = P * world * a.steps
@@ -169,6 +208,11 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4 * out_w * P * world},
+            "e2e_uint8": {"value": n / (ms_u8 / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": h2d_u8,
+                          "d2h_bytes_per_step": 4 * out_w * P * world,
+                          "note": "uint8 1024x1024 images from pinned host memory, Qwen2-VL preprocessing on the GPU "
+                                  "(smart_resize to 980x980, lr_resample_u8 bicubic + lr_qwen_patchify_f32), then the "
+                                  "same scoring step"},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "pair::gemm_pair_kernel<256,SWIGLU> (decoder gate|up + 2 LoRA-B blocks)",
                          "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",

@@ -8,6 +8,6 @@ python - <<'PY'
 import json
 try:
     d=json.loads(open('gpurun_out/bench_qwen.log').read().strip().splitlines()[-1])
-    print({k:d[k] for k in ('value','ms_per_step','gpu_launches','clocks')}, 'e2e', d['e2e']['value'], 'gate_up', d['roofline']['achieved'], d['step_roofline'])
+    print({k:d[k] for k in ('value','ms_per_step','gpu_launches','clocks')}, 'e2e', d['e2e']['value'], 'u8', d.get('e2e_uint8',{}).get('value'), 'gate_up', d['roofline']['achieved'], d['step_roofline'])
 except Exception as e: print("parse fail", e)
 PY
