@@ -290,6 +290,12 @@ int lr_mrope_plan(const int64_t* input_ids, const int64_t* attention_mask, int B
 int lr_compact_rows_bf16(const void* src, int lds, const int* ord, const int* plan, void* dst, int ldd, int B, int S,
                          int cols, void* stream);
 
+/* dst[i, :] = src[row_index[i], :] (bf16 rows, cols % 8 == 0). Used to continue the LAST decoder layer on the
+ * last-valid-token rows only - the only rows of hidden_states[-1] the reference's eval-mode head reads
+ * (rw_model_general_preference.py:420-421, 439-444): o_proj / MLP of that layer run on B rows instead of B*S. */
+int lr_gather_rows_bf16(const void* src, int lds, const int* row_index, void* dst, int ldd, int rows, int cols,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,7 @@ SIGNATURES = {
     "lr_patch_rows_bf16": ([p, p, p, i32, i32, i32, i32, p], i32),
     "lr_qwen_patchify_f32": ([p, i32, i32, i32, i32, p, p, p], i32),
     "lr_mrope_plan": ([p, p, i32, i32, i64, p, i32, i32, p, p, p, i32, i32, i32, i32, p, p, p, p, p], i32),
+    "lr_gather_rows_bf16": ([p, i32, p, p, i32, i32, i32, p], i32),
     "lr_compact_rows_bf16": ([p, i32, p, p, p, i32, i32, i32, i32, p], i32),
 }
 

@@ -138,6 +138,17 @@ compact_rows_kernel(const bf16* __restrict__ src, int lds, const int* __restrict
   for (int c = lane * 8; c < cols; c += 256) stg128(d + c, ldg128(s + c));
 }
 
+// dst[i, :] = src[row_index[i], :]. One warp per row.
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const bf16* __restrict__ src, int lds, const int* __restrict__ row_index, bf16* __restrict__ dst,
+                   int ldd, int rows, int cols) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const bf16* s = src + size_t(row_index[warp]) * lds;
+  bf16* d = dst + size_t(warp) * ldd;
+  for (int c = lane * 8; c < cols; c += 256) stg128(d + c, ldg128(s + c));
+}
+
 }  // namespace lr
 
 using namespace lr;
@@ -183,5 +194,15 @@ extern "C" int lr_compact_rows_bf16(const void* src, int lds, const int* ord, co
   const long long warps = (long long)B * S;
   compact_rows_kernel<<<unsigned((warps + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(src), lds, ord, plan, reinterpret_cast<bf16*>(dst), ldd, B, S, cols);
+  return lr_launch_status();
+}
+
+
+extern "C" int lr_gather_rows_bf16(const void* src, int lds, const int* row_index, void* dst, int ldd, int rows,
+                                   int cols, void* stream) {
+  LR_CHECK_ARG(src && row_index && dst && rows > 0 && cols > 0 && cols % 8 == 0 && lds >= cols && ldd >= cols);
+  if (!q_aligned16(src) || !q_aligned16(dst) || (lds % 8) || (ldd % 8)) return LR_ERR_ALIGN;
+  gather_rows_kernel<<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(src), lds, row_index, reinterpret_cast<bf16*>(dst), ldd, rows, cols);
   return lr_launch_status();
 }

@@ -30,6 +30,10 @@ class RewardEngine:
         self.launches = 0        # C-ABI calls issued by the last forward (= kernel launches, see _lib.launch_count)
         self.taps: Optional[dict] = None  # set to {} to capture intermediates (tests)
         self.profile: Optional[dict] = None  # {"gate_up": []} -> CUDA-event pairs around that GEMM (bench roofline)
+        # Output-identical shortcut: after the attention of the LAST decoder layer only the
+        # last-valid-token row of every sample is read by the head, so o_proj / post-norm / MLP of that layer run on
+        # those B rows. Off while intermediates are being captured (taps) so tests can compare both forms.
+        self.last_layer_rows = True
 
     # ------------------------------------------------------------------ helpers
     def buf(self, name: str, shape, dtype=torch.bfloat16) -> torch.Tensor:
@@ -98,10 +102,12 @@ class RewardEngine:
         self._tap("clip_out", x)
         return x
 
-    def _decoder(self, hid, B: int, S: int, pos, seq_start, seq_len, cos_tab, sin_tab) -> None:
+    def _decoder(self, hid, B: int, S: int, pos, seq_start, seq_len, cos_tab, sin_tab, eos_row=None):
         """Pre-norm decoder layers in place on hid [B*S, H] (Phi3DecoderLayer, modeling_phi3_v.py:1130-1205; the
         Llama layers of the LLaVA-v1.6 branch have the same dataflow). LoRA ranks come from the packed weights:
-        the K-extension of a fused projection is the stack of its branches' ranks (weights.py)."""
+        the K-extension of a fused projection is the stack of its branches' ranks (weights.py).
+        Returns None (the output is hid) or, with `eos_row` and the last-layer shortcut, the [B, H] output rows of the
+        last layer at those row indices (hid then holds the INPUT of the last layer)."""
         cfg, w = self.cfg, self.w
         M, H, I = B * S, cfg.hidden_size, cfg.intermediate_size
         lw0 = w.layers[0] if w.layers else {}
@@ -132,6 +138,25 @@ class RewardEngine:
             else:
                 ops.attention(dqkv, dqkv[:, H:], dqkv[:, 2 * H:], dao, 3 * H, H + ro, B, S, seq_start, seq_len, nh, hd,
                               True, att_scale, self.attn_impl)
+            if eos_row is not None and self.last_layer_rows and self.taps is None and li == len(w.layers) - 1:
+                # last layer: everything after the attention on the B last-valid-token rows only
+                dao_e = self.buf("dec_ao_e", (B, H + ro))
+                hid_e = self.buf("dec_hid_e", (B, H))
+                ops.gather_rows(dao, eos_row, dao_e, B, H)
+                ops.gather_rows(hid, eos_row, hid_e, B, H)
+                if ro:
+                    self._gemm(dao_e, lw["o_a"], dao_e[:, H:], B, ro, H)
+                self._gemm(dao_e, lw["o_w"], hid_e, B, H, H + ro, L.EPI_RESIDUAL, None, hid_e)
+                xn_e = self.buf("dec_xn_e", (B, H + rg))
+                ops.rmsnorm(hid_e, lw["post_ln"], xn_e, B, H, cfg.rms_eps)
+                if rg:
+                    self._gemm(xn_e, lw["gu_a"], xn_e[:, H:], B, rg, H)
+                gg_e = self.buf("dec_g_e", (B, I + rd))
+                self._gemm(xn_e, lw["gu_w"], gg_e, B, 2 * I, H + rg, L.EPI_SWIGLU)
+                if rd:
+                    self._gemm(gg_e, lw["dn_a"], gg_e[:, I:], B, rd, I)
+                self._gemm(gg_e, lw["dn_w"], hid_e, B, H, I + rd, L.EPI_RESIDUAL, None, hid_e)
+                return hid_e
             if ro:
                 self._gemm(dao, lw["o_a"], dao[:, H:], M, ro, H)
             self._gemm(dao, lw["o_w"], hid, M, H, H + ro, L.EPI_RESIDUAL, None, hid)
@@ -150,6 +175,18 @@ class RewardEngine:
             self._gemm(gg, lw["dn_w"], hid, M, H, I + rd, L.EPI_RESIDUAL, None, hid)
             if self.taps is not None:
                 self._tap(f"hidden_{li}", hid)
+        return None
+
+    def _final_rows(self, hid, hid_e, eos_row, B: int) -> torch.Tensor:
+        """final RMSNorm of the last-valid-token rows -> x_eos [B, H]"""
+        cfg, w = self.cfg, self.w
+        xe = self.buf("x_eos", (max(B, 1), cfg.hidden_size))
+        if hid_e is not None:
+            ops.rmsnorm(hid_e, w.head["norm"], xe, B, cfg.hidden_size, cfg.rms_eps)
+        else:
+            ops.rmsnorm(hid, w.head["norm"], xe, B, cfg.hidden_size, cfg.rms_eps, row_index=eos_row)
+        self._tap("last_hidden_eos", xe)
+        return xe
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
@@ -225,12 +262,10 @@ class RewardEngine:
 
         # 5. decoder
         cos_tab, sin_tab = self.rope_tables(max(S, 2), max_len > cfg.original_max_position_embeddings)
-        self._decoder(hid, B, S, pos, seq_start, seq_len, cos_tab, sin_tab)
+        hid_e = self._decoder(hid, B, S, pos, seq_start, seq_len, cos_tab, sin_tab, eos_row)
 
         # 6. reward head on the last valid token of each sample
-        xe = self.buf("x_eos", (max(B, 1), H))
-        ops.rmsnorm(hid, w.head["norm"], xe, B, H, cfg.rms_eps, row_index=eos_row)
-        self._tap("last_hidden_eos", xe)
+        xe = self._final_rows(hid, hid_e, eos_row, B)
         vhd = cfg.vhd
         reward = torch.empty(B, vhd, dtype=bf, device=dev)
         if cfg.add_cross_attention:
@@ -348,12 +383,10 @@ class LlavaNextRewardEngine(RewardEngine):
 
         # 5. decoder
         cos_tab, sin_tab = self.rope_tables(max(S, 2))
-        self._decoder(hid, B, S, pos, seq_start, seq_len, cos_tab, sin_tab)
+        hid_e = self._decoder(hid, B, S, pos, seq_start, seq_len, cos_tab, sin_tab, eos_row)
 
         # 6. final norm on the last valid row + value head
-        xe = self.buf("x_eos", (max(B, 1), H))
-        ops.rmsnorm(hid, w.head["norm"], xe, B, H, cfg.rms_eps, row_index=eos_row)
-        self._tap("last_hidden_eos", xe)
+        xe = self._final_rows(hid, hid_e, eos_row, B)
         reward = torch.empty(B, cfg.vhd, dtype=torch.bfloat16, device=dev)
         ops.skipca_head(None, None, None, xe, None, w.head["vh"], reward, B, H, 0, cfg.vhd, cfg.rms_eps)
         self.launches = L.launch_count() - launches0
@@ -569,12 +602,10 @@ class QwenVLRewardEngine(RewardEngine):
             ops.compact_rows(hid, pad_ord, pad_plan, kv_src, B, S, H)
 
         # 4. decoder (per-token M-RoPE rows: position_ids = None)
-        self._decoder(hid, B, S, None, seq_start, seq_len, cos_tok, sin_tok)
+        hid_e = self._decoder(hid, B, S, None, seq_start, seq_len, cos_tok, sin_tok, eos_row)
 
         # 5. final norm on the last valid row, SkipCA (qwen arm), value head
-        xe = self.buf("x_eos", (max(B, 1), H))
-        ops.rmsnorm(hid, w.head["norm"], xe, B, H, cfg.rms_eps, row_index=eos_row)
-        self._tap("last_hidden_eos", xe)
+        xe = self._final_rows(hid, hid_e, eos_row, B)
         vhd = cfg.vhd
         reward = torch.empty(B, vhd, dtype=torch.bfloat16, device=dev)
         if ca and sum_pad > 0:

@@ -164,3 +164,9 @@ def compact_rows(src, ord_, plan, dst, B, S, cols):
     _need_cuda(src, ord_, plan, dst)
     L.call("lr_compact_rows_bf16", _ptr(src), src.stride(0), _ptr(ord_), _ptr(plan), _ptr(dst), dst.stride(0), B, S,
            cols, _stream())
+
+
+def gather_rows(src, row_index, dst, rows, cols):
+    _need_cuda(src, row_index, dst)
+    L.call("lr_gather_rows_bf16", _ptr(src), src.stride(0), _ptr(row_index), _ptr(dst), dst.stride(0), rows, cols,
+           _stream())

@@ -384,3 +384,25 @@ def test_batch_eval_loops(tmp_path_factory):
     gargs, gmodel, _ = build_model(gfx, tmp_path_factory)
     with pytest.raises(ValueError):
         score_single(gmodel, gargs, [])
+
+
+@pytest.mark.parametrize("case", ["slim_gpm", "slim_bt"])
+def test_last_layer_row_shortcut_is_output_identical(case, tmp_path_factory):
+    """o_proj / MLP of the LAST decoder layer on the last-valid-token rows only (engine.last_layer_rows, the product
+    default) against the same layer run on every row: the value the head consumes must not change."""
+    fx = load_fixture(case)
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    ids, mask, pix, sizes = fixture_batch(fx, fx["batches"][0], cfg, device="cuda")
+    eng = model.engine
+    assert eng.last_layer_rows
+    r_short, _ = model.custom_forward(ids, mask, pix, sizes)
+    n_short = eng.launches
+    eng.last_layer_rows = False
+    try:
+        r_full, _ = model.custom_forward(ids, mask, pix, sizes)
+    finally:
+        eng.last_layer_rows = True
+    d = (r_short.float() - r_full.float()).abs().max().item()
+    print(f"{case}: shortcut {r_short.flatten().tolist()} full {r_full.flatten().tolist()} |d| {d:.3g}; "
+          f"launches {n_short} vs {eng.launches}")
+    assert d <= 4e-3   # same arithmetic per row; only the GEMM tile shape (small-M kernel) may differ in fp32 summation

@@ -467,6 +467,21 @@ def test_qwen_window_attention_layouts_agree(tmp_path_factory):
     assert (r_seg.float() - r_pk.float()).abs().max().item() < 1e-2
 
 
+def test_qwen_last_layer_row_shortcut(tmp_path_factory):
+    fx = load_fixture("qwen_slim_gpm")
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    batch = to_dev(qwen_fixture_batch(fx, fx["batches"][0], cfg))
+    r_short, _ = model.custom_forward(inputs_batch=batch)
+    model.engine.last_layer_rows = False
+    try:
+        r_full, _ = model.custom_forward(inputs_batch=batch)
+    finally:
+        model.engine.last_layer_rows = True
+    d = (r_short.float() - r_full.float()).abs().max().item()
+    print(f"last-layer rows: shortcut {r_short.flatten().tolist()} full {r_full.flatten().tolist()} |d| {d:.3g}")
+    assert d <= 4e-3
+
+
 def test_qwen_validation_errors(tmp_path_factory):
     fx = load_fixture("qwen_slim_bt")
     args, model, cfg = build_model(fx, tmp_path_factory)
