@@ -9,6 +9,8 @@
 // remotely by the peer's epilogue warps.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -445,6 +447,10 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, void* C, 
   // L2-resident while the group sweeps all n-tiles; W is then streamed from HBM once per group.
   int group_m = int((32ll << 20) / (int64_t(2 * kBM) * K * 2));
   group_m = group_m < 4 ? 4 : (group_m > 32 ? 32 : group_m);
+  if (const char* e = getenv("LR_GEMM_GROUP_M")) {  // raster experiments (tools/gemm_raster_bench.py)
+    const int g = atoi(e);
+    if (g > 0) group_m = g;
+  }
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, M, N, K, reinterpret_cast<const bf16*>(bias),
                                                         reinterpret_cast<const bf16*>(R), ldr, group_m, pos, rope_hd,
                                                         reinterpret_cast<const bf16*>(lin_bias));
