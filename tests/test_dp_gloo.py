@@ -30,7 +30,8 @@ def _worker(rank, world, port, n_pairs, micro, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         out = score_pairs_dp(_fake_score, n_pairs, micro, rank, world)
-        q.put((rank, [t.clone() for t in out]))
+        # plain lists: a tensor in an mp.Queue is shared through an fd served by the producer, which may have exited
+        q.put((rank, [t.tolist() for t in out]))
     finally:
         dist.destroy_process_group()
 
@@ -50,7 +51,7 @@ def test_dp_matches_single_process(world, n_pairs, micro):
     ref = _fake_score(range(n_pairs))
     for rank, out in results:
         for a, b in zip(out, ref):
-            assert torch.allclose(a, b), (rank, a, b)
+            assert torch.allclose(torch.tensor(a), b), (rank, a, b)
 
 
 def test_shard_indices_cover_everything_once():

@@ -107,7 +107,7 @@ def test_llava_checkpoint_name_mapping_and_loader_errors(tmp_path):
     with pytest.raises(RuntimeError):
         model.to("cpu")                                # no CPU fallback
     with pytest.raises(NotImplementedError):
-        load_reward_adaptor(args, "qwen", str(y))
+        load_reward_adaptor(args, "internvl", str(y))   # the reference knows phi3v / qwen / llava only
     args.pretrain = str(tmp_path / "missing")
     with pytest.raises(FileNotFoundError):
         load_reward_adaptor(args, "llava", str(y))
