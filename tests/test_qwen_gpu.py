@@ -482,6 +482,44 @@ def test_qwen_last_layer_row_shortcut(tmp_path_factory):
     assert d <= 4e-3
 
 
+def test_qwen_two_images_in_one_sample(tmp_path_factory):
+    """a sample with TWO images (two <|vision_start|> ... <|vision_end|> runs): M-RoPE restarts the grid positions at
+    the running offset, image rows are scattered in order - engine vs the oracle (positions bit-exact, rewards within the
+    bf16 noise). The reference's datasets put one image per sample; the path itself is general."""
+    from llava_reward_b200.synth import hash_normal, hash_randint
+    fx = load_fixture("qwen_slim_bt")
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    grids = [(8, 12), (14, 6), (10, 10)]                      # sample 0: images 0 and 1; sample 1: image 2
+    pix = torch.cat([hash_normal(f"mi.{i}", (h * w, cfg.patch_dim), 1.0, 3) for i, (h, w) in enumerate(grids)], 0)
+
+    def img(i):
+        h, w = grids[i]
+        return [cfg.vision_start_token_id] + [cfg.image_token_id] * (h * w // 4) + [cfg.vision_end_token_id]
+
+    def txt(tag, n):
+        return hash_randint(tag, n, 3, 151000, 3).tolist()
+
+    rows = [[151644, 872, 198] + img(0) + txt("a", 9) + img(1) + txt("b", 17) + [151645],
+            [151644, 872, 198] + img(2) + txt("c", 30) + [151645]]
+    S = max(len(r) for r in rows)
+    ids = torch.tensor([[cfg.pad_token_id] * (S - len(r)) + r for r in rows])
+    mask = torch.tensor([[0] * (S - len(r)) + [1] * len(r) for r in rows])
+    batch = to_dev({"input_ids": ids, "attention_mask": mask, "pixel_values": pix,
+                    "image_grid_thw": torch.tensor([[1, h, w] for h, w in grids])})
+    model.engine.taps = {}
+    r, _ = model.custom_forward(inputs_batch=batch)
+    te, model.engine.taps = model.engine.taps, None
+    ref_pos = O.rope_index(cfg, ids, mask, batch["image_grid_thw"].tolist())
+    assert torch.equal(te["pos3"].view(3, 2, S).cpu().long(), ref_pos)
+    P16 = Params(SynthProvider(cfg, seed=fx["seed_w"], device=DEV), dtype=bf, device=DEV)
+    P32 = Params(SynthProvider(cfg, seed=fx["seed_w"], device=DEV), dtype=torch.float32, device=DEV)
+    with torch.no_grad():
+        o16, o32 = O.custom_forward(P16, cfg, batch).float(), O.custom_forward(P32, cfg, batch).float()
+    floor, err = (o16 - o32).abs().max().item(), (r.float() - o32).abs().max().item()
+    print(f"two images: engine {r.flatten().tolist()} fp32 {o32.flatten().tolist()} err {err:.4g} floor {floor:.4g}")
+    assert err < REWARD_TOL + 3 * floor
+
+
 def test_qwen_validation_errors(tmp_path_factory):
     fx = load_fixture("qwen_slim_bt")
     args, model, cfg = build_model(fx, tmp_path_factory)

@@ -12,7 +12,6 @@ try:
 except Exception as e: print("parse fail", e)
 PY
 tail -3 gpurun_out/bench.err
-K='regex:^(gemm_|attn_|rmsnorm|layernorm|clip_|token_plan|rope_su|hd_gather|embed_scatter|skipca|preference)'
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -s 1055 -c 1055 --csv --log-file gpurun_out/launches.csv python bench.py --profile-run > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_pair -s 97 -c 1 -o gpurun_out/prof_gate_up_pair -f python bench.py --profile-run > gpurun_out/ncu_gemm.log 2>&1; echo "ncu gate_up exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_tc -s 30 -c 1 -o gpurun_out/prof_attn_dec -f python bench.py --profile-run > gpurun_out/ncu_attn.log 2>&1; echo "ncu attn exit $?"
+K='regex:^(gemm_|attn_|rmsnorm|layernorm|clip_|token_plan|rope_su|hd_gather|embed_scatter|skipca|preference|gather_rows)'
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -s 1057 -c 1057 --csv --log-file gpurun_out/launches.csv python bench.py --profile-run > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches exit $?"
+python tools/launch_summary.py gpurun_out/launches.csv gpurun_out/launches.md | head -30
