@@ -58,6 +58,33 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes,
 }
 constexpr uint32_t kLayoutSW128 = 2, kLayoutSW64 = 4;
 
+// Softmax exponentials: LR_ATTN_POLY_NUM of every 4 elements of a row are computed on the FMA pipe instead of the
+// MUFU (16 ex2/clk/SM is the scarcest pipe of this kernel): Cody-Waite split 2^x = 2^floor(x) * 2^frac with a
+// round-down add against 1.5 * 2^23 (floor(x) lands in the low mantissa bits), a degree-3 minimax polynomial for
+// 2^frac on [0, 1) (max relative error 9e-5, well under the bf16 rounding of P) and an integer add into the
+// exponent field. Inputs are clamped to -127, so masked (-inf) entries become ~2^-127 instead of 0; rows that are
+// masked completely are zero-filled by the epilogue either way.
+#ifndef LR_ATTN_POLY_NUM
+#define LR_ATTN_POLY_NUM 0
+#endif
+// Release the S buffer as soon as the row is in registers (before mask + max) when one thread owns the whole row.
+#ifndef LR_ATTN_EARLY_SFREE
+#define LR_ATTN_EARLY_SFREE 0
+#endif
+__device__ __forceinline__ float exp2_fma_pipe(float x) {
+  x = fmaxf(x, -127.f);
+  float r;
+  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(12582912.f));
+  const float f = x - (r - 12582912.f);
+  float p = fmaf(f, 0.077119089663028717f, 0.227564394474029541f);
+  p = fmaf(p, f, 0.695146143436431885f);
+  p = fmaf(p, f, 1.f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+__device__ __forceinline__ float softmax_exp2(float x, int idx) {  // idx is a constant after unrolling
+  return ((idx & 3) < LR_ATTN_POLY_NUM) ? exp2_fma_pipe(x) : exp2f(x);
+}
+
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -357,6 +384,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
 #pragma unroll
       for (int c = 0; c < NCH; ++c) tmem_ld_32x32(tm_S[x] + lane_addr + (h * NCH + c) * 32, sv[c]);
       tmem_ld_wait();
+      if constexpr (SPLIT == 1 && LR_ATTN_EARLY_SFREE) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[x]);
+      }
       if (tr) ATTN_TRACE(1 + x, 2, j);
       if (need_mask) {
 #pragma unroll
@@ -385,9 +417,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         asm volatile("bar.sync %0, 256;" ::"r"(1 + x) : "memory");
         mx = fmaxf(mx, mb[(h ^ 1) * 128 + r]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[x]);
+      if constexpr (!(SPLIT == 1 && LR_ATTN_EARLY_SFREE)) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[x]);
+      }
       mx *= scale_log2;  // scale > 0, so max commutes with the scaling
       // lazy rescale: move the reference max only when it grew by more than the threshold
       float alpha = 1.f;
@@ -430,8 +464,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = exp2f(fmaf(__uint_as_float(sv[c][2 * i]), scale_log2, -msafe));
-          const float p1 = exp2f(fmaf(__uint_as_float(sv[c][2 * i + 1]), scale_log2, -msafe));
+          const float p0 = softmax_exp2(fmaf(__uint_as_float(sv[c][2 * i]), scale_log2, -msafe), 2 * i);
+          const float p1 = softmax_exp2(fmaf(__uint_as_float(sv[c][2 * i + 1]), scale_log2, -msafe), 2 * i + 1);
           if constexpr (!ONES) {
             l_reg[(2 * i) & 3] += p0;
             l_reg[(2 * i + 1) & 3] += p1;

@@ -20,6 +20,9 @@ def build():
     subprocess.run(cmd, check=True)
 
 
+IMPL = int(sys.argv[sys.argv.index("--impl") + 1]) if "--impl" in sys.argv else 3  # 3 = two tiles per CTA, 4 = one
+
+
 def main():
     if not os.path.exists(OUT) or "--build" in sys.argv:
         build()
@@ -38,7 +41,7 @@ def main():
         assert lib.lr_attn_trace_set(trace.data_ptr()) == 0
         for _ in range(2):
             st = lib.lr_attention_bf16(qkv.data_ptr(), qkv[:, D:].data_ptr(), qkv[:, 2 * D:].data_ptr(), o.data_ptr(), 3 * D,
-                                       D, nseq, T, None, None, heads, hd, int(causal), hd ** -0.5, 3,
+                                       D, nseq, T, None, None, heads, hd, int(causal), hd ** -0.5, IMPL,
                                        torch.cuda.current_stream().cuda_stream)
             assert st == 0, st
         torch.cuda.synchronize()
