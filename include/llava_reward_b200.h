@@ -290,11 +290,26 @@ int lr_mrope_plan(const int64_t* input_ids, const int64_t* attention_mask, int B
 int lr_compact_rows_bf16(const void* src, int lds, const int* ord, const int* plan, void* dst, int ldd, int B, int S,
                          int cols, void* stream);
 
-/* dst[i, :] = src[row_index[i], :] (bf16 rows, cols % 8 == 0). Used to continue the LAST decoder layer on the
+/* dst[i, :] = src[row_index[i], :], zeros where row_index[i] < 0 (bf16 rows, cols % 8 == 0). Used to continue the LAST decoder layer on the
  * last-valid-token rows only - the only rows of hidden_states[-1] the reference's eval-mode head reads
  * (rw_model_general_preference.py:420-421, 439-444): o_proj / MLP of that layer run on B rows instead of B*S. */
 int lr_gather_rows_bf16(const void* src, int lds, const int* row_index, void* dst, int ldd, int rows, int cols,
                         void* stream);
+
+/* ---- all-rows head: `mean_hidden_state` pooling (rw_model_general_preference.py:398-406) ---------------------------
+ * With that attribute set the reference pools EVERY row of the (SkipCA'd) last hidden state, so the S x N_v cross
+ * attention of :376-386 is needed for all rows: Q K^T and P V run as lr_gemm_bf16 per sample on the zero-padded
+ * vision rows (lr_gather_rows_bf16 with -1 indices builds the reference's zero padding), and these two entries are the
+ * pieces between the GEMMs.
+ *
+ * In place on bf16 scores [rows, lds]: p_j = bf16(softmax_j(bf16(s_j * inv_sqrt_d))) over columns j < n_valid,
+ * 0 for n_valid <= j < n_total (n_total % 8 == 0). Replaces `scores / sqrt(d_k)` + F.softmax (:381-383). */
+int lr_softmax_rows_bf16(void* scores, int lds, int rows, int n_valid, int n_total, float inv_sqrt_d, void* stream);
+
+/* out[b,:] = bf16(bf16(sum_s x[b*S+s,:] * mask[b,s]) / bf16(sum_s mask[b,s])) (H % 256 == 0). Replaces the masked mean
+ * of :398-406 (each torch op rounds to bf16 once; mask.sum() is itself a bf16 tensor). */
+int lr_masked_mean_rows_bf16(const void* x, int ldx, const int64_t* attention_mask, void* out, int ldo, int B, int S,
+                             int H, void* stream);
 
 #ifdef __cplusplus
 }

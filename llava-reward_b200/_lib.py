@@ -55,6 +55,8 @@ SIGNATURES = {
     "lr_mrope_plan": ([p, p, i32, i32, i64, p, i32, i32, p, p, p, i32, i32, i32, i32, p, p, p, p, p], i32),
     "lr_gather_rows_bf16": ([p, i32, p, p, i32, i32, i32, p], i32),
     "lr_compact_rows_bf16": ([p, i32, p, p, p, i32, i32, i32, i32, p], i32),
+    "lr_softmax_rows_bf16": ([p, i32, i32, i32, i32, f32, p], i32),
+    "lr_masked_mean_rows_bf16": ([p, i32, p, p, i32, i32, i32, i32, p], i32),
 }
 
 

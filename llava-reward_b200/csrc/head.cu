@@ -153,6 +153,88 @@ __global__ void preference_kernel(const bf16* __restrict__ c, const bf16* __rest
   prob[i] = bf16_round(1.f / (1.f + expf(-z)));
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// All-rows form of the head (mean_hidden_state pooling, rw_model_general_preference.py:376-386 + 398-406): the S x N_v
+// score matrix of every sample comes out of the GEMM kernel in bf16 (torch.bmm output); this kernel turns it into the
+// bf16 softmax in place. One warp per row: v_j = bf16(s_j / sqrt(d_k)) for j < n_valid (the batch-wide vision length
+// incl. the reference's zero-padded rows, whose scores are exact zeros), p_j = bf16(exp(v_j - max) / sum);
+// columns n_valid <= j < n_total (alignment padding of the K dimension of the P.V GEMM) are set to 0.
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(bf16* __restrict__ s, int lds, int rows, int n_valid, int n_total, float inv_sqrt_d) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  bf16* r = s + size_t(row) * lds;
+  auto load8 = [&](int c, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(r + c);
+    const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+    const float t[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = (c + e < n_valid) ? bf16_round(t[e] * inv_sqrt_d) : -INFINITY;
+  };
+  float mx = -INFINITY;
+  for (int c = lane * 8; c < n_valid; c += 256) {
+    float v[8];
+    load8(c, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) mx = fmaxf(mx, v[e]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int c = lane * 8; c < n_valid; c += 256) {
+    float v[8];
+    load8(c, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sum += __expf(v[e] - mx);  // exp(-inf) = 0 for the columns beyond n_valid
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  for (int c = lane * 8; c < n_total; c += 256) {
+    float v[8];
+    load8(c, v);
+    uint32_t pk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      pk[e] = pack_bf16x2(__expf(v[2 * e] - mx) * inv, __expf(v[2 * e + 1] - mx) * inv);
+    *reinterpret_cast<uint4*>(r + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// out[b, :] = bf16( bf16(sum_s x[b,s,:] * mask[b,s]) / bf16(sum_s mask[b,s]) ), each torch op of the reference's pooling
+// rounded to bf16 once (fp32 accumulation inside the sums). grid (H/256, B), 8 warps split the rows of a sample.
+__global__ void __launch_bounds__(256)
+masked_mean_kernel(const bf16* __restrict__ x, int ldx, const int64_t* __restrict__ mask, bf16* __restrict__ out,
+                   int ldo, int S) {
+  __shared__ float part[8][256];
+  __shared__ int cnt[8];
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int n = 0;
+  for (int srow = warp; srow < S; srow += 8) {
+    if (mask[size_t(b) * S + srow] == 0) continue;
+    ++n;
+    const uint4 u = ldg128(x + (size_t(b) * S + srow) * ldx + c0);
+    const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+    acc[0] += f0.x, acc[1] += f0.y, acc[2] += f1.x, acc[3] += f1.y;
+    acc[4] += f2.x, acc[5] += f2.y, acc[6] += f3.x, acc[7] += f3.y;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) part[warp][lane * 8 + e] = acc[e];
+  if (lane == 0) cnt[warp] = n;
+  __syncthreads();
+  const int t = threadIdx.x;
+  float tot = 0.f;
+  int len = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    tot += part[w][t];
+    len += cnt[w];
+  }
+  const float lens = fmaxf(bf16_round(float(len)), 1e-8f);  // mask.sum(dim=1) is a bf16 tensor, then .clamp(min=1e-8)
+  out[size_t(b) * ldo + blockIdx.x * 256 + t] = __float2bfloat16_rn(bf16_round(tot) / lens);
+}
+
 }  // namespace lr
 
 using namespace lr;
@@ -195,5 +277,23 @@ extern "C" int lr_preference(const void* chosen, const void* reject, float* prob
   LR_CHECK_ARG(chosen && reject && prob && n > 0 && vhd > 0 && tau != 0.f);
   preference_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(chosen), reinterpret_cast<const bf16*>(reject), prob, n, vhd, is_gpm, tau);
+  return lr_launch_status();
+}
+
+extern "C" int lr_softmax_rows_bf16(void* scores, int lds, int rows, int n_valid, int n_total, float inv_sqrt_d,
+                                    void* stream) {
+  LR_CHECK_ARG(scores && rows > 0 && n_valid > 0 && n_total >= n_valid && n_total % 8 == 0 && lds >= n_total);
+  if ((lds % 8) || !aligned16(scores)) return LR_ERR_ALIGN;
+  softmax_rows_kernel<<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<bf16*>(scores), lds, rows, n_valid, n_total, inv_sqrt_d);
+  return lr_launch_status();
+}
+
+extern "C" int lr_masked_mean_rows_bf16(const void* x, int ldx, const int64_t* attention_mask, void* out, int ldo,
+                                        int B, int S, int H, void* stream) {
+  LR_CHECK_ARG(x && attention_mask && out && B > 0 && S > 0 && H > 0 && H % 256 == 0 && ldx >= H && ldo >= H);
+  if ((ldx % 8) || !aligned16(x)) return LR_ERR_ALIGN;
+  masked_mean_kernel<<<dim3(H / 256, B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(x), ldx, attention_mask, reinterpret_cast<bf16*>(out), ldo, S);
   return lr_launch_status();
 }

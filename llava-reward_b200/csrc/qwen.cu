@@ -138,15 +138,16 @@ compact_rows_kernel(const bf16* __restrict__ src, int lds, const int* __restrict
   for (int c = lane * 8; c < cols; c += 256) stg128(d + c, ldg128(s + c));
 }
 
-// dst[i, :] = src[row_index[i], :]. One warp per row.
+// dst[i, :] = src[row_index[i], :], or zeros where row_index[i] < 0. One warp per row.
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const bf16* __restrict__ src, int lds, const int* __restrict__ row_index, bf16* __restrict__ dst,
                    int ldd, int rows, int cols) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
-  const bf16* s = src + size_t(row_index[warp]) * lds;
+  const int ri = row_index[warp];
+  const bf16* s = src + size_t(ri < 0 ? 0 : ri) * lds;
   bf16* d = dst + size_t(warp) * ldd;
-  for (int c = lane * 8; c < cols; c += 256) stg128(d + c, ldg128(s + c));
+  for (int c = lane * 8; c < cols; c += 256) stg128(d + c, ri < 0 ? make_uint4(0, 0, 0, 0) : ldg128(s + c));
 }
 
 }  // namespace lr

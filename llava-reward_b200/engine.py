@@ -102,13 +102,15 @@ class RewardEngine:
         self._tap("clip_out", x)
         return x
 
-    def _decoder(self, hid, B: int, S: int, pos, seq_start, seq_len, cos_tab, sin_tab, eos_row=None):
+    def _decoder(self, hid, B: int, S: int, pos, seq_start, seq_len, cos_tab, sin_tab, eos_row=None, n_layers=None):
         """Pre-norm decoder layers in place on hid [B*S, H] (Phi3DecoderLayer, modeling_phi3_v.py:1130-1205; the
         Llama layers of the LLaVA-v1.6 branch have the same dataflow). LoRA ranks come from the packed weights:
         the K-extension of a fused projection is the stack of its branches' ranks (weights.py).
         Returns None (the output is hid) or, with `eos_row` and the last-layer shortcut, the [B, H] output rows of the
-        last layer at those row indices (hid then holds the INPUT of the last layer)."""
+        last layer at those row indices (hid then holds the INPUT of the last layer). `n_layers` stops after that many
+        layers (the reference's `layer_id` attribute: hidden_states[layer_id], rw_model_general_preference.py:349-352)."""
         cfg, w = self.cfg, self.w
+        layers = w.layers if n_layers is None else w.layers[:n_layers]
         M, H, I = B * S, cfg.hidden_size, cfg.intermediate_size
         lw0 = w.layers[0] if w.layers else {}
         rq, ro, rg, rd = (lw0[k].shape[0] if k in lw0 else 0 for k in ("qkv_a", "o_a", "gu_a", "dn_a"))
@@ -121,7 +123,7 @@ class RewardEngine:
         dao = self.buf("dec_ao", (M, H + ro))
         gg = self.buf("dec_g", (M, I + rd))
         att_scale = 1.0 / math.sqrt(cfg.head_dim)
-        for li, lw in enumerate(w.layers):
+        for li, lw in enumerate(layers):
             ops.rmsnorm(hid, lw["in_ln"], xn, M, H, cfg.rms_eps)
             if rq:
                 self._gemm(xn, lw["qkv_a"], xn[:, H:], M, rq, H)
@@ -138,7 +140,7 @@ class RewardEngine:
             else:
                 ops.attention(dqkv, dqkv[:, H:], dqkv[:, 2 * H:], dao, 3 * H, H + ro, B, S, seq_start, seq_len, nh, hd,
                               True, att_scale, self.attn_impl)
-            if eos_row is not None and self.last_layer_rows and self.taps is None and li == len(w.layers) - 1:
+            if eos_row is not None and self.last_layer_rows and self.taps is None and li == len(layers) - 1:
                 # last layer: everything after the attention on the B last-valid-token rows only
                 dao_e = self.buf("dec_ao_e", (B, H + ro))
                 hid_e = self.buf("dec_hid_e", (B, H))
@@ -177,10 +179,16 @@ class RewardEngine:
                 self._tap(f"hidden_{li}", hid)
         return None
 
-    def _final_rows(self, hid, hid_e, eos_row, B: int) -> torch.Tensor:
-        """final RMSNorm of the last-valid-token rows -> x_eos [B, H]"""
+    def _final_rows(self, hid, hid_e, eos_row, B: int, final_norm: bool = True) -> torch.Tensor:
+        """final RMSNorm of the last-valid-token rows -> x_eos [B, H] (`final_norm` False: the rows themselves, for
+        the un-normed hidden_states[layer_id] of the reference's `layer_id` attribute)"""
         cfg, w = self.cfg, self.w
         xe = self.buf("x_eos", (max(B, 1), cfg.hidden_size))
+        if not final_norm:
+            if hid_e is not None:
+                return hid_e
+            ops.gather_rows(hid, eos_row, xe, B, cfg.hidden_size)
+            return xe
         if hid_e is not None:
             ops.rmsnorm(hid_e, w.head["norm"], xe, B, cfg.hidden_size, cfg.rms_eps)
         else:
@@ -188,12 +196,85 @@ class RewardEngine:
         self._tap("last_hidden_eos", xe)
         return xe
 
+    def _resolve_layer_id(self, layer_id):
+        """-> (decoder layers to run, apply the final norm). The reference takes `last_hidden_state` for layer_id 32 and
+        otherwise indexes (inputs_embeds, h_1 .. h_{L-1}, norm(h_L), vision_embeds) (rw_model_general_preference.py
+        :349-352, modeling_phi3_v.py:1463-1505)."""
+        n = self.cfg.num_layers
+        if layer_id is None or layer_id == 32 or layer_id == n:
+            return n, True
+        if 0 <= layer_id < n:
+            return int(layer_id), False
+        raise ValueError(f"layer_id {layer_id}: expected 32 or 0..{n}")
+
+    def _head_rows(self, eos_row, B: int, S: int, last_position: bool):
+        """row index per sample the head reads: the last valid token (eval) or position S-1 (the reference's
+        `self.training` gather, values[:, -1], rw_model_general_preference.py:413-418, 432-436)"""
+        if not last_position:
+            return eos_row
+        key = ("last_rows", B, S)
+        if getattr(self, "_last_rows_key", None) != key:
+            self._last_rows = (torch.arange(B, dtype=torch.int32, device=self.device) * S + (S - 1)).contiguous()
+            self._last_rows_key = key
+        return self._last_rows
+
+    def _mean_head(self, hid, mask, B: int, S: int, final_norm: bool, img=None, plan_h=None, max_nv: int = 0,
+                   cross_attention=None):
+        """`mean_hidden_state` pooling (rw_model_general_preference.py:376-386 for ALL rows, then :398-406 and the value
+        head): final norm of every row, the S x N_v cross attention of every sample as GEMMs on the zero-padded
+        vision rows, residual + ca_layernorm, masked mean, value head."""
+        cfg, w = self.cfg, self.w
+        M, H = B * S, cfg.hidden_size
+        if final_norm:
+            xa = self.buf("x_all", (M, H))
+            ops.rmsnorm(hid, w.head["norm"], xa, M, H, cfg.rms_eps)
+        else:
+            xa = hid
+        self._tap("last_hidden_all", xa)
+        if cfg.add_cross_attention if cross_attention is None else cross_attention:
+            NVP = (max_nv + 255) // 256 * 256
+            idx_h = np.full((B, NVP), -1, dtype=np.int32)  # -1 = the reference's zero-padded vision rows
+            for b in range(B):
+                nv = int(plan_h[b, L.PLAN_NV])
+                idx_h[b, :nv] = int(plan_h[b, L.PLAN_ROW_BASE]) + np.arange(nv, dtype=np.int32)
+            idx = self.buf("ca_pad_idx", (B * NVP,), torch.int32)
+            idx.copy_(torch.from_numpy(idx_h.reshape(-1)))
+            vis = self.buf("ca_vis_pad", (B * NVP, H))
+            ops.gather_rows(img, idx, vis, B * NVP, H)
+            wk, wv = w.head["wkv"][:H], w.head["wkv"][H:]
+            kp = self.buf("ca_k_pad", (B * NVP, H))
+            self._gemm(vis, wk, kp, B * NVP, H, H)
+            q = self.buf("ca_q_all", (M, H))
+            self._gemm(xa, w.head["wq"], q, M, H, H)
+            sc = self.buf("ca_scores_all", (M, NVP))
+            vt = self.buf("ca_vt", (B * H, NVP))      # V^T per sample: the K-major operand of the P.V GEMM
+            y = self.buf("ca_y", (M, H))
+            for b in range(B):
+                self._gemm(q[b * S:(b + 1) * S], kp[b * NVP:(b + 1) * NVP], sc[b * S:(b + 1) * S], S, NVP, H)
+                self._gemm(wv, vis[b * NVP:(b + 1) * NVP], vt[b * H:(b + 1) * H], H, NVP, H)
+            ops.softmax_rows(sc, M, max_nv, NVP, 1.0 / math.sqrt(H))
+            for b in range(B):
+                self._gemm(sc[b * S:(b + 1) * S], vt[b * H:(b + 1) * H], y[b * S:(b + 1) * S], S, H, NVP,
+                           L.EPI_RESIDUAL, None, xa[b * S:(b + 1) * S])
+            y2 = self.buf("ca_y2", (M, H))
+            ops.rmsnorm(y, w.head["ca_ln"], y2, M, H, cfg.rms_eps)
+            xa = y2
+            self._tap("skipca_all", xa)
+        pooled = self.buf("pooled", (B, H))
+        ops.masked_mean_rows(xa, mask, pooled, B, S, H)
+        reward = torch.empty(B, cfg.vhd, dtype=torch.bfloat16, device=self.device)
+        ops.skipca_head(None, None, None, pooled, None, w.head["vh"], reward, B, H, 0, cfg.vhd, cfg.rms_eps)
+        return reward
+
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, pixel_values: torch.Tensor,
-                image_sizes) -> torch.Tensor:
+                image_sizes, layer_id=None, last_position: bool = False, mean_pool: bool = False) -> torch.Tensor:
+        """layer_id / last_position / mean_pool = the reference's `layer_id`, `training` and `mean_hidden_state`
+        attributes (rw_model_general_preference.py:327-333); the defaults are the eval-mode scoring path."""
         cfg, w, dev = self.cfg, self.w, self.device
         bf = torch.bfloat16
+        n_run, final_norm = self._resolve_layer_id(layer_id)
         launches0 = L.launch_count()
         B, S = input_ids.shape
         H = cfg.hidden_size
@@ -262,10 +343,16 @@ class RewardEngine:
 
         # 5. decoder
         cos_tab, sin_tab = self.rope_tables(max(S, 2), max_len > cfg.original_max_position_embeddings)
-        hid_e = self._decoder(hid, B, S, pos, seq_start, seq_len, cos_tab, sin_tab, eos_row)
+        head_row = self._head_rows(eos_row, B, S, last_position)
+        hid_e = self._decoder(hid, B, S, pos, seq_start, seq_len, cos_tab, sin_tab, None if mean_pool else head_row,
+                              n_layers=n_run)
+        if mean_pool:
+            reward = self._mean_head(hid, mask, B, S, final_norm, img, plan_h, max_nv)
+            self.launches = L.launch_count() - launches0
+            return reward
 
         # 6. reward head on the last valid token of each sample
-        xe = self._final_rows(hid, hid_e, eos_row, B)
+        xe = self._final_rows(hid, hid_e, head_row, B, final_norm)
         vhd = cfg.vhd
         reward = torch.empty(B, vhd, dtype=bf, device=dev)
         if cfg.add_cross_attention:
@@ -313,7 +400,7 @@ class LlavaNextRewardEngine(RewardEngine):
 
     @torch.no_grad()
     def forward(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, pixel_values: torch.Tensor,
-                image_sizes) -> torch.Tensor:
+                image_sizes, last_position: bool = False, mean_pool: bool = False) -> torch.Tensor:
         from .config import anyres_geometry
 
         cfg, w, dev = self.cfg, self.w, self.device
@@ -383,10 +470,15 @@ class LlavaNextRewardEngine(RewardEngine):
 
         # 5. decoder
         cos_tab, sin_tab = self.rope_tables(max(S, 2))
-        hid_e = self._decoder(hid, B, S, pos, seq_start, seq_len, cos_tab, sin_tab, eos_row)
+        head_row = self._head_rows(eos_row, B, S, last_position)
+        hid_e = self._decoder(hid, B, S, pos, seq_start, seq_len, cos_tab, sin_tab, None if mean_pool else head_row)
+        if mean_pool:   # the reference has no SkipCA arm for this backbone: final norm, masked mean, value head
+            reward = self._mean_head(hid, mask, B, S, True, cross_attention=False)
+            self.launches = L.launch_count() - launches0
+            return reward
 
         # 6. final norm on the last valid row + value head
-        xe = self._final_rows(hid, hid_e, eos_row, B)
+        xe = self._final_rows(hid, hid_e, head_row, B)
         reward = torch.empty(B, cfg.vhd, dtype=torch.bfloat16, device=dev)
         ops.skipca_head(None, None, None, xe, None, w.head["vh"], reward, B, H, 0, cfg.vhd, cfg.rms_eps)
         self.launches = L.launch_count() - launches0
@@ -518,7 +610,7 @@ class QwenVLRewardEngine(RewardEngine):
 
     @torch.no_grad()
     def forward(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, pixel_values: torch.Tensor,
-                image_grid_thw) -> torch.Tensor:
+                image_grid_thw, last_position: bool = False, mean_pool: bool = False) -> torch.Tensor:
         cfg, w, dev = self.cfg, self.w, self.device
         launches0 = L.launch_count()
         B, S = input_ids.shape
@@ -602,10 +694,17 @@ class QwenVLRewardEngine(RewardEngine):
             ops.compact_rows(hid, pad_ord, pad_plan, kv_src, B, S, H)
 
         # 4. decoder (per-token M-RoPE rows: position_ids = None)
-        hid_e = self._decoder(hid, B, S, None, seq_start, seq_len, cos_tok, sin_tok, eos_row)
+        if mean_pool and ca:
+            raise NotImplementedError("mean_hidden_state together with the qwen SkipCA arm")
+        head_row = self._head_rows(eos_row, B, S, last_position)
+        hid_e = self._decoder(hid, B, S, None, seq_start, seq_len, cos_tok, sin_tok, None if mean_pool else head_row)
+        if mean_pool:
+            reward = self._mean_head(hid, mask, B, S, True, cross_attention=False)
+            self.launches = L.launch_count() - launches0
+            return reward
 
         # 5. final norm on the last valid row, SkipCA (qwen arm), value head
-        xe = self._final_rows(hid, hid_e, eos_row, B)
+        xe = self._final_rows(hid, hid_e, head_row, B)
         vhd = cfg.vhd
         reward = torch.empty(B, vhd, dtype=torch.bfloat16, device=dev)
         if ca and sum_pad > 0:

@@ -59,9 +59,12 @@ class B200RewardModel:
         return self
 
     def train(self, mode: bool = True):
-        if mode:
-            raise NotImplementedError("the B200 path implements the scoring forward only (no backward)")
-        return self.eval()
+        """Sets the `training` attribute custom_forward reads. There is no backward and no dropout on this path (the
+        reference's scoring configs have every dropout probability at 0), so the only effect is the reference's
+        training-mode gather: the reward is read at the LAST position instead of the last valid token
+        (rw_model_general_preference.py:413-418, 432-436) - identical for left-padded batches."""
+        self.training = bool(mode)
+        return self
 
     def parameters(self):
         return iter(())
@@ -78,20 +81,25 @@ class B200RewardModel:
             raise NotImplementedError("inputs_batch is the qwen/llava calling convention; this build covers phi3v")
         if return_output:
             raise NotImplementedError("return_output=True (HF BaseModelOutputWithPast) is not produced by the fused path")
-        if self.mean_hidden_state:
-            raise NotImplementedError("mean_hidden_state pooling is off in all shipped reference configs")
-        if self.layer_id != self.config.num_layers and self.layer_id != 32:
-            raise NotImplementedError("layer_id other than the last layer")
+        if self.vision_layer_id != -1:
+            raise NotImplementedError("vision_layer_id other than -1 (the vision_embeds entry of hidden_states)")
         if input_ids is None or attention_mask is None:
             raise ValueError("input_ids and attention_mask are required")
         if pixel_values is None or image_sizes is None:
             # the reference path is image-only by construction (UnboundLocalError at modeling_phi3_v.py:252)
             raise ValueError("pixel_values and image_sizes are required (the scoring path is image-only)")
-        if self.training:
-            raise NotImplementedError("training-mode gather (values[:, -1]) is not part of the scoring path")
         with torch.cuda.device(self.device):
-            reward = self.engine.forward(input_ids, attention_mask, pixel_values, image_sizes)
-        return reward, None
+            reward = self.engine.forward(input_ids, attention_mask, pixel_values, image_sizes, layer_id=self.layer_id,
+                                         last_position=bool(self.training) and not self.mean_hidden_state,
+                                         mean_pool=bool(self.mean_hidden_state))
+        return self._shape_like_reference(reward), None
+
+    def _shape_like_reference(self, reward):
+        """BT + training-mode gather returns `values.squeeze(-1)[:, -1]`, shape [B] (rw_model_general_preference.py
+        :413-414); every other combination is [B, vhd]."""
+        if self.training and not self.mean_hidden_state and not self.is_general_preference:
+            return reward[:, 0]
+        return reward
 
     __call__ = custom_forward
 
@@ -118,17 +126,15 @@ class B200LlavaNextRewardModel(B200RewardModel):
             raise TypeError("model_type 'llava' is called as custom_forward(inputs_batch=processor_output)")
         if return_output:
             raise NotImplementedError("return_output=True (HF LlavaNextCausalLMOutputWithPast) is not produced by the fused path")
-        if self.mean_hidden_state:
-            raise NotImplementedError("mean_hidden_state pooling is off in all shipped reference configs")
-        if self.training:
-            raise NotImplementedError("training-mode gather (values[:, -1]) is not part of the scoring path")
         for k in ("input_ids", "attention_mask", "pixel_values", "image_sizes"):
             if k not in inputs_batch:
                 raise KeyError(k)
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device):   # `layer_id` is not read by the reference in this branch (:372-375)
             reward = self.engine.forward(inputs_batch["input_ids"], inputs_batch["attention_mask"],
-                                         inputs_batch["pixel_values"], inputs_batch["image_sizes"])
-        return reward, None
+                                         inputs_batch["pixel_values"], inputs_batch["image_sizes"],
+                                         last_position=bool(self.training) and not self.mean_hidden_state,
+                                         mean_pool=bool(self.mean_hidden_state))
+        return self._shape_like_reference(reward), None
 
     __call__ = custom_forward
 
@@ -155,10 +161,6 @@ class B200QwenRewardModel(B200RewardModel):
             raise TypeError("model_type 'qwen' is called as custom_forward(inputs_batch=processor_output)")
         if return_output:
             raise NotImplementedError("return_output=True (HF Qwen2_5_VLCausalLMOutputWithPast) is not produced by the fused path")
-        if self.mean_hidden_state:
-            raise NotImplementedError("mean_hidden_state pooling is off in all shipped reference configs")
-        if self.training:
-            raise NotImplementedError("training-mode gather (values[:, -1]) is not part of the scoring path")
         for k in ("input_ids", "attention_mask", "pixel_values", "image_grid_thw"):
             if k not in inputs_batch:
                 raise KeyError(k)
@@ -166,7 +168,9 @@ class B200QwenRewardModel(B200RewardModel):
             raise NotImplementedError("video inputs: the reference's reward datasets are image-only")
         with torch.cuda.device(self.device):
             reward = self.engine.forward(inputs_batch["input_ids"], inputs_batch["attention_mask"],
-                                         inputs_batch["pixel_values"], inputs_batch["image_grid_thw"])
-        return reward, None
+                                         inputs_batch["pixel_values"], inputs_batch["image_grid_thw"],
+                                         last_position=bool(self.training) and not self.mean_hidden_state,
+                                         mean_pool=bool(self.mean_hidden_state))
+        return self._shape_like_reference(reward), None
 
     __call__ = custom_forward

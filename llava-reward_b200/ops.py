@@ -170,3 +170,15 @@ def gather_rows(src, row_index, dst, rows, cols):
     _need_cuda(src, row_index, dst)
     L.call("lr_gather_rows_bf16", _ptr(src), src.stride(0), _ptr(row_index), _ptr(dst), dst.stride(0), rows, cols,
            _stream())
+
+
+# ---- all-rows head (mean_hidden_state) ------------------------------------------------------------------------------
+def softmax_rows(scores, rows, n_valid, n_total, inv_sqrt_d):
+    """In place: bf16 softmax over columns [0, n_valid) of bf16(score * inv_sqrt_d), zeros in [n_valid, n_total)."""
+    _need_cuda(scores)
+    L.call("lr_softmax_rows_bf16", _ptr(scores), scores.stride(0), rows, n_valid, n_total, float(inv_sqrt_d), _stream())
+
+
+def masked_mean_rows(x, mask, out, B, S, H):
+    _need_cuda(x, mask, out)
+    L.call("lr_masked_mean_rows_bf16", _ptr(x), x.stride(0), _ptr(mask), _ptr(out), out.stride(0), B, S, H, _stream())

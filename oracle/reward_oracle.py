@@ -249,8 +249,22 @@ def eos_gather(values: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tens
     return values[torch.arange(values.shape[0], device=values.device), eos]
 
 
-def custom_forward(P: Params, cfg, input_ids, attention_mask, pixel_values, image_sizes, taps=None):
-    """-> reward [B, vhd] (GPM) or [B, 1] (BT)."""
+def masked_mean(last_hidden: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:
+    """mean_hidden_state pooling (rw_model_general_preference.py:398-406): every op in the model dtype."""
+    mask = attention_mask.to(dtype=last_hidden.dtype).unsqueeze(-1)
+    total = (last_hidden * mask).sum(dim=1)
+    lens = mask.sum(dim=1).clamp(min=1e-8)
+    return total / lens
+
+
+def custom_forward(P: Params, cfg, input_ids, attention_mask, pixel_values, image_sizes, taps=None, layer_id: int = 32,
+                   training: bool = False, mean_hidden_state: bool = False):
+    """-> reward [B, vhd] (GPM) or [B, 1] (BT).
+    layer_id / training / mean_hidden_state are the attributes the reference's custom_forward reads
+    (rw_model_general_preference.py:327-333): `layer_id == 32` -> last_hidden_state (after the final norm), otherwise
+    `hidden_states[layer_id]` of (inputs_embeds, h_1 .. h_{L-1}, norm(h_L), vision_embeds) (:349-352,
+    modeling_phi3_v.py:1463-1505); training -> the LAST position instead of the last valid one (:413-418, 432-436);
+    mean_hidden_state -> masked mean over the sequence before the value head (:398-406)."""
     position_ids = attention_mask.long().cumsum(-1) - 1
     position_ids = position_ids.masked_fill(attention_mask == 0, 1)
     B, C = pixel_values.shape[:2]
@@ -262,18 +276,30 @@ def custom_forward(P: Params, cfg, input_ids, attention_mask, pixel_values, imag
         taps["clip_features"], taps["img_proj"], taps["inputs_embeds"] = feats, proj, x
     mask4d = causal_padding_mask(attention_mask, P.dtype)
     cos, sin = su_rope_cos_sin(cfg, position_ids, P.dtype)
-    for i in range(cfg.num_layers):
+    if layer_id == 32 or layer_id == cfg.num_layers:
+        n_run, final_norm = cfg.num_layers, True
+    elif 0 <= layer_id < cfg.num_layers:
+        n_run, final_norm = layer_id, False
+    else:
+        raise ValueError(f"layer_id {layer_id}")
+    for i in range(n_run):
         x = decoder_layer(P, cfg, i, x, mask4d, cos, sin)
         if taps is not None:
             taps[f"hidden_{i}"] = x
-    x = rmsnorm(x, P("model.norm.weight"), cfg.rms_eps)
+    if final_norm:
+        x = rmsnorm(x, P("model.norm.weight"), cfg.rms_eps)
     if taps is not None:
         taps["last_hidden"] = x
     if cfg.add_cross_attention:
         x = skipca(P, cfg, x, vis)
         if taps is not None:
             taps["skipca_out"] = x
+    if mean_hidden_state:
+        return F.linear(masked_mean(x, attention_mask), P("value_head.weight"))
     values = F.linear(x, P("value_head.weight"))
+    if training:
+        # BT: `values.squeeze(-1)[:, -1]` -> [B]; GPM: `values[:, -1, :]` -> [B, vhd] (:413-418, 432-436)
+        return values[:, -1] if cfg.is_general_preference else values.squeeze(-1)[:, -1]
     return eos_gather(values, attention_mask)
 
 

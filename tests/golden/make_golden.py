@@ -157,6 +157,9 @@ CASES = {
     "full_gpm": (dict(), [("c", 1, [(1008, 1344)], 2048), ("r", 1, [(1008, 1344)], 2048)]),
 }
 SEED_W, SEED_X = 1234, 7
+ATTR_CASES = ("slim_gpm", "slim_bt")
+ATTR_VARIANTS = {"layer_id_1": {"layer_id": 1}, "layer_id_0": {"layer_id": 0}, "training": {"training": True},
+                 "mean": {"mean_hidden_state": True}, "mean_layer_id_1": {"mean_hidden_state": True, "layer_id": 1}}
 
 
 def run_case(name: str, refmods):
@@ -188,6 +191,21 @@ def run_case(name: str, refmods):
                           "last_hidden": sample(out["last_hidden_state"]), "vision_embeds": sample(hs[-1])}}
         # exact small slices (last valid row of first/last sample) for tighter checks
         entry["last_hidden_eos"] = out["last_hidden_state"][:, -1, :64].float().clone()
+        if name in ATTR_CASES:
+            # the attributes custom_forward honours (rw_model_general_preference.py:327-333, 349-352, 398-448), set on
+            # the reference model object exactly as a caller would; dropout probabilities are 0 in these configs, so
+            # the top-level `training` flag only switches the gather rule
+            entry["attrs"] = {}
+            for key, attrs in ATTR_VARIANTS.items():
+                saved = {k: getattr(model, k) for k in attrs}
+                for k, v in attrs.items():
+                    setattr(model, k, v)
+                with torch.no_grad():
+                    r2, _ = model.custom_forward(ids, mask, pix, sizes)
+                for k, v in saved.items():
+                    setattr(model, k, v)
+                entry["attrs"][key] = r2.float().clone()
+                print(f"    {key}: {r2.flatten().tolist()}", flush=True)
         fixture["batches"].append(entry)
         rewards[tag] = reward
     prob = ral.preference_compute(args, rewards["c"], rewards["r"])

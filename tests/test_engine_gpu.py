@@ -406,3 +406,78 @@ def test_last_layer_row_shortcut_is_output_identical(case, tmp_path_factory):
     print(f"{case}: shortcut {r_short.flatten().tolist()} full {r_full.flatten().tolist()} |d| {d:.3g}; "
           f"launches {n_short} vs {eng.launches}")
     assert d <= 4e-3   # same arithmetic per row; only the GEMM tile shape (small-M kernel) may differ in fp32 summation
+
+
+ATTR_VARIANTS = {"layer_id_1": dict(layer_id=1), "layer_id_0": dict(layer_id=0), "training": dict(training=True),
+                 "mean": dict(mean_hidden_state=True), "mean_layer_id_1": dict(mean_hidden_state=True, layer_id=1)}
+
+
+@pytest.mark.parametrize("case", ["slim_gpm", "slim_bt"])
+def test_attribute_variants_vs_reference_golden(case, tmp_path_factory):
+    """`layer_id`, `training` and `mean_hidden_state` - the attributes the reference's custom_forward reads
+    (rw_model_general_preference.py:327-333) - set on the model object exactly as on the reference's; goldens were
+    made by setting them on the reference model (tests/golden/make_golden.py). mean_hidden_state runs the all-rows
+    SkipCA (per-sample GEMMs + lr_softmax_rows_bf16) and lr_masked_mean_rows_bf16."""
+    fx = load_fixture(case)
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    entry = fx["batches"][0]
+    ids, mask, pix, sizes = fixture_batch(fx, entry, cfg, device="cuda")
+    P = O.Params(SynthProvider(cfg, seed=fx["seed_w"], device="cuda"), dtype=torch.bfloat16, device="cuda", cache=False)
+    saved = {k: getattr(model, k) for k in ("layer_id", "training", "mean_hidden_state")}
+    try:
+        for key, attrs in ATTR_VARIANTS.items():
+            for k, v in saved.items():
+                setattr(model, k, v)
+            for k, v in attrs.items():
+                setattr(model, k, v)
+            r, _ = model.custom_forward(ids, mask, pix, sizes)
+            g = entry["attrs"][key]
+            assert tuple(r.shape) == tuple(g.shape), key
+            with torch.no_grad():
+                ro = O.custom_forward(P, cfg, ids, mask, pix, sizes, **attrs).float().cpu()
+            err, floor = (r.float().cpu() - g).abs().max().item(), (ro - g).abs().max().item()
+            print(f"{case}/{key}: engine {r.float().flatten().tolist()} ref {g.flatten().tolist()} | engine-vs-fp32 "
+                  f"{err:.4g}, reference bf16-vs-fp32 {floor:.4g}")
+            assert err < REWARD_TOL + 3.0 * floor, key
+    finally:
+        for k, v in saved.items():
+            setattr(model, k, v)
+    # training-mode gather = eval gather on a left-padded batch (position S-1 is the last valid token)
+    assert bool((mask[:, -1] == 1).all())
+
+
+def test_gather_rows_negative_index_is_zero_row():
+    from llava_reward_b200 import ops
+    src = torch.randn(5, 64, device="cuda").to(torch.bfloat16)
+    idx = torch.tensor([3, -1, 0, -1], dtype=torch.int32, device="cuda")
+    dst = torch.full((4, 64), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.gather_rows(src, idx, dst, 4, 64)
+    torch.cuda.synchronize()
+    assert torch.equal(dst[0], src[3]) and torch.equal(dst[2], src[0])
+    assert (dst[1] == 0).all() and (dst[3] == 0).all()
+
+
+@pytest.mark.parametrize("rows,n_valid,n_total", [(7, 100, 256), (33, 1921, 2048), (5, 8, 8)])
+def test_softmax_rows_and_masked_mean_kernels(rows, n_valid, n_total):
+    from llava_reward_b200 import ops
+    torch.manual_seed(rows)
+    s = (torch.randn(rows, n_total, device="cuda") * 30).to(torch.bfloat16)
+    ref = torch.softmax((s[:, :n_valid] / 55.42562584220407).float().to(torch.bfloat16), dim=-1)  # sqrt(3072)
+    out = s.clone()
+    ops.softmax_rows(out, rows, n_valid, n_total, 1.0 / 55.42562584220407)
+    torch.cuda.synchronize()
+    assert (out[:, n_valid:] == 0).all()
+    assert (out[:, :n_valid].float() - ref.float()).abs().max().item() <= 2 ** -8 * ref.float().max().item() + 1e-6
+    B, S, H = 3, 37, 512
+    x = torch.randn(B * S, H, device="cuda").to(torch.bfloat16)
+    m = torch.zeros(B, S, dtype=torch.int64, device="cuda")
+    m[0, 5:] = 1
+    m[1, :] = 1
+    m[2, 30:] = 1
+    pooled = torch.empty(B, H, device="cuda", dtype=torch.bfloat16)
+    ops.masked_mean_rows(x, m, pooled, B, S, H)
+    xb = x.view(B, S, H)
+    mb = m.to(torch.bfloat16).unsqueeze(-1)
+    want = (xb * mb).sum(dim=1) / mb.sum(dim=1).clamp(min=1e-8)
+    torch.cuda.synchronize()
+    assert (pooled.float() - want.float()).abs().max().item() <= 2 ** -7 * want.float().abs().max().item()

@@ -41,3 +41,24 @@ def test_oracle_matches_reference(case):
     p = O.preference_compute(cfg, rewards["c"], rewards["r"])
     assert (p - fx["prob"]).abs().max().item() < 1e-3
     assert ((p > 0.5) == (fx["prob"] > 0.5)).all()
+
+
+ATTR_KW = {"layer_id_1": dict(layer_id=1), "layer_id_0": dict(layer_id=0), "training": dict(training=True),
+           "mean": dict(mean_hidden_state=True), "mean_layer_id_1": dict(mean_hidden_state=True, layer_id=1)}
+
+
+@pytest.mark.parametrize("case", ["slim_gpm", "slim_bt"])
+def test_oracle_attribute_variants_match_reference(case):
+    """layer_id / training / mean_hidden_state, the attributes the reference's custom_forward reads
+    (rw_model_general_preference.py:327-333): fixtures made by setting them on the reference model object."""
+    fx = load_fixture(case)
+    cfg = fixture_cfg(fx)
+    P = O.Params(SynthProvider(cfg, seed=fx["seed_w"]), dtype=torch.float32)
+    entry = fx["batches"][0]
+    ids, mask, pix, sizes = fixture_batch(fx, entry, cfg)
+    for key, kw in ATTR_KW.items():
+        with torch.no_grad():
+            r = O.custom_forward(P, cfg, ids, mask, pix, sizes, **kw)
+        g = entry["attrs"][key]
+        assert r.shape == g.shape, key
+        assert (r - g).abs().max().item() < TOL, (key, r, g)
