@@ -196,6 +196,30 @@ class RewardEngine:
         self._tap("last_hidden_eos", xe)
         return xe
 
+    def model_outputs(self, taps: dict, B: int, S: int):
+        """The `outputs` object of custom_forward(return_output=True) from a forward run with `self.taps` set:
+        last_hidden_state = norm(h_L) and hidden_states = (inputs_embeds, h_1 .. h_{L-1}, norm(h_L), vision_embeds),
+        vision_embeds zero-padded to the batch maximum (modeling_phi3_v.py:250-252, 1463-1505). Rows at padded
+        positions follow the reference's flash-attention path (attention output 0 there), not its eager path."""
+        from transformers.modeling_outputs import BaseModelOutputWithPast
+
+        cfg, w = self.cfg, self.w
+        H, n = cfg.hidden_size, cfg.num_layers
+        last = torch.empty(B * S, H, dtype=torch.bfloat16, device=self.device)
+        src = taps[f"hidden_{n - 1}"] if n > 0 else taps["inputs_embeds"]
+        ops.rmsnorm(src, w.head["norm"], last, B * S, H, cfg.rms_eps)
+        plan_h, max_nv = self._last_plan
+        idx_h = np.full((B, max_nv), -1, dtype=np.int32)
+        for b in range(B):
+            nv = int(plan_h[b, L.PLAN_NV])
+            idx_h[b, :nv] = int(plan_h[b, L.PLAN_ROW_BASE]) + np.arange(nv, dtype=np.int32)
+        idx = torch.from_numpy(idx_h.reshape(-1)).to(self.device)
+        vis = torch.empty(B * max_nv, H, dtype=torch.bfloat16, device=self.device)
+        ops.gather_rows(taps["img_proj"], idx, vis, B * max_nv, H)
+        hs = [taps["inputs_embeds"]] + [taps[f"hidden_{i}"] for i in range(n - 1)] + [last]
+        hs = tuple(t.view(B, S, H) for t in hs) + (vis.view(B, max_nv, H),)
+        return BaseModelOutputWithPast(last_hidden_state=hs[-2], past_key_values=None, hidden_states=hs, attentions=None)
+
     def _resolve_layer_id(self, layer_id):
         """-> (decoder layers to run, apply the final norm). The reference takes `last_hidden_state` for layer_id 32 and
         otherwise indexes (inputs_embeds, h_1 .. h_{L-1}, norm(h_L), vision_embeds) (rw_model_general_preference.py
@@ -316,6 +340,7 @@ class RewardEngine:
             row_base += nv
         n_crops, sum_nv = crop_base, row_base
         max_nv = int(plan_h[:, L.PLAN_NV].max())
+        self._last_plan = (plan_h, max_nv)
         max_len = int(meta_h[B:2 * B].max())
         host = torch.from_numpy(np.concatenate([plan_h.reshape(-1), np.asarray(crop_src, dtype=np.int32)]))
         dev_plan = self.buf("plan", (host.numel(),), torch.int32)

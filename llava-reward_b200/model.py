@@ -79,8 +79,6 @@ class B200RewardModel:
             raise RuntimeError("call .to('cuda') before custom_forward (weights are packed on the device)")
         if inputs_batch is not None:
             raise NotImplementedError("inputs_batch is the qwen/llava calling convention; this build covers phi3v")
-        if return_output:
-            raise NotImplementedError("return_output=True (HF BaseModelOutputWithPast) is not produced by the fused path")
         if self.vision_layer_id != -1:
             raise NotImplementedError("vision_layer_id other than -1 (the vision_embeds entry of hidden_states)")
         if input_ids is None or attention_mask is None:
@@ -88,11 +86,24 @@ class B200RewardModel:
         if pixel_values is None or image_sizes is None:
             # the reference path is image-only by construction (UnboundLocalError at modeling_phi3_v.py:252)
             raise ValueError("pixel_values and image_sizes are required (the scoring path is image-only)")
+        kw = dict(layer_id=self.layer_id, last_position=bool(self.training) and not self.mean_hidden_state,
+                  mean_pool=bool(self.mean_hidden_state))
         with torch.cuda.device(self.device):
-            reward = self.engine.forward(input_ids, attention_mask, pixel_values, image_sizes, layer_id=self.layer_id,
-                                         last_position=bool(self.training) and not self.mean_hidden_state,
-                                         mean_pool=bool(self.mean_hidden_state))
-        return self._shape_like_reference(reward), None
+            if not return_output:
+                reward = self.engine.forward(input_ids, attention_mask, pixel_values, image_sizes, **kw)
+                return self._shape_like_reference(reward), None
+            # return_output: the trainer-side callers read outputs["hidden_states"] / ["last_hidden_state"]
+            # (rw_model_general_preference.py:422-425, 445-448). Every layer's hidden state is copied out of the
+            # in-place residual buffer - a debugging / analysis path, not the scoring path.
+            if self.engine._resolve_layer_id(self.layer_id)[0] != self.config.num_layers:
+                raise NotImplementedError("return_output=True together with an early layer_id")
+            self.engine.taps = {}
+            try:
+                reward = self.engine.forward(input_ids, attention_mask, pixel_values, image_sizes, **kw)
+                outputs = self.engine.model_outputs(self.engine.taps, *input_ids.shape)
+            finally:
+                self.engine.taps = None
+        return self._shape_like_reference(reward), outputs
 
     def _shape_like_reference(self, reward):
         """BT + training-mode gather returns `values.squeeze(-1)[:, -1]`, shape [B] (rw_model_general_preference.py

@@ -481,3 +481,30 @@ def test_softmax_rows_and_masked_mean_kernels(rows, n_valid, n_total):
     want = (xb * mb).sum(dim=1) / mb.sum(dim=1).clamp(min=1e-8)
     torch.cuda.synchronize()
     assert (pooled.float() - want.float()).abs().max().item() <= 2 ** -7 * want.float().abs().max().item()
+
+
+def test_return_output_hidden_states(tmp_path_factory):
+    """custom_forward(return_output=True): the reference returns its BaseModelOutputWithPast; the golden fixture holds
+    strided samples of hidden_states[0], [1], last_hidden_state and the zero-padded vision_embeds ([-1])."""
+    fx = load_fixture("slim_gpm")
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    entry = fx["batches"][0]
+    ids, mask, pix, sizes = fixture_batch(fx, entry, cfg, device="cuda")
+    r0, none = model.custom_forward(ids, mask, pix, sizes)
+    r, out = model.custom_forward(ids, mask, pix, sizes, return_output=True)
+    assert none is None and model.engine.taps is None
+    assert (r.float() - r0.float()).abs().max().item() < 2e-2   # the capture path runs the un-shortcut last layer
+    hs = out["hidden_states"]
+    assert len(hs) == cfg.num_layers + 2 and out["last_hidden_state"] is hs[-2]
+    valid = mask.bool()[:, :, None]
+    for name, t in (("inputs_embeds", hs[0]), ("hidden_0", hs[1]), ("last_hidden", out.last_hidden_state),
+                    ("vision_embeds", hs[-1])):
+        g = entry["taps"][name]
+        assert list(t.shape) == g["shape"], name
+        tt = t if name == "vision_embeds" else torch.where(valid.expand_as(t), t, torch.zeros_like(t))
+        a = tt.float().flatten()[:: g["stride"]][:2048].cpu()
+        w = torch.ones_like(a) if name == "vision_embeds" else \
+            valid.expand_as(t).float().flatten()[:: g["stride"]][:2048].cpu()
+        rel = ((a - g["vals"] * w).norm() / (g["vals"] * w).norm()).item()
+        print(f"return_output {name}: rel L2 err vs reference fp32 {rel:.4g}")
+        assert rel < 3e-2, name
