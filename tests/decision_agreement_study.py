@@ -2,7 +2,7 @@
 engine (bf16, this repo) vs the oracle = the reference's arithmetic in fp32 and in bf16 (eager attention) on N
 synthetic config-2 pairs (Phi-3.5-V + SkipCA + LoRA + GPM, (1008,1344), S=2048, 23+32 layers).
 Prints agreement rates next to the reference's own bf16-vs-fp32 flip rate (noise floor).
-usage: python tools/decision_agreement.py [n_pairs]"""
+usage: python tests/decision_agreement_study.py [n_pairs]"""
 import os
 import sys
 import types
