@@ -36,3 +36,20 @@ def test_binary_metrics_match_sklearn():
     assert abs(m["f1"] - f1_score(label, pred, average="binary")) < 1e-12
     assert abs(m["recall"] - recall_score(label, pred)) < 1e-12
     assert abs(m["accuracy"] - (pred == label).mean()) < 1e-12
+
+
+def test_feed_map_tensors_keeps_structure():
+    """feed._map_tensors walks dict / BatchFeature / tuple / list batches and leaves non-tensors alone; the prefetcher
+    itself refuses a CPU target (no CPU path in this package)."""
+    import pytest
+    import torch
+    from transformers import BatchFeature
+    from llava_reward_b200.feed import DevicePrefetcher, _map_tensors
+    b = BatchFeature({"input_ids": torch.arange(6).view(2, 3), "pixel_values": torch.ones(2, 2)})
+    nested = ({"x": torch.zeros(2), "n": 3, "s": "keep"}, [torch.ones(1), (torch.ones(2), None)], b)
+    out = _map_tensors(nested, lambda t: t + 1)
+    assert out[0]["n"] == 3 and out[0]["s"] == "keep" and torch.equal(out[0]["x"], torch.ones(2))
+    assert torch.equal(out[1][0], torch.full((1,), 2.0)) and out[1][1][1] is None
+    assert isinstance(out[2], BatchFeature) and torch.equal(out[2]["input_ids"], b["input_ids"] + 1)
+    with pytest.raises(RuntimeError):
+        DevicePrefetcher([], device="cpu")

@@ -508,3 +508,41 @@ def test_return_output_hidden_states(tmp_path_factory):
         rel = ((a - g["vals"] * w).norm() / (g["vals"] * w).norm()).item()
         print(f"return_output {name}: rel L2 err vs reference fp32 {rel:.4g}")
         assert rel < 3e-2, name
+
+
+def test_device_prefetcher_feeds_the_eval_loop(tmp_path_factory):
+    """feed.DevicePrefetcher: CPU batches of any nesting arrive on the device unchanged and in order (pinned staging
+    sets reused round-robin, copies on a side stream), and score_pairs over the prefetcher gives exactly the rewards of
+    the blocking loop."""
+    from llava_reward_b200.batch_eval import collate_samples, score_pairs
+    from llava_reward_b200.feed import DevicePrefetcher
+    from llava_reward_b200.synth import synth_batch, PAD
+    raw = [{"a": torch.full((3, 5), float(i)), "nest": (torch.arange(4) + i, [torch.ones(2, 2) * i]), "tag": f"b{i}"}
+           for i in range(5)]
+    pf = DevicePrefetcher(raw, device="cuda")
+    seen = list(pf)
+    assert len(seen) == 5 and pf.h2d_bytes == 5 * (15 * 4 + 4 * 8 + 4 * 4)
+    for i, b in enumerate(seen):
+        assert b["tag"] == f"b{i}" and b["a"].is_cuda and b["nest"][1][0].is_cuda
+        assert torch.equal(b["a"].cpu(), raw[i]["a"]) and torch.equal(b["nest"][0].cpu(), raw[i]["nest"][0])
+    assert list(DevicePrefetcher([], device="cuda")) == []
+
+    fx = load_fixture("slim_bt")
+    args, model, cfg = build_model(fx, tmp_path_factory)
+
+    def samples(tag, n):
+        out = []
+        for i in range(n):
+            ids, mask, pix, sizes = synth_batch(cfg, 1, (336, 336 * (1 + i % 2)), None, seed=50 + i, tag=f"{tag}{i}",
+                                                text_len_range=(5, 40))
+            out.append({"input_ids": ids, "attention_mask": mask, "pixel_values": pix, "image_sizes": sizes})
+        return out
+
+    ch, rj = samples("c", 6), samples("r", 6)
+    cpu_batches = [(collate_samples(ch[i:i + 2], PAD), collate_samples(rj[i:i + 2], PAD)) for i in (0, 2, 4)]
+    dev_batches = [tuple({k: v.cuda() for k, v in b.items()} for b in pair) for pair in cpu_batches]
+    blocking = score_pairs(model, args, dev_batches)
+    prefetched = score_pairs(model, args, DevicePrefetcher(cpu_batches, device="cuda"))
+    assert blocking["chosen_rewards"] == prefetched["chosen_rewards"]
+    assert blocking["reject_rewards"] == prefetched["reject_rewards"]
+    assert (blocking["probs"] == prefetched["probs"]).all()
