@@ -155,6 +155,11 @@ CASES = {
     "full_bt": (dict(is_general_preference=False, add_cross_attention=False, use_lora=False),
                 [("c", 1, [(1344, 1344)], None), ("r", 1, [(1344, 1344)], None)]),
     "full_gpm": (dict(), [("c", 1, [(1008, 1344)], 2048), ("r", 1, [(1008, 1344)], 2048)]),
+    # sequences beyond original_max_position_embeddings (4096): the su-RoPE switches to the long factors for the WHOLE
+    # batch (seq_len = max(position_ids) + 1 over the batch, modeling_phi3_v.py:446-451), incl. the short sample
+    "slim_bt_long": (dict(num_layers=2, clip_layers=2, is_general_preference=False, add_cross_attention=False,
+                          use_lora=False), [("c", 2, [(1344, 1344), (336, 336)], None, (1600, 1700)),
+                                            ("r", 2, [(1344, 1344), (336, 336)], None, (1600, 1700))]),
 }
 SEED_W, SEED_X = 1234, 7
 ATTR_CASES = ("slim_gpm", "slim_bt")
@@ -177,8 +182,10 @@ def run_case(name: str, refmods):
     fixture = {"case": name, "cfg_overrides": over, "seed_w": SEED_W, "seed_x": SEED_X, "batches": [],
                "torch": torch.__version__}
     rewards = {}
-    for tag, B, hw_list, seq_len in batches:
-        ids, mask, pix, sizes = synth_batch(cfg, B, hw_list[0], seq_len, seed=SEED_X, tag=tag, image_hw_list=hw_list)
+    for tag, B, hw_list, seq_len, *rest in batches:
+        tlr = rest[0] if rest else (40, 128)
+        ids, mask, pix, sizes = synth_batch(cfg, B, hw_list[0], seq_len, seed=SEED_X, tag=tag, image_hw_list=hw_list,
+                                            text_len_range=tlr)
         t0 = time.time()
         with torch.no_grad():
             reward, out = model.custom_forward(ids, mask, pix, sizes, return_output=True)
@@ -186,6 +193,7 @@ def run_case(name: str, refmods):
         print(f"  batch {tag}: S={ids.shape[1]} reward={reward.flatten().tolist()} ({dt:.1f}s)", flush=True)
         hs = out["hidden_states"]
         entry = {"tag": tag, "batch": B, "image_hw": hw_list, "seq_len": seq_len, "S": ids.shape[1],
+                 "text_len_range": list(tlr),
                  "seconds": dt, "reward": reward.float().clone(),
                  "taps": {"inputs_embeds": sample(hs[0]), "hidden_0": sample(hs[1]),
                           "last_hidden": sample(out["last_hidden_state"]), "vision_embeds": sample(hs[-1])}}

@@ -20,7 +20,7 @@ def fixture_batch(fx, entry, cfg, device="cpu"):
     from llava_reward_b200.synth import synth_batch
     hw = [tuple(x) for x in entry["image_hw"]]
     return synth_batch(cfg, entry["batch"], hw[0], entry["seq_len"], seed=fx["seed_x"], tag=entry["tag"],
-                       image_hw_list=hw, device=device)
+                       image_hw_list=hw, device=device, text_len_range=tuple(entry.get("text_len_range", (40, 128))))
 
 
 def strided(t, stride, n=2048):

@@ -83,7 +83,7 @@ def rel_err(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
 
 
-@pytest.mark.parametrize("case", ["slim_gpm", "slim_bt"])
+@pytest.mark.parametrize("case", ["slim_gpm", "slim_bt", "slim_bt_long"])
 def test_slim_vs_reference_golden(case, tmp_path_factory):
     fx = load_fixture(case)
     args, model, cfg = build_model(fx, tmp_path_factory)

@@ -11,7 +11,7 @@ from llava_reward_b200.synth import SynthProvider
 TOL = 1e-4
 
 
-@pytest.mark.parametrize("case", ["slim_gpm", "slim_bt"])
+@pytest.mark.parametrize("case", ["slim_gpm", "slim_bt", "slim_bt_long"])
 def test_oracle_matches_reference(case):
     fx = load_fixture(case)
     cfg = fixture_cfg(fx)
