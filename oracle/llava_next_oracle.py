@@ -22,7 +22,7 @@ from typing import List, Tuple
 import torch
 import torch.nn.functional as F
 
-from .reward_oracle import Params, _rot_half, causal_padding_mask, clip_features, eos_gather, lora_linear, rmsnorm
+from .reward_oracle import Params, _rot_half, causal_padding_mask, clip_features, eos_gather, head_tail, lora_linear, rmsnorm
 
 CLIP = "vision_tower.vision_model."
 LM = "language_model.model."
@@ -118,7 +118,8 @@ def decoder_layer(P: Params, cfg, i: int, x: torch.Tensor, mask4d, cos, sin) -> 
     return x + lora_linear(P, cfg, p + "mlp.down_proj", act)
 
 
-def custom_forward(P: Params, cfg, inputs_batch, taps=None) -> torch.Tensor:
+def custom_forward(P: Params, cfg, inputs_batch, taps=None, training: bool = False,
+                   mean_hidden_state: bool = False) -> torch.Tensor:
     """-> reward [B, vhd] (GPM) or [B, 1] (BT) for the `inputs_batch` dict of the LlavaNext processor."""
     ids, mask = inputs_batch["input_ids"], inputs_batch["attention_mask"]
     B, S = ids.shape
@@ -142,5 +143,4 @@ def custom_forward(P: Params, cfg, inputs_batch, taps=None) -> torch.Tensor:
     x = rmsnorm(x, P(LM + "norm.weight"), cfg.rms_eps)
     if taps is not None:
         taps["last_hidden"] = x
-    values = F.linear(x, P("value_head.weight"))
-    return eos_gather(values, mask)
+    return head_tail(P, cfg, x, mask, training, mean_hidden_state)

@@ -21,7 +21,7 @@ import math
 import torch
 import torch.nn.functional as F
 
-from .reward_oracle import Params, _rot_half, causal_padding_mask, eos_gather, rmsnorm
+from .reward_oracle import Params, _rot_half, causal_padding_mask, eos_gather, head_tail, rmsnorm
 
 V = "visual."
 LM = "model."
@@ -215,7 +215,8 @@ def skipca_qwen(P: Params, cfg, last_hidden: torch.Tensor, hidden0: torch.Tensor
     return rmsnorm(last_hidden + o, P("ca_layernorm.weight"), cfg.rms_eps)
 
 
-def custom_forward(P: Params, cfg, inputs_batch, taps=None) -> torch.Tensor:
+def custom_forward(P: Params, cfg, inputs_batch, taps=None, training: bool = False,
+                   mean_hidden_state: bool = False) -> torch.Tensor:
     """-> reward [B, vhd] (GPM) or [B, 1] (BT) for the `inputs_batch` dict of the Qwen2.5-VL processor."""
     ids, mask = inputs_batch["input_ids"], inputs_batch["attention_mask"]
     grid = inputs_batch["image_grid_thw"].tolist()
@@ -243,5 +244,4 @@ def custom_forward(P: Params, cfg, inputs_batch, taps=None) -> torch.Tensor:
         x = skipca_qwen(P, cfg, x, hidden0, ids)
         if taps is not None:
             taps["after_skipca"] = x
-    values = F.linear(x, P("value_head.weight"))
-    return eos_gather(values, mask)
+    return head_tail(P, cfg, x, mask, training, mean_hidden_state)

@@ -257,6 +257,18 @@ def masked_mean(last_hidden: torch.Tensor, attention_mask: torch.Tensor) -> torc
     return total / lens
 
 
+def head_tail(P: Params, cfg, x: torch.Tensor, attention_mask: torch.Tensor, training: bool = False,
+              mean_hidden_state: bool = False) -> torch.Tensor:
+    """value head + the gather rule of rw_model_general_preference.py:398-448 on the final hidden states x [B,S,H]"""
+    if mean_hidden_state:
+        return F.linear(masked_mean(x, attention_mask), P("value_head.weight"))
+    values = F.linear(x, P("value_head.weight"))
+    if training:
+        # BT: `values.squeeze(-1)[:, -1]` -> [B]; GPM: `values[:, -1, :]` -> [B, vhd] (:413-418, 432-436)
+        return values[:, -1] if cfg.is_general_preference else values.squeeze(-1)[:, -1]
+    return eos_gather(values, attention_mask)
+
+
 def custom_forward(P: Params, cfg, input_ids, attention_mask, pixel_values, image_sizes, taps=None, layer_id: int = 32,
                    training: bool = False, mean_hidden_state: bool = False):
     """-> reward [B, vhd] (GPM) or [B, 1] (BT).
@@ -294,13 +306,7 @@ def custom_forward(P: Params, cfg, input_ids, attention_mask, pixel_values, imag
         x = skipca(P, cfg, x, vis)
         if taps is not None:
             taps["skipca_out"] = x
-    if mean_hidden_state:
-        return F.linear(masked_mean(x, attention_mask), P("value_head.weight"))
-    values = F.linear(x, P("value_head.weight"))
-    if training:
-        # BT: `values.squeeze(-1)[:, -1]` -> [B]; GPM: `values[:, -1, :]` -> [B, vhd] (:413-418, 432-436)
-        return values[:, -1] if cfg.is_general_preference else values.squeeze(-1)[:, -1]
-    return eos_gather(values, attention_mask)
+    return head_tail(P, cfg, x, attention_mask, training, mean_hidden_state)
 
 
 def preference_compute(cfg, chosen: torch.Tensor, reject: torch.Tensor) -> torch.Tensor:

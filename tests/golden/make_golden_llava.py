@@ -28,6 +28,8 @@ from make_golden import LoraWrapped, import_reference, sample  # noqa: E402
 
 SEED_W, SEED_X = 1234, 7
 
+ATTR_VARIANTS = {"training": {"training": True}, "mean": {"mean_hidden_state": True}}
+ATTR_CASES = {"llava_slim_bt": ("training", "mean"), "llava_slim_gpm": ("training", "mean")}
 CASES = {
     # name: (cfg overrides, batches [(tag, original image sizes, seq_len, padding_side)])
     "llava_slim_bt": (dict(hidden_size=512, intermediate_size=1024, num_heads=4, num_layers=2, clip_layers=2),
@@ -126,6 +128,20 @@ def run_case(name, refmods):
                  "S": batch["input_ids"].shape[1], "seconds": dt, "reward": reward.float().clone(),
                  "taps": {"inputs_embeds": sample(hs[0]), "hidden_0": sample(hs[1]), "last_hidden": sample(hs[-1])},
                  "last_hidden_eos": hs[-1][torch.arange(len(hw_list)), eos, :64].float().clone()}
+        # attributes custom_forward reads (rw_model_general_preference.py:327-333, 398-448), set on the reference model
+        entry["attrs"] = {}
+        for key, attrs in ATTR_VARIANTS.items():
+            if key not in ATTR_CASES.get(name, ()):
+                continue
+            saved = {k: getattr(model, k) for k in attrs}
+            for k, v in attrs.items():
+                setattr(model, k, v)
+            with torch.no_grad():
+                r2, _ = model.custom_forward(inputs_batch=batch)
+            for k, v in saved.items():
+                setattr(model, k, v)
+            entry["attrs"][key] = r2.float().clone()
+            print(f"    {key}: {r2.flatten().tolist()}", flush=True)
         fixture["batches"].append(entry)
         rewards[tag] = reward
     prob = ral.preference_compute(args, rewards["c"], rewards["r"])

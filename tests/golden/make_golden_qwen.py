@@ -41,6 +41,8 @@ SEED_W, SEED_X = 1234, 7
 
 SLIM = dict(hidden_size=512, intermediate_size=1024, num_heads=4, num_kv_heads=2, num_layers=2, vit_depth=4,
             vit_hidden=640, vit_intermediate=856, vit_heads=8, vit_fullatt=[1, 3], vocab_size=152064)
+ATTR_VARIANTS = {"training": {"training": True}, "mean": {"mean_hidden_state": True}}
+ATTR_CASES = {"qwen_slim_bt": ("training", "mean"), "qwen_slim_gpm": ("training",)}
 CASES = {
     # name: (cfg overrides, batches [(tag, (h, w) patch grids, seq_len, padding_side)])
     "qwen_slim_bt": (dict(SLIM), [("c", [(16, 24), (22, 10)], None, "left"), ("r", [(8, 8), (34, 18)], None, "left")]),
@@ -181,6 +183,20 @@ def run_case(name, refmods):
                  "taps": {"image_embeds": sample(vis), "inputs_embeds": sample(hs[0]), "hidden_0": sample(hs[1]),
                           "last_hidden": sample(hs[-1])},
                  "last_hidden_eos": hs[-1][torch.arange(len(grids)), eos, :64].float().clone(), "n_hidden": len(hs)}
+        # attributes custom_forward reads (rw_model_general_preference.py:327-333, 398-448), set on the reference model
+        entry["attrs"] = {}
+        for key, attrs in ATTR_VARIANTS.items():
+            if key not in ATTR_CASES.get(name, ()):
+                continue
+            saved = {k: getattr(model, k) for k in attrs}
+            for k, v in attrs.items():
+                setattr(model, k, v)
+            with torch.no_grad():
+                r2, _ = model.custom_forward(inputs_batch=batch)
+            for k, v in saved.items():
+                setattr(model, k, v)
+            entry["attrs"][key] = r2.float().clone()
+            print(f"    {key}: {r2.flatten().tolist()}", flush=True)
         fixture["batches"].append(entry)
         rewards[tag] = reward
     prob = ral.preference_compute(args, rewards["c"], rewards["r"])

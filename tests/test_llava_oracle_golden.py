@@ -29,6 +29,14 @@ def test_llava_oracle_matches_reference(case):
         rewards[entry["tag"]] = r
         assert r.shape == entry["reward"].shape
         assert (r - entry["reward"]).abs().max().item() < TOL
+        # `training` / `mean_hidden_state` set on the reference model object (rw_model_general_preference.py:327-333)
+        for key, g in entry.get("attrs", {}).items():
+            if key == "training" and entry["padding_side"] == "right":
+                continue  # position S-1 is a padded row there: not defined behaviour (differs between attention paths)
+            kw = {"training": dict(training=True), "mean": dict(mean_hidden_state=True)}[key]
+            with torch.no_grad():
+                r2 = O.custom_forward(P, cfg, batch, **kw)
+            assert r2.shape == g.shape and (r2 - g).abs().max().item() < TOL, (key, r2, g)
         for k in ("inputs_embeds", "hidden_0", "last_hidden"):
             t, g = taps[k], entry["taps"][k]
             assert list(t.shape) == g["shape"], k
