@@ -337,10 +337,11 @@ def main():
         value = pairs / (ms_dev / 1e3)
         e2e_value = pairs / (ms_e2e / 1e3)
         # dominant kernel: decoder gate_up GEMM (tcgen05, SWIGLU epilogue), 32 launches per forward
-        M = PAIRS_PER_STEP * SEQ_LEN
+        # rows per launch = the valid (un-padded) tokens of the 32 samples of a forward: the decoder runs on packed rows
         K = cfg.hidden_size + (cfg.lora_rank if cfg.use_lora else 0)
-        flops = 2.0 * M * (2 * cfg.intermediate_size) * K
-        durs = [s.elapsed_time(e) for s, e in prof["gate_up"]]
+        durs = [s.elapsed_time(e) for s, e, _ in prof["gate_up"]]
+        rows = [m for _, _, m in prof["gate_up"]]
+        flops = 2.0 * (sum(rows) / max(len(rows), 1)) * (2 * cfg.intermediate_size) * K   # mean per launch
         ach = flops / (sum(durs) / len(durs) * 1e-3) / 1e12 if durs else None
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r01_gate_up_traffic.json")
@@ -361,7 +362,8 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "pair::gemm_pair_kernel<256,SWIGLU> (tcgen05 cta_group::2; decoder gate_up_proj + LoRA-B)",
                          "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": (ach / peaks["bf16_sustained"]) if ach else None, "traffic": traffic,
-                         "launches_timed": len(durs), "flops_per_launch": flops, "peak_source": peaks["source"]},
+                         "launches_timed": len(durs), "flops_per_launch": flops,
+                         "rows_per_launch": (sum(rows) / len(rows)) if rows else None, "peak_source": peaks["source"]},
             "step_roofline": {"tflop_per_pair": TFLOP_PER_PAIR,
                               "achieved_tflops_per_gpu": value / world * TFLOP_PER_PAIR,
                               "frac_of_sustained": value / world * TFLOP_PER_PAIR / peaks["bf16_sustained"],

@@ -34,6 +34,11 @@ class RewardEngine:
         # last-valid-token row of every sample is read by the head, so o_proj / post-norm / MLP of that layer run on
         # those B rows. Off while intermediates are being captured (taps) so tests can compare both forms.
         self.last_layer_rows = True
+        # Output-identical shortcut: the decoder runs on the VALID rows only, packed back to
+        # back (padded positions never reach the head; every kernel of the decoder is row-wise except the attention,
+        # which already works on [start, start+len) of each sample and has a packed-sequence layout). Plain eval path
+        # with a tcgen05 attention only; off while intermediates are captured.
+        self.pack_rows = True
 
     # ------------------------------------------------------------------ helpers
     def buf(self, name: str, shape, dtype=torch.bfloat16) -> torch.Tensor:
@@ -102,7 +107,8 @@ class RewardEngine:
         self._tap("clip_out", x)
         return x
 
-    def _decoder(self, hid, B: int, S: int, pos, seq_start, seq_len, cos_tab, sin_tab, eos_row=None, n_layers=None):
+    def _decoder(self, hid, B: int, S: int, pos, seq_start, seq_len, cos_tab, sin_tab, eos_row=None, n_layers=None,
+                 packed=None):
         """Pre-norm decoder layers in place on hid [B*S, H] (Phi3DecoderLayer, modeling_phi3_v.py:1130-1205; the
         Llama layers of the LLaVA-v1.6 branch have the same dataflow). LoRA ranks come from the packed weights:
         the K-extension of a fused projection is the stack of its branches' ranks (weights.py).
@@ -111,17 +117,21 @@ class RewardEngine:
         layers (the reference's `layer_id` attribute: hidden_states[layer_id], rw_model_general_preference.py:349-352)."""
         cfg, w = self.cfg, self.w
         layers = w.layers if n_layers is None else w.layers[:n_layers]
-        M, H, I = B * S, cfg.hidden_size, cfg.intermediate_size
+        H, I = cfg.hidden_size, cfg.intermediate_size
+        # packed = (seq_base [B] int32, rows, longest sequence): hid holds the valid rows of sample b at
+        # [seq_base[b], +seq_len[b]); buffers keep the B*S capacity so ragged batches do not re-allocate
+        cap = B * S
+        M = packed[1] if packed is not None else cap
         lw0 = w.layers[0] if w.layers else {}
         rq, ro, rg, rd = (lw0[k].shape[0] if k in lw0 else 0 for k in ("qkv_a", "o_a", "gu_a", "dn_a"))
-        xn = self.buf("dec_xn", (M, H + max(rq, rg)))
+        xn = self.buf("dec_xn", (cap, H + max(rq, rg)))[:M]
         nh, hd = cfg.num_heads, cfg.head_dim
         nkv = getattr(cfg, "num_kv_heads", nh)      # grouped-query attention (Qwen2 decoder): k/v are nkv*hd wide
         kvw = nkv * hd
         QW = H + 2 * kvw
-        dqkv = self.buf("dec_qkv", (M, QW))
-        dao = self.buf("dec_ao", (M, H + ro))
-        gg = self.buf("dec_g", (M, I + rd))
+        dqkv = self.buf("dec_qkv", (cap, QW))[:M]
+        dao = self.buf("dec_ao", (cap, H + ro))[:M]
+        gg = self.buf("dec_g", (cap, I + rd))[:M]
         att_scale = 1.0 / math.sqrt(cfg.head_dim)
         for li, lw in enumerate(layers):
             ops.rmsnorm(hid, lw["in_ln"], xn, M, H, cfg.rms_eps)
@@ -134,7 +144,10 @@ class RewardEngine:
             else:
                 ops.gemm_rope(xn, lw["qkv_w"], dqkv, M, QW, H + rq, pos, cos_tab, sin_tab, H + kvw, hd,
                               L.GEMM_SIMT if self.gemm_impl == L.GEMM_SIMT else L.GEMM_TCGEN05)
-            if nkv != nh:
+            if packed is not None:
+                ops.attention_ex(dqkv, dqkv[:, H:], dqkv[:, H + kvw:], dao, QW, H + ro, M, B, packed[2], packed[0], None,
+                                 seq_len, nh, nkv, hd, True, att_scale, self.attn_impl)
+            elif nkv != nh:
                 ops.attention_ex(dqkv, dqkv[:, H:], dqkv[:, H + kvw:], dao, QW, H + ro, M, B, S, None, seq_start,
                                  seq_len, nh, nkv, hd, True, att_scale, self.attn_impl)
             else:
@@ -171,7 +184,7 @@ class RewardEngine:
             self._gemm(xn, lw["gu_w"], gg, M, 2 * I, H + rg, L.EPI_SWIGLU)
             if self.profile is not None:
                 ev[1].record()
-                self.profile["gate_up"].append(ev)
+                self.profile["gate_up"].append(ev + (M,))   # rows of this launch (packed valid rows or B*S)
             if rd:
                 self._gemm(gg, lw["dn_a"], gg[:, I:], M, rd, I)
             self._gemm(gg, lw["dn_w"], hid, M, H, I + rd, L.EPI_RESIDUAL, None, hid)
@@ -219,6 +232,31 @@ class RewardEngine:
         hs = [taps["inputs_embeds"]] + [taps[f"hidden_{i}"] for i in range(n - 1)] + [last]
         hs = tuple(t.view(B, S, H) for t in hs) + (vis.view(B, max_nv, H),)
         return BaseModelOutputWithPast(last_hidden_state=hs[-2], past_key_values=None, hidden_states=hs, attentions=None)
+
+    def _pack_valid_rows(self, hid, meta_h, B: int, S: int, pos_from_zero: bool):
+        """Gather the valid rows of hid [B*S, H] back to back
+        -> (hid_p [rows, H], pos_p, seq_base, eos_p, rows, longest, row index of every packed row).
+        Positions of the valid tokens are 0..len-1 for position_ids = cumsum(mask) - 1 (phi3v) and the slot index for
+        position_ids = arange(S) (llava); the index / position vectors are built on the host from the token-plan
+        record that is already there and go up in one copy."""
+        H = self.cfg.hidden_size
+        start, length = meta_h[:B].astype(np.int64), meta_h[B:2 * B].astype(np.int64)
+        base = np.concatenate([[0], np.cumsum(length)[:-1]])
+        rows = int(length.sum())
+        idx = np.concatenate([b * S + start[b] + np.arange(length[b]) for b in range(B)])
+        posv = np.concatenate([(0 if pos_from_zero else start[b]) + np.arange(length[b]) for b in range(B)])
+        host = torch.from_numpy(np.concatenate([idx, posv, base, base + length - 1]).astype(np.int32))
+        dev = self.buf("pack_plan", (2 * B * S + 2 * B,), torch.int32)[: host.numel()]
+        dev.copy_(host.pin_memory(), non_blocking=True)
+        idx_d, pos_d = dev[:rows], dev[rows:2 * rows]
+        base_d, eos_d = dev[2 * rows:2 * rows + B], dev[2 * rows + B:]
+        hid_p = self.buf("hidden_packed", (B * S, H))[:rows]
+        ops.gather_rows(hid, idx_d, hid_p, rows, H)
+        return hid_p, pos_d, base_d, eos_d, rows, int(length.max()), idx_d
+
+    def _can_pack(self, meta_h, B: int, S: int, last_position: bool, mean_pool: bool) -> bool:
+        return (self.pack_rows and self.taps is None and not last_position and not mean_pool and
+                self.attn_impl != L.ATTN_MMA_SYNC and int(meta_h[B:2 * B].sum()) < B * S)
 
     def _resolve_layer_id(self, layer_id):
         """-> (decoder layers to run, apply the final norm). The reference takes `last_hidden_state` for layer_id 32 and
@@ -369,8 +407,13 @@ class RewardEngine:
         # 5. decoder
         cos_tab, sin_tab = self.rope_tables(max(S, 2), max_len > cfg.original_max_position_embeddings)
         head_row = self._head_rows(eos_row, B, S, last_position)
-        hid_e = self._decoder(hid, B, S, pos, seq_start, seq_len, cos_tab, sin_tab, None if mean_pool else head_row,
-                              n_layers=n_run)
+        if self._can_pack(meta_h, B, S, last_position, mean_pool):
+            hid, pos_p, base_p, head_row, rows_p, longest, _ = self._pack_valid_rows(hid, meta_h, B, S, True)
+            hid_e = self._decoder(hid, B, S, pos_p, None, seq_len, cos_tab, sin_tab, head_row, n_layers=n_run,
+                                  packed=(base_p, rows_p, longest))
+        else:
+            hid_e = self._decoder(hid, B, S, pos, seq_start, seq_len, cos_tab, sin_tab,
+                                  None if mean_pool else head_row, n_layers=n_run)
         if mean_pool:
             reward = self._mean_head(hid, mask, B, S, final_norm, img, plan_h, max_nv)
             self.launches = L.launch_count() - launches0
@@ -496,7 +539,14 @@ class LlavaNextRewardEngine(RewardEngine):
         # 5. decoder
         cos_tab, sin_tab = self.rope_tables(max(S, 2))
         head_row = self._head_rows(eos_row, B, S, last_position)
-        hid_e = self._decoder(hid, B, S, pos, seq_start, seq_len, cos_tab, sin_tab, None if mean_pool else head_row)
+        if self._can_pack(meta_h, B, S, last_position, mean_pool):
+            # position_ids = arange(S) in this branch: a valid token keeps its slot index as position
+            hid, pos_p, base_p, head_row, rows_p, longest, _ = self._pack_valid_rows(hid, meta_h, B, S, False)
+            hid_e = self._decoder(hid, B, S, pos_p, None, seq_len, cos_tab, sin_tab, head_row,
+                                  packed=(base_p, rows_p, longest))
+        else:
+            hid_e = self._decoder(hid, B, S, pos, seq_start, seq_len, cos_tab, sin_tab,
+                                  None if mean_pool else head_row)
         if mean_pool:   # the reference has no SkipCA arm for this backbone: final norm, masked mean, value head
             reward = self._mean_head(hid, mask, B, S, True, cross_attention=False)
             self.launches = L.launch_count() - launches0
@@ -722,7 +772,18 @@ class QwenVLRewardEngine(RewardEngine):
         if mean_pool and ca:
             raise NotImplementedError("mean_hidden_state together with the qwen SkipCA arm")
         head_row = self._head_rows(eos_row, B, S, last_position)
-        hid_e = self._decoder(hid, B, S, None, seq_start, seq_len, cos_tok, sin_tok, None if mean_pool else head_row)
+        if self._can_pack(meta_h, B, S, last_position, mean_pool):
+            # per-token M-RoPE rows travel with their tokens: the same gather on the cos / sin tables
+            hid, _, base_p, head_row, rows_p, longest, idx_p = self._pack_valid_rows(hid, meta_h, B, S, True)
+            cos_p = self.buf("cos_tok_packed", (M, half))[:rows_p]
+            sin_p = self.buf("sin_tok_packed", (M, half))[:rows_p]
+            ops.gather_rows(cos_tok, idx_p, cos_p, rows_p, half)
+            ops.gather_rows(sin_tok, idx_p, sin_p, rows_p, half)
+            hid_e = self._decoder(hid, B, S, None, None, seq_len, cos_p, sin_p, head_row,
+                                  packed=(base_p, rows_p, longest))
+        else:
+            hid_e = self._decoder(hid, B, S, None, seq_start, seq_len, cos_tok, sin_tok,
+                                  None if mean_pool else head_row)
         if mean_pool:
             reward = self._mean_head(hid, mask, B, S, True, cross_attention=False)
             self.launches = L.launch_count() - launches0

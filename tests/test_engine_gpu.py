@@ -546,3 +546,44 @@ def test_device_prefetcher_feeds_the_eval_loop(tmp_path_factory):
     assert blocking["chosen_rewards"] == prefetched["chosen_rewards"]
     assert blocking["reject_rewards"] == prefetched["reject_rewards"]
     assert (blocking["probs"] == prefetched["probs"]).all()
+
+
+@pytest.mark.parametrize("case", ["slim_gpm", "slim_bt"])
+def test_packed_valid_rows_are_output_identical(case, tmp_path_factory):
+    """engine.pack_rows (product default): the decoder runs on the valid rows only, packed back to back, with the
+    packed-sequence attention layout. Every decoder kernel is row-wise and the attention walks the same K/V blocks from
+    the start of each sample in both layouts, so the rewards must be BIT-identical to the slot layout - for left and
+    right padding, mixed lengths and a batch without any padding (where packing switches itself off)."""
+    from llava_reward_b200.synth import synth_batch
+    fx = load_fixture(case)
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    eng = model.engine
+    batches = [fixture_batch(fx, e, cfg, device="cuda") for e in fx["batches"]]
+    ids, mask, pix, sizes = synth_batch(cfg, 3, (336, 672), 900, seed=91, tag="pk", device="cuda",
+                                        image_hw_list=[(336, 672), (672, 672), (336, 336)], text_len_range=(3, 90))
+    batches.append((ids, mask, pix, sizes))
+    # the same samples right-padded: roll every row so that its valid run starts at column 0
+    S = ids.shape[1]
+    lens = mask.sum(1)
+    ids_r, mask_r = ids.clone(), mask.clone()
+    for b in range(ids.shape[0]):
+        n = int(lens[b])
+        ids_r[b] = torch.cat([ids[b, S - n:], ids[b, :S - n]])
+        mask_r[b] = torch.cat([mask[b, S - n:], mask[b, :S - n]])
+    batches.append((ids_r, mask_r, pix, sizes))
+    one = synth_batch(cfg, 1, (336, 336), None, seed=92, tag="np", device="cuda")   # no padding at all
+    batches.append(one)
+    try:
+        for i, (ids, mask, pix, sizes) in enumerate(batches):
+            eng.pack_rows = True
+            rp = model.custom_forward(ids, mask, pix, sizes)[0].clone()
+            n_packed = eng.launches
+            eng.pack_rows = False
+            rs = model.custom_forward(ids, mask, pix, sizes)[0].clone()
+            d = (rp.float() - rs.float()).abs().max().item()
+            print(f"{case} batch {i}: valid rows {int(mask.sum())} of {mask.numel()}, packed {rp.flatten().tolist()} "
+                  f"slot {rs.flatten().tolist()} |d| {d:.3g}, launches {n_packed} / {eng.launches}")
+            assert torch.equal(rp, rs)
+    finally:
+        eng.pack_rows = True
+    # left- and right-padded forms of the same samples agree as well (positions count from the first valid token)

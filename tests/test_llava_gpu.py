@@ -450,3 +450,26 @@ def test_llava_attribute_variants_vs_reference_golden(case, tmp_path_factory):
             assert err < REWARD_TOL + 3.0 * floor, key
             checked += 1
     assert checked >= 1
+
+
+@pytest.mark.parametrize("case", ["llava_slim_bt", "llava_slim_gpm"])
+def test_llava_packed_valid_rows_are_output_identical(case, tmp_path_factory):
+    """engine.pack_rows (the decoder on the valid rows only, packed-sequence attention) against the slot layout:
+    bit-identical rewards on the golden batches (left and right padding, mixed lengths)."""
+    fx = load_fixture(case)
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    eng = model.engine
+    try:
+        for entry in fx["batches"]:
+            batch = to_dev(llava_fixture_batch(fx, entry, cfg))
+            eng.pack_rows = True
+            rp = model.custom_forward(inputs_batch=batch)[0].clone()
+            n_packed = eng.launches
+            eng.pack_rows = False
+            rs = model.custom_forward(inputs_batch=batch)[0].clone()
+            m = batch["attention_mask"]
+            print(f"{case}/{entry['tag']} ({entry['padding_side']} padding): valid rows {int(m.sum())} of {m.numel()}, "
+                  f"|d| {(rp.float() - rs.float()).abs().max().item():.3g}, launches {n_packed} / {eng.launches}")
+            assert torch.equal(rp, rs)
+    finally:
+        eng.pack_rows = True

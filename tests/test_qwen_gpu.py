@@ -669,3 +669,26 @@ def test_qwen_attribute_variants_vs_reference_golden(case, tmp_path_factory):
                 model.custom_forward(inputs_batch=batch)
         finally:
             model.mean_hidden_state = None
+
+
+@pytest.mark.parametrize("case", ["qwen_slim_bt", "qwen_slim_gpm", "qwen_wide_gpm"])
+def test_qwen_packed_valid_rows_are_output_identical(case, tmp_path_factory):
+    """engine.pack_rows (the decoder on the valid rows only, packed-sequence attention) against the slot layout:
+    bit-identical rewards on the golden batches (left and right padding, mixed lengths)."""
+    fx = load_fixture(case)
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    eng = model.engine
+    try:
+        for entry in fx["batches"]:
+            batch = to_dev(qwen_fixture_batch(fx, entry, cfg))
+            eng.pack_rows = True
+            rp = model.custom_forward(inputs_batch=batch)[0].clone()
+            n_packed = eng.launches
+            eng.pack_rows = False
+            rs = model.custom_forward(inputs_batch=batch)[0].clone()
+            m = batch["attention_mask"]
+            print(f"{case}/{entry['tag']} ({entry['padding_side']} padding): valid rows {int(m.sum())} of {m.numel()}, "
+                  f"|d| {(rp.float() - rs.float()).abs().max().item():.3g}, launches {n_packed} / {eng.launches}")
+            assert torch.equal(rp, rs)
+    finally:
+        eng.pack_rows = True

@@ -192,7 +192,7 @@ def main():
         M = B * S
         K = cfg.hidden_size + (2 * cfg.lora_rank if cfg.use_lora else 0)
         flops = 2.0 * M * (2 * cfg.intermediate_size) * K
-        durs = [s.elapsed_time(e) for s, e in prof["gate_up"]]
+        durs = [s.elapsed_time(e) for s, e, _ in prof["gate_up"]]
         ach = flops / (sum(durs) / len(durs) * 1e-3) / 1e12 if durs else None
         line = {
             "metric": "text-image pairs scored/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": a.steps,
