@@ -12,6 +12,8 @@ try:
 except Exception as e: print("parse fail", e)
 PY
 tail -3 gpurun_out/bench.err
+NL=$(python -c "import json;d=json.loads(open('gpurun_out/bench.log').read().strip().splitlines()[-1]);print(d['gpu_launches']//d['steps'])" 2>/dev/null || echo 1059)
+echo "launches per step: $NL"
 K='regex:^(gemm_|attn_|rmsnorm|layernorm|clip_|token_plan|rope_su|hd_gather|embed_scatter|skipca|preference|gather_rows)'
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -s 1057 -c 1057 --csv --log-file gpurun_out/launches.csv python bench.py --profile-run > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches exit $?"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -s $NL -c $NL --csv --log-file gpurun_out/launches.csv python bench.py --profile-run > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches exit $?"
 python tools/launch_summary.py gpurun_out/launches.csv gpurun_out/launches.md | head -30
