@@ -303,3 +303,21 @@ def qwen_window_plan(grid_thw, merge: int = 2, window: int = 112, patch: int = 1
     return dict(window_index=widx.astype(np.int32), src_row=src_row.astype(np.int32),
                 pos_hw=pos[src_row].astype(np.int32), win_cu=np.asarray(win_cu, dtype=np.int32),
                 img_cu=np.asarray(img_cu, dtype=np.int32))
+
+
+def packed_row_plan(seq_start, seq_len, S: int, pos_from_zero: bool):
+    """Host-side index plan of the packed decoder layout (engine.pack_rows): sample b's valid run
+    [seq_start[b], +seq_len[b]) of the slot layout [B, S] moves to rows [base[b], +seq_len[b]).
+    -> (row_index [rows] into the slot layout, position [rows], base [B], last_row [B]) as int32 numpy arrays.
+    Positions count from the first valid token when position_ids = cumsum(mask) - 1 (phi3v, and the order in which the
+    per-token M-RoPE rows of the qwen branch are gathered) or keep the slot index when position_ids = arange(S) (llava)."""
+    import numpy as np
+    start = np.asarray(seq_start, dtype=np.int64)
+    length = np.asarray(seq_len, dtype=np.int64)
+    B = start.shape[0]
+    if (length < 0).any() or (start < 0).any() or (start + length > S).any():
+        raise ValueError("valid runs must lie inside [0, S)")
+    base = np.concatenate([[0], np.cumsum(length)[:-1]]) if B else np.zeros(0, dtype=np.int64)
+    idx = np.concatenate([b * S + start[b] + np.arange(length[b]) for b in range(B)]) if B else np.zeros(0, np.int64)
+    pos = np.concatenate([(0 if pos_from_zero else start[b]) + np.arange(length[b]) for b in range(B)]) if B else idx
+    return idx.astype(np.int32), pos.astype(np.int32), base.astype(np.int32), (base + length - 1).astype(np.int32)

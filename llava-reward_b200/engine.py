@@ -15,7 +15,7 @@ import torch
 
 from . import _lib as L
 from . import ops
-from .config import RewardConfig, num_image_tokens, qwen_window_plan
+from .config import RewardConfig, num_image_tokens, packed_row_plan, qwen_window_plan
 from .weights import PackedWeights
 
 
@@ -240,19 +240,16 @@ class RewardEngine:
         position_ids = arange(S) (llava); the index / position vectors are built on the host from the token-plan
         record that is already there and go up in one copy."""
         H = self.cfg.hidden_size
-        start, length = meta_h[:B].astype(np.int64), meta_h[B:2 * B].astype(np.int64)
-        base = np.concatenate([[0], np.cumsum(length)[:-1]])
-        rows = int(length.sum())
-        idx = np.concatenate([b * S + start[b] + np.arange(length[b]) for b in range(B)])
-        posv = np.concatenate([(0 if pos_from_zero else start[b]) + np.arange(length[b]) for b in range(B)])
-        host = torch.from_numpy(np.concatenate([idx, posv, base, base + length - 1]).astype(np.int32))
+        idx, posv, base, last = packed_row_plan(meta_h[:B], meta_h[B:2 * B], S, pos_from_zero)
+        rows = int(idx.shape[0])
+        host = torch.from_numpy(np.concatenate([idx, posv, base, last]))
         dev = self.buf("pack_plan", (2 * B * S + 2 * B,), torch.int32)[: host.numel()]
         dev.copy_(host.pin_memory(), non_blocking=True)
         idx_d, pos_d = dev[:rows], dev[rows:2 * rows]
         base_d, eos_d = dev[2 * rows:2 * rows + B], dev[2 * rows + B:]
         hid_p = self.buf("hidden_packed", (B * S, H))[:rows]
         ops.gather_rows(hid, idx_d, hid_p, rows, H)
-        return hid_p, pos_d, base_d, eos_d, rows, int(length.max()), idx_d
+        return hid_p, pos_d, base_d, eos_d, rows, int(meta_h[B:2 * B].max()), idx_d
 
     def _can_pack(self, meta_h, B: int, S: int, last_position: bool, mean_pool: bool) -> bool:
         return (self.pack_rows and self.taps is None and not last_position and not mean_pool and

@@ -53,3 +53,25 @@ def test_feed_map_tensors_keeps_structure():
     assert isinstance(out[2], BatchFeature) and torch.equal(out[2]["input_ids"], b["input_ids"] + 1)
     with pytest.raises(RuntimeError):
         DevicePrefetcher([], device="cpu")
+
+
+def test_packed_row_plan():
+    """config.packed_row_plan: the host index plan of the packed decoder layout (left / right padding, full rows)."""
+    import numpy as np
+    import pytest
+    from llava_reward_b200.config import packed_row_plan
+    S = 8
+    start, length = [3, 0, 0, 6], [5, 8, 2, 2]          # left-padded, full, right-padded, left-padded
+    idx, pos, base, last = packed_row_plan(start, length, S, True)
+    assert idx.dtype == np.int32 and idx.tolist() == [3, 4, 5, 6, 7] + list(range(8, 16)) + [16, 17] + [30, 31]
+    assert pos.tolist() == [0, 1, 2, 3, 4] + list(range(8)) + [0, 1] + [0, 1]
+    assert base.tolist() == [0, 5, 13, 15] and last.tolist() == [4, 12, 14, 16]
+    _, pos_slot, _, _ = packed_row_plan(start, length, S, False)   # position_ids = arange(S): keep the slot index
+    assert pos_slot.tolist() == [3, 4, 5, 6, 7] + list(range(8)) + [0, 1] + [6, 7]
+    mask = np.zeros((4, S), dtype=np.int64)
+    for b in range(4):
+        mask[b, start[b]:start[b] + length[b]] = 1
+    assert (np.flatnonzero(mask.reshape(-1)) == idx).all()            # exactly the valid positions, in order
+    assert ((np.cumsum(mask, 1) - 1)[mask == 1] == pos).all()         # position_ids = cumsum(mask) - 1 on them
+    with pytest.raises(ValueError):
+        packed_row_plan([5], [4], S, True)
