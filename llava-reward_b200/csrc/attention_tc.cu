@@ -30,6 +30,13 @@ namespace lr {
 // Optional in-kernel timeline (tools/attn_trace.py builds a separate .so with -DLR_ATTN_TRACE): clock64 stamps of
 // CTA (0,0,0) at the main pipeline events, [role][event][block] -> global buffer.
 #ifdef LR_ATTN_TRACE
+// per-CTA record {SM id, start ns, end ns, K/V blocks} of EVERY CTA (tools/attn_cta_times.py): occupancy timeline
+__device__ long long* g_attn_cta = nullptr;
+__device__ __forceinline__ long long attn_globaltimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ long long* g_attn_trace = nullptr;
 #define ATTN_TRACE(role, ev, j)                                                                     \
   do {                                                                                              \
@@ -191,6 +198,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     nblk[x] = (kv_end[x] - start + 127) / 128;
   }
   const int n = max(nblk[0], nblk[1]);
+#ifdef LR_ATTN_TRACE
+  long long cta_t0 = 0;
+  if (threadIdx.x == 0) cta_t0 = attn_globaltimer();
+#endif
 
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_qkv);
   if (warp == 1 && lane == 0) {
@@ -536,6 +547,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+#ifdef LR_ATTN_TRACE
+  if (threadIdx.x == 0 && g_attn_cta) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    const long long id = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z);
+    g_attn_cta[id * 4 + 0] = smid;
+    g_attn_cta[id * 4 + 1] = cta_t0;
+    g_attn_cta[id * 4 + 2] = attn_globaltimer();
+    g_attn_cta[id * 4 + 3] = nblk[0] + (NT == 2 ? nblk[1] : 0);
+  }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -641,5 +663,8 @@ int attention_tc_seg(const void* q, const void* k, const void* v, void* o, int l
 #ifdef LR_ATTN_TRACE
 extern "C" int lr_attn_trace_set(long long* buf) {
   return static_cast<int>(cudaMemcpyToSymbol(lr::g_attn_trace, &buf, sizeof(buf)));
+}
+extern "C" int lr_attn_cta_set(long long* buf) {
+  return static_cast<int>(cudaMemcpyToSymbol(lr::g_attn_cta, &buf, sizeof(buf)));
 }
 #endif
