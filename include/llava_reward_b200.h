@@ -119,6 +119,9 @@ int lr_clip_embed_ln(const void* patch, const void* class_emb, const void* pos_e
 #define LR_ATTN_TCGEN05_2TILE 3 /* tcgen05 kernel with two query tiles per CTA sharing K/V, one CTA per SM (slower on CLIP;
                                    at head_dim 128 the row sums live in registers and K/V are single-staged) */
 #define LR_ATTN_TCGEN05_1TILE 4 /* tcgen05 kernel, one query tile per CTA (= LR_ATTN_TCGEN05 for head_dim 64 / 96) */
+#define LR_ATTN_TCGEN05_MULTITILE 5 /* the one-tile pipeline walking several query tiles per CTA (causal: the pair
+                                       {nt-1-x, x}, every CTA nt+1 K/V blocks; otherwise up to 5 consecutive tiles): the
+                                       6.4 us per-CTA fixed cost is paid once per CTA instead of once per tile */
 #define LR_ATTN_TCGEN05_SPLIT 2 /* tcgen05 kernel with two softmax threads per query row (4 softmax warpgroups);
                                    measured slower than the default (the kernel is shared-memory-bandwidth bound) */
 int lr_attention_bf16(const void* q, const void* k, const void* v, void* o, int ld_qkv, int ld_o, int n_seq,

@@ -16,6 +16,7 @@ EPI_NONE, EPI_BIAS, EPI_BIAS_QUICKGELU, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_BIAS_RE
 EPI_BIAS_SWIGLU, EPI_BIAS_ROPE, EPI_BIAS_ROPE_F32 = 8, 9, 10
 GEMM_TCGEN05, GEMM_SIMT, GEMM_TCGEN05_PAIR, GEMM_TCGEN05_SINGLE = 0, 1, 2, 3
 ATTN_TCGEN05, ATTN_MMA_SYNC, ATTN_TCGEN05_SPLIT, ATTN_TCGEN05_2TILE, ATTN_TCGEN05_1TILE = 0, 1, 2, 3, 4
+ATTN_TCGEN05_MULTITILE = 5
 PLAN_STRIDE = 8
 PLAN_HCROP, PLAN_WCROP, PLAN_CROP_BASE, PLAN_ROW_BASE, PLAN_NV, PLAN_TOP, PLAN_LEFT = 0, 1, 2, 3, 4, 5, 6
 POS_FROM_MASK, POS_ARANGE = 0, 1

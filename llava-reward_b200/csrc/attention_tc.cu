@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(128 + 128 * NT * SPLIT, AttnTcCfg<HD, NT>::kOn
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o, int ld_o, int rows_per_seq,
                const int* __restrict__ seq_base, const int* __restrict__ seq_start, const int* __restrict__ seq_len,
                int q_col0, int k_col0, int v_col0, int kv_group, float scale_log2,
-               const int* __restrict__ row_lo, const int* __restrict__ row_hi) {
+               const int* __restrict__ row_lo, const int* __restrict__ row_hi, int tile_mode) {
   using Cfg = AttnTcCfg<HD, NT>;
   constexpr int NS = Cfg::kStages;
   constexpr int NA = Cfg::kAtoms;
@@ -170,8 +170,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int seq = blockIdx.z, head = blockIdx.y;
   const int kv_head = head / kv_group;  // grouped-query attention: kv_group query heads share one K/V head
-  const int qt = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
-  const int m0 = qt * 128 * NT;
+  // Query tiles of this CTA (the per-CTA fixed cost - launch, TMEM allocation, barrier setup, pipeline fill and drain,
+  // 6.4 us on the causal decoder shape against 2.2 us per K/V block - is paid once per CTA, not once per tile):
+  //   tile_mode 0: the one tile blockIdx.x names (causal: heaviest first);
+  //   tile_mode 1 (causal): the pair {nt-1-x, x} - every CTA walks nt+1 K/V blocks, so the grid is balanced as well;
+  //   tile_mode k >= 2: the k consecutive tiles x*k .. x*k+k-1.
+  // Barrier phases run on counters of K/V blocks / tiles processed by this CTA, so they carry across tiles.
+  const int nt_total = (rows_per_seq + 128 * NT - 1) / (128 * NT);
+  int n_tiles = 1;
+  if (tile_mode == 1) n_tiles = (int(blockIdx.x) < nt_total - 1 - int(blockIdx.x)) ? 2 : 1;
+  else if (tile_mode >= 2) n_tiles = min(tile_mode, nt_total - int(blockIdx.x) * tile_mode);
+  auto tile_qt = [&](int ti) -> int {
+    if (tile_mode == 0) return CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+    if (tile_mode == 1) return ti == 0 ? nt_total - 1 - int(blockIdx.x) : int(blockIdx.x);
+    return int(blockIdx.x) * tile_mode + ti;
+  };
+  int m0 = tile_qt(0) * 128 * NT;
   // slot layout: sequence s owns rows [s*rows_per_seq, +rows_per_seq), valid run [start, start+len);
   // packed layout (seq_base != NULL): sequence s owns exactly rows [seq_base[s], +seq_len[s]), rows_per_seq = max len
   // segment layout (row_lo != NULL; non-causal, NT == 1): ONE buffer of rows_per_seq rows cut into short segments (the
@@ -188,16 +202,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     end = row_hi[min(m0 + 128 * NT, rows_per_seq) - 1];
   }
 
-  int lo[2], hi[2], nblk[2], kv_end[2];
+  int lo[2], hi[2], nblk[2], kv_end[2], n;
+  auto set_tile = [&](int ti) {   // every role calls this with the same ti sequence
+    m0 = tile_qt(ti) * 128 * NT;
 #pragma unroll
-  for (int x = 0; x < 2; ++x) {
-    lo[x] = max(m0 + x * 128, start);
-    hi[x] = min(min(m0 + x * 128 + 128, end), rows_per_seq);
-    const bool valid = lo[x] < hi[x] && x < NT;
-    kv_end[x] = valid ? (CAUSAL ? min(end, hi[x]) : end) : start;
-    nblk[x] = (kv_end[x] - start + 127) / 128;
-  }
-  const int n = max(nblk[0], nblk[1]);
+    for (int x = 0; x < 2; ++x) {
+      lo[x] = max(m0 + x * 128, start);
+      hi[x] = min(min(m0 + x * 128 + 128, end), rows_per_seq);
+      const bool valid = lo[x] < hi[x] && x < NT;
+      kv_end[x] = valid ? (CAUSAL ? min(end, hi[x]) : end) : start;
+      nblk[x] = (kv_end[x] - start + 127) / 128;
+    }
+    n = max(nblk[0], nblk[1]);
+  };
+  set_tile(0);
 #ifdef LR_ATTN_TRACE
   long long cta_t0 = 0;
   if (threadIdx.x == 0) cta_t0 = attn_globaltimer();
@@ -247,34 +265,44 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
   }
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0 && n > 0) {
-      const uint32_t q_bytes = (nblk[0] > 0 ? TILE : 0) + (nblk[1] > 0 ? TILE : 0);
-      mbar_arrive_expect_tx(q_full, q_bytes);
+    if (lane == 0) {
+      int g = 0;  // K/V blocks of the earlier tiles of this CTA (ring positions and phases continue across tiles)
+      for (int ti = 0; ti < n_tiles; ++ti) {
+        set_tile(ti);
+        if (n == 0) continue;
+        // K and V rings advance independently (the MMA thread consumes them out of lock-step)
+        int kj = 0, vj = 0;
+        while (kj < n || vj < n) {
+          if (kj < n && mbar_test_wait(&k_empty[(g + kj) % NS], (((g + kj) / NS) & 1) ^ 1)) {
+            if (kj == 0) {
+              // Q of this tile. For a later tile (single-stage ring only) the wait above also says that every S MMA
+              // of the previous tile - the only readers of the Q buffer - has retired.
+              const uint32_t q_bytes = (nblk[0] > 0 ? TILE : 0) + (nblk[1] > 0 ? TILE : 0);
+              mbar_arrive_expect_tx(q_full, q_bytes);
 #pragma unroll
-      for (int x = 0; x < 2; ++x)
-        if (nblk[x] > 0)
-          for (int a = 0; a < NA; ++a)
-            tma_load_2d(sQ + x * TILE + a * kAtomBytes, &tm_qkv, q_full, q_col0 + head * HD + a * 32,
-                        slot_row0 + m0 + x * 128);
-      // K and V rings advance independently (the MMA thread consumes them out of lock-step)
-      int kj = 0, vj = 0;
-      while (kj < n || vj < n) {
-        if (kj < n && mbar_test_wait(&k_empty[kj % NS], ((kj / NS) & 1) ^ 1)) {
-          const int s = kj % NS;
-          mbar_arrive_expect_tx(&k_full[s], TILE);
-          for (int a = 0; a < NA; ++a)
-            tma_load_2d(sK + s * TILE + a * kAtomBytes, &tm_qkv, &k_full[s], k_col0 + kv_head * HD + a * 32,
-                        slot_row0 + start + kj * 128);
-          ++kj;
+              for (int x = 0; x < 2; ++x)
+                if (nblk[x] > 0)
+                  for (int a = 0; a < NA; ++a)
+                    tma_load_2d(sQ + x * TILE + a * kAtomBytes, &tm_qkv, q_full, q_col0 + head * HD + a * 32,
+                                slot_row0 + m0 + x * 128);
+            }
+            const int s = (g + kj) % NS;
+            mbar_arrive_expect_tx(&k_full[s], TILE);
+            for (int a = 0; a < NA; ++a)
+              tma_load_2d(sK + s * TILE + a * kAtomBytes, &tm_qkv, &k_full[s], k_col0 + kv_head * HD + a * 32,
+                          slot_row0 + start + kj * 128);
+            ++kj;
+          }
+          if (vj < n && vj < kj && mbar_test_wait(&v_empty[(g + vj) % NS], (((g + vj) / NS) & 1) ^ 1)) {
+            const int s = (g + vj) % NS;
+            mbar_arrive_expect_tx(&v_full[s], TILE);
+            for (int a = 0; a < NA; ++a)
+              tma_load_2d(sV + s * VTILE + a * kAtomBytes, &tm_qkv, &v_full[s], v_col0 + kv_head * HD + a * 32,
+                          slot_row0 + start + vj * 128);
+            ++vj;
+          }
         }
-        if (vj < n && vj < kj && mbar_test_wait(&v_empty[vj % NS], ((vj / NS) & 1) ^ 1)) {
-          const int s = vj % NS;
-          mbar_arrive_expect_tx(&v_full[s], TILE);
-          for (int a = 0; a < NA; ++a)
-            tma_load_2d(sV + s * VTILE + a * kAtomBytes, &tm_qkv, &v_full[s], v_col0 + kv_head * HD + a * 32,
-                        slot_row0 + start + vj * 128);
-          ++vj;
-        }
+        g += n;
       }
     }
     __syncwarp();
@@ -286,8 +314,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     // registers, O_x += P_x(j) V_j the moment P_x(j) is in smem. A K (V) stage goes back to the producer when both
     // threads have arrived on its `empty` barrier (tcgen05.commit after the last MMA that reads it, or a plain arrive
     // for blocks a tile does not need).
-    if (lane == 0 && n > 0) {
+    if (lane == 0) {
       const int x = warp == 1 ? 0 : 1;
+      int g = 0, tq = 0;  // K/V blocks / non-empty tiles already processed by this CTA
+      for (int ti = 0; ti < n_tiles; ++ti) {
+      set_tile(ti);
+      if (n == 0) continue;
       const int nx = nblk[x];
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, HDX) | (1u << 16);  // B (= [V | 1]) is MN-major
@@ -313,8 +345,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         umma_commit(&v_empty[vs]);
       };
       if (nx > 0) {
-        mbar_wait(q_full, 0);
-        mbar_wait(&k_full[0], 0);
+        mbar_wait(q_full, tq & 1);
+        mbar_wait(&k_full[g % NS], (g / NS) & 1);
+        if (g > 0) mbar_wait(&s_free[x], (g - 1) & 1);  // the S row of the previous tile's last block has been read
         if (NT == 2 && x == 1 && nblk[0] > 0) {
           // Start tile B half a softmax period after tile A: both softmax warpgroups share the SM's 16 ex2/clk, and
           // the exponential phase is about half of an iteration, so in anti-phase each runs its exponentials alone.
@@ -324,27 +357,28 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
           }
         }
         tc_fence_after();
-        issue_s(0);
+        issue_s(g % NS);
         int s_next = 1, pv_next = 0;
         while (pv_next < nx) {
-          if (s_next < nx && mbar_test_wait(&s_free[x], (s_next - 1) & 1) &&
-              mbar_test_wait(&k_full[s_next % NS], (s_next / NS) & 1)) {
+          if (s_next < nx && mbar_test_wait(&s_free[x], (g + s_next - 1) & 1) &&
+              mbar_test_wait(&k_full[(g + s_next) % NS], ((g + s_next) / NS) & 1)) {
             tc_fence_after();
             ATTN_TRACE(0, x * 4 + 0, s_next - 1);
-            issue_s(s_next % NS);
+            issue_s((g + s_next) % NS);
             ++s_next;
           }
-          if (mbar_test_wait(&p_full[x], pv_next & 1) && mbar_test_wait(&v_full[pv_next % NS], (pv_next / NS) & 1)) {
+          if (mbar_test_wait(&p_full[x], (g + pv_next) & 1) &&
+              mbar_test_wait(&v_full[(g + pv_next) % NS], ((g + pv_next) / NS) & 1)) {
             tc_fence_after();
             ATTN_TRACE(0, x * 4 + 1, pv_next);
-            issue_pv(pv_next % NS, pv_next > 0);
+            issue_pv((g + pv_next) % NS, pv_next > 0);
             if (pv_next + 1 == nx) umma_commit(&o_final[x]);
             ATTN_TRACE(0, x * 4 + 2, pv_next);
             ++pv_next;
           }
         }
       }
-      for (int j = nx; j < n; ++j) {  // K/V blocks only the other tile reads: arrive in phase order
+      for (int j = nx; j < n; ++j) {  // K/V blocks only the other tile reads (NT == 2: one tile pair per CTA, g == 0)
         const int st = j % NS;
         if (j >= NS) {
           mbar_wait(&k_empty[st], ((j - NS) / NS) & 1);
@@ -352,6 +386,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         }
         mbar_arrive(&k_empty[st]);
         mbar_arrive(&v_empty[st]);
+      }
+      g += n;
+      ++tq;
       }
     }
     __syncwarp();
@@ -371,13 +408,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     const int h = (sw >> 2) % SPLIT;               // column half (SPLIT == 2)
     const int q = warp & 3;                        // TMEM lane quarter
     const int r = q * 32 + lane;                   // row inside the tile
-    const int row_abs = m0 + x * 128 + r;
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     uint8_t* prow = sP + x * kPBytes + r * 128;
+    const bool tr = (q == 0 && lane == 0 && h == 0);
+    int g = 0, tq = 0;  // K/V blocks / non-empty tiles already processed by this CTA (barrier phases)
+    for (int ti = 0; ti < n_tiles; ++ti) {
+    set_tile(ti);
+    const int row_abs = m0 + x * 128 + r;
     float m_ref = -INFINITY;
     float l_reg[4] = {0.f, 0.f, 0.f, 0.f};  // row sum kept in registers when there are no ones columns (!ONES)
     const int nx = nblk[x];
-    const bool tr = (q == 0 && lane == 0 && h == 0);
     int my_lo = 0, my_hi = 0;  // segment layout: this row's key range (absolute rows)
     if (seg && row_abs < rows_per_seq) {
       my_lo = row_lo[row_abs];
@@ -385,7 +425,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     }
     for (int j = 0; j < nx; ++j) {
       if (tr) ATTN_TRACE(1 + x, 0, j);
-      mbar_wait(&s_full[x], j & 1);
+      mbar_wait(&s_full[x], (g + j) & 1);
       tc_fence_after();
       if (tr) ATTN_TRACE(1 + x, 1, j);
       const int kv0 = start + j * 128;
@@ -451,7 +491,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       if (tr) ATTN_TRACE(1 + x, 3, j);
       // P_x buffer and O_x may be touched only after O_x += P_x(j-1) V_(j-1) has retired
       if (j > 0) {
-        mbar_wait(&pv_done[x], (j - 1) & 1);
+        mbar_wait(&pv_done[x], (g + j - 1) & 1);
         tc_fence_after();
         if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll 1
@@ -503,7 +543,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     const bool row_valid = row_abs >= lo[x] && row_abs < hi[x];
     bf16* orow = o + size_t(slot_row0 + row_abs) * ld_o + head * HD;
     if (nx > 0) {
-      mbar_wait(&o_final[x], 0);
+      mbar_wait(&o_final[x], tq & 1);
       tc_fence_after();
       float inv;
       if constexpr (!ONES) {
@@ -538,6 +578,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     } else if (row_in_slot && h == 0) {
 #pragma unroll 1
       for (int c = 0; c < HD / 8; ++c) *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(0, 0, 0, 0);
+    }
+    g += n;
+    if (n > 0) ++tq;
+    // the O accumulator and the P buffer of this tile are free again: the next tile's first P.V is issued only after
+    // these threads have arrived on p_full for it, i.e. after the tcgen05.ld of the epilogue above have completed
     }
   }
 
@@ -583,7 +628,7 @@ template <int HD, bool CAUSAL, int SPLIT, int NT>
 static int launch_attn_tc(const void* base, int total_rows, int ld_qkv, int q_col0, int k_col0, int v_col0, void* o,
                           int ld_o, int n_seq, int rows_per_seq, const int* seq_base, const int* seq_start,
                           const int* seq_len, int n_heads, int kv_group, float scale, cudaStream_t stream,
-                          const int* row_lo = nullptr, const int* row_hi = nullptr) {
+                          const int* row_lo = nullptr, const int* row_hi = nullptr, bool multi_tile = false) {
   using Cfg = AttnTcCfg<HD, NT>;
   EncodeTiledFn fn = attn_encode_fn();
   if (!fn) return LR_ERR_NO_DRIVER;
@@ -601,10 +646,22 @@ static int launch_attn_tc(const void* base, int total_rows, int ld_qkv, int q_co
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
-  dim3 grid((rows_per_seq + 128 * NT - 1) / (128 * NT), n_heads, n_seq);
+  // several query tiles per CTA (see the kernel): single-stage K/V ring only, not for the segment layout
+  const int nt = (rows_per_seq + 128 * NT - 1) / (128 * NT);
+  int tile_mode = 0, gx = nt;
+  if (multi_tile && NT == 1 && Cfg::kStages == 1 && row_lo == nullptr && nt > 1) {
+    if (CAUSAL) {
+      tile_mode = 1;                 // pairs {nt-1-x, x}
+      gx = (nt + 1) / 2;
+    } else {
+      tile_mode = nt < 5 ? nt : 5;   // up to 5 consecutive tiles (a whole 577-token CLIP crop)
+      gx = (nt + tile_mode - 1) / tile_mode;
+    }
+  }
+  dim3 grid(gx, n_heads, n_seq);
   kern<<<grid, 128 + 128 * NT * SPLIT, Cfg::kSmemBytes, stream>>>(tm, reinterpret_cast<bf16*>(o), ld_o, rows_per_seq, seq_base,
                                                       seq_start, seq_len, q_col0, k_col0, v_col0, kv_group,
-                                                      scale * 1.4426950408889634f, row_lo, row_hi);
+                                                      scale * 1.4426950408889634f, row_lo, row_hi, tile_mode);
   return lr_launch_status();
 }
 
@@ -623,6 +680,7 @@ int attention_tc(const void* q, const void* k, const void* v, void* o, int ld_qk
   if (head_dim == HD_ && bool(causal) == CAUSAL_) {                                    \
     if (split == 2) return launch_attn_tc<HD_, CAUSAL_, 2, 2>(LR_ATTN_ARGS);           \
     if (split == 3) return launch_attn_tc<HD_, CAUSAL_, 1, 1>(LR_ATTN_ARGS);           \
+    if (split == 4) return launch_attn_tc<HD_, CAUSAL_, 1, 1>(LR_ATTN_ARGS, nullptr, nullptr, true); \
     return launch_attn_tc<HD_, CAUSAL_, 1, 2>(LR_ATTN_ARGS);                           \
   }
   LR_ATTN_CASE(64, false)
@@ -630,7 +688,7 @@ int attention_tc(const void* q, const void* k, const void* v, void* o, int ld_qk
 #undef LR_ATTN_CASE
   if (head_dim == 96 && !causal) {  // Qwen2.5-VL vision tower (head_dim 80 zero-padded to 96): one tile per CTA only
     if (split == 2 || split == 1) return LR_ERR_BAD_ARG;
-    return launch_attn_tc<96, false, 1, 1>(LR_ATTN_ARGS);
+    return launch_attn_tc<96, false, 1, 1>(LR_ATTN_ARGS, nullptr, nullptr, split == 4);
   }
   if (head_dim == 128 && causal) {  // one CTA per SM either way (smem / TMEM, see AttnTcCfg); no split-softmax form
     if (split == 2) return LR_ERR_BAD_ARG;

@@ -211,7 +211,8 @@ def attn_ref(q, k, v, causal, scale, start=0, length=None):
     return out
 
 
-@pytest.mark.parametrize("impl", [L.ATTN_TCGEN05, L.ATTN_MMA_SYNC, L.ATTN_TCGEN05_SPLIT, L.ATTN_TCGEN05_2TILE])
+@pytest.mark.parametrize("impl", [L.ATTN_TCGEN05, L.ATTN_MMA_SYNC, L.ATTN_TCGEN05_SPLIT, L.ATTN_TCGEN05_2TILE,
+                                  L.ATTN_TCGEN05_1TILE, L.ATTN_TCGEN05_MULTITILE])
 @pytest.mark.parametrize("hd,heads,T,nseq,causal", [(64, 16, 577, 3, False), (96, 32, 700, 2, True),
                                                     (96, 4, 130, 3, True), (64, 2, 64, 1, False),
                                                     (96, 2, 2048, 3, True), (64, 3, 1000, 2, False)])
@@ -292,3 +293,27 @@ def test_preference():
     ops.preference(c1, r1, prob, n, 1, False, 0.1)
     ref = torch.sigmoid((c1 - r1) / 0.1).squeeze(-1).float()
     assert (prob - ref).abs().max().item() <= 4e-3
+
+
+@pytest.mark.parametrize("hd,heads,T,nseq,causal", [(64, 16, 577, 5, False), (96, 8, 2048, 3, True), (96, 4, 900, 2, True),
+                                                    (64, 4, 1400, 2, False)])
+def test_attention_multitile_is_bit_identical_to_one_tile_per_cta(hd, heads, T, nseq, causal):
+    """LR_ATTN_TCGEN05_MULTITILE walks several query tiles per CTA with the SAME per-tile pipeline (barrier phases carried
+    across tiles): every output element must equal the one-tile-per-CTA kernel's bit for bit, incl. ragged valid runs."""
+    D = heads * hd
+    qkv = rnd(nseq * T, 3 * D, seed=3)
+    if causal:
+        lens = [T, T - 87, 300][:nseq]
+        ss = torch.tensor([T - n for n in lens], dtype=torch.int32, device=DEV)
+        sl = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    else:
+        ss, sl = None, None
+    outs = []
+    for impl in (L.ATTN_TCGEN05_1TILE, L.ATTN_TCGEN05_MULTITILE):
+        o = torch.full((nseq * T, D), float("nan"), dtype=bf, device=DEV)
+        for _ in range(2):   # twice: a second launch must not depend on leftovers of the first
+            ops.attention(qkv, qkv[:, D:], qkv[:, 2 * D:], o, 3 * D, D, nseq, T, ss, sl, heads, hd, causal, hd ** -0.5, impl)
+        torch.cuda.synchronize()
+        outs.append(o)
+    assert not torch.isnan(outs[1].float()).any()
+    assert torch.equal(outs[0], outs[1])
