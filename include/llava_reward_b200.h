@@ -113,12 +113,13 @@ int lr_clip_embed_ln(const void* patch, const void* class_emb, const void* pos_e
  * head_dim 64 (CLIP, non-causal; replaces CLIPAttentionFA2, modeling_phi3_v.py:85-115) or
  * 96 (Phi-3, causal varlen; replaces Phi3FlashAttention2._flash_attention_forward, :888-986).
  * For LR_ATTN_TCGEN05 q, k, v must be column offsets into one row-major buffer (the fused qkv projection). */
-#define LR_ATTN_TCGEN05 0 /* tcgen05.mma + TMEM + TMA, the product configuration for the head_dim: one 128-row query tile
-                             per CTA and two CTAs per SM (head_dim 64 / 96); see LR_ATTN_TCGEN05_2TILE for head_dim 128 */
+#define LR_ATTN_TCGEN05 0 /* tcgen05.mma + TMEM + TMA, the product configuration for the head_dim: the one-query-tile
+                             pipeline with two CTAs per SM, several tiles per CTA where that pays (= LR_ATTN_TCGEN05_MULTITILE,
+                             head_dim 64 / 96); see LR_ATTN_TCGEN05_2TILE for head_dim 128 */
 #define LR_ATTN_MMA_SYNC 1 /* mma.sync kernel, kept to cross-check the tcgen05 path in tests */
 #define LR_ATTN_TCGEN05_2TILE 3 /* tcgen05 kernel with two query tiles per CTA sharing K/V, one CTA per SM (slower on CLIP;
                                    at head_dim 128 the row sums live in registers and K/V are single-staged) */
-#define LR_ATTN_TCGEN05_1TILE 4 /* tcgen05 kernel, one query tile per CTA (= LR_ATTN_TCGEN05 for head_dim 64 / 96) */
+#define LR_ATTN_TCGEN05_1TILE 4 /* tcgen05 kernel, strictly one query tile per CTA (the reference point of the multi-tile form) */
 #define LR_ATTN_TCGEN05_MULTITILE 5 /* the one-tile pipeline walking several query tiles per CTA (causal: the pair
                                        {nt-1-x, x}, every CTA nt+1 K/V blocks; otherwise up to 5 consecutive tiles): the
                                        6.4 us per-CTA fixed cost is paid once per CTA instead of once per tile */

@@ -269,8 +269,7 @@ extern "C" int lr_attention_bf16(const void* q, const void* k, const void* v, vo
     // attention_tc's variant code: 1 = two tiles per CTA, 2 = split softmax, 3 = one tile per CTA,
     // 4 = the one-tile pipeline walking several query tiles per CTA
     int variant = impl == LR_ATTN_TCGEN05_SPLIT ? 2 : (impl == LR_ATTN_TCGEN05_2TILE ? 1 : 3);
-    if (impl == LR_ATTN_TCGEN05_MULTITILE) variant = head_dim == 128 ? kHd128Product : 4;
-    if (impl == LR_ATTN_TCGEN05 && head_dim == 128) variant = kHd128Product;
+    if (impl == LR_ATTN_TCGEN05_MULTITILE || impl == LR_ATTN_TCGEN05) variant = head_dim == 128 ? kHd128Product : 4;
     return attention_tc(q, k, v, o, ld_qkv, ld_o, n_seq * rows_per_seq, n_seq, rows_per_seq, nullptr, seq_start, seq_len,
                         n_heads, n_heads, head_dim, causal, scale, variant, s);
   }
@@ -301,8 +300,7 @@ extern "C" int lr_attention_ex_bf16(const void* q, const void* k, const void* v,
                                      reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(o)) & 15)
     return LR_ERR_ALIGN;
   int variant = impl == LR_ATTN_TCGEN05_SPLIT ? 2 : (impl == LR_ATTN_TCGEN05_2TILE ? 1 : 3);
-  if (impl == LR_ATTN_TCGEN05_MULTITILE) variant = head_dim == 128 ? kHd128Product : 4;
-  if (impl == LR_ATTN_TCGEN05 && head_dim == 128) variant = kHd128Product;
+  if (impl == LR_ATTN_TCGEN05_MULTITILE || impl == LR_ATTN_TCGEN05) variant = head_dim == 128 ? kHd128Product : 4;
   if (impl != LR_ATTN_TCGEN05 && impl != LR_ATTN_TCGEN05_SPLIT && impl != LR_ATTN_TCGEN05_2TILE &&
       impl != LR_ATTN_TCGEN05_1TILE && impl != LR_ATTN_TCGEN05_MULTITILE)
     return LR_ERR_BAD_ARG;

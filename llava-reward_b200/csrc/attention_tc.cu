@@ -649,13 +649,17 @@ static int launch_attn_tc(const void* base, int total_rows, int ld_qkv, int q_co
   // several query tiles per CTA (see the kernel): single-stage K/V ring only, not for the segment layout
   const int nt = (rows_per_seq + 128 * NT - 1) / (128 * NT);
   int tile_mode = 0, gx = nt;
+  // Measured (B200, profiles/r01_attention_multitile.txt): CLIP (5 tiles of 5 K/V blocks) 1.39 -> 1.29 ms, causal
+  // decoder pairs 1.264 -> 1.252 ms; a 4900-token non-causal sequence (39 blocks per tile, fixed cost already
+  // amortised, fewer and longer CTAs -> wave quantisation) 1.45 -> 1.60 ms, so long non-causal sequences keep one
+  // tile per CTA.
   if (multi_tile && NT == 1 && Cfg::kStages == 1 && row_lo == nullptr && nt > 1) {
     if (CAUSAL) {
       tile_mode = 1;                 // pairs {nt-1-x, x}
       gx = (nt + 1) / 2;
-    } else {
-      tile_mode = nt < 5 ? nt : 5;   // up to 5 consecutive tiles (a whole 577-token CLIP crop)
-      gx = (nt + tile_mode - 1) / tile_mode;
+    } else if (nt <= 6) {
+      tile_mode = nt;                // all tiles of a short sequence (a whole 577-token CLIP crop) in one CTA
+      gx = 1;
     }
   }
   dim3 grid(gx, n_heads, n_seq);
