@@ -34,6 +34,17 @@ def test_argument_validation_without_gpu(lib):
     assert lib.lr_gemm_bf16(None, 0, None, 0, None, 0, 1, 1, 1, 0, None, None, 0, 0, None) == -1
     assert lib.lr_rmsnorm_bf16(None, 0, None, None, None, 0, 1, 8, 1e-5, None) == -1
     assert lib.lr_attention_bf16(None, None, None, None, 0, 0, 1, 1, None, None, 1, 64, 0, 1.0, 0, None) == -1
+    assert lib.lr_softmax_rows_bf16(None, 8, 1, 8, 8, 1.0, None) == -1
+    assert lib.lr_masked_mean_rows_bf16(None, 256, None, None, 256, 1, 1, 256, None) == -1
+    assert lib.lr_gather_rows_bf16(None, 8, None, None, 8, 1, 8, None) == -1
+    # the model surface honours the reference's attributes without a device (rw_model_general_preference.py:327-333)
+    from llava_reward_b200.config import RewardConfig as _RC
+    from llava_reward_b200.model import B200RewardModel as _M
+    from llava_reward_b200.synth import SynthProvider as _SP
+    _cfg = _RC(num_layers=1, clip_layers=1)
+    _m = _M(_cfg, _SP(_cfg))
+    assert _m.layer_id == 32 and _m.mean_hidden_state is None and _m.training is False
+    assert _m.train().training is True and _m.eval().training is False and _m.train(False).training is False
     if not torch.cuda.is_available():
         assert lib.lr_device_check() != 0
         from llava_reward_b200 import ops
