@@ -78,6 +78,16 @@ constexpr uint32_t kLayoutSW128 = 2, kLayoutSW64 = 4;
 #ifndef LR_ATTN_EARLY_SFREE
 #define LR_ATTN_EARLY_SFREE 0
 #endif
+// Experiments on the MMA-issue path (default off = the measured product; tools/attn_variants.py builds them):
+// LR_ATTN_HOIST_DESC 1 builds the shared-memory descriptors once and adds the byte offset (>> 4) per tcgen05.mma instead
+// of rebuilding both descriptors from the address every time; LR_ATTN_AUX_REGS is the register count the non-softmax
+// warps keep after setmaxnreg in the one-tile configuration (40, or 48 = 128 x 48 + 128 x 208 = the CTA's allocation).
+#ifndef LR_ATTN_HOIST_DESC
+#define LR_ATTN_HOIST_DESC 0
+#endif
+#ifndef LR_ATTN_AUX_REGS
+#define LR_ATTN_AUX_REGS 40
+#endif
 __device__ __forceinline__ float exp2_fma_pipe(float x) {
   x = fmaxf(x, -127.f);
   float r;
@@ -259,7 +269,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
   // register re-allocation between warpgroups: the softmax threads keep a whole 128-column S row in registers
   if (warp < 4) {
   if constexpr (NT == 1) {
+#if LR_ATTN_AUX_REGS == 40
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+#else
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(LR_ATTN_AUX_REGS));
+#endif
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   }
@@ -325,21 +339,37 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, HDX) | (1u << 16);  // B (= [V | 1]) is MN-major
       auto issue_s = [&](int ks) {  // S_x = Q_x K^T : A = Q (K-major, SW64), B = K stage ks (K-major, SW64)
         const uint32_t qa = smem_u32(sQ + x * TILE), ka = smem_u32(sK + ks * TILE);
+#if LR_ATTN_HOIST_DESC
+        const uint64_t qd = umma_desc(qa, 16, 512, kLayoutSW64), kd = umma_desc(ka, 16, 512, kLayoutSW64);
+#endif
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
           const uint32_t off = (kk >> 1) * kAtomBytes + (kk & 1) * 32;
+#if LR_ATTN_HOIST_DESC
+          // the start-address field holds (addr >> 4) in 14 bits; shared memory ends below 2^18, so the add cannot carry
+          umma_bf16_ss(tm_S[x], qd + (off >> 4), kd + (off >> 4), idesc_s, kk != 0);
+#else
           umma_bf16_ss(tm_S[x], umma_desc(qa + off, 16, 512, kLayoutSW64), umma_desc(ka + off, 16, 512, kLayoutSW64),
                        idesc_s, kk != 0);
+#endif
         }
         umma_commit(&s_full[x]);
         umma_commit(&k_empty[ks]);
       };
       auto issue_pv = [&](int vs, bool acc) {  // O_x += P_x V : A = P (K-major, SW128), B = V (MN-major, SW64)
         const uint32_t pa = smem_u32(sP + x * kPBytes), va = smem_u32(sV + vs * VTILE);
+#if LR_ATTN_HOIST_DESC
+        const uint64_t pd = umma_desc(pa, 16, 1024, kLayoutSW128), vd = umma_desc(va, kAtomBytes, 512, kLayoutSW64);
+#endif
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
+#if LR_ATTN_HOIST_DESC
+          umma_bf16_ss(tm_O[x], pd + (((kk >> 2) * (kPBytes / 2) + (kk & 3) * 32) >> 4), vd + ((kk * 1024) >> 4), idesc_o,
+                       acc || kk != 0);
+#else
           umma_bf16_ss(tm_O[x], umma_desc(pa + (kk >> 2) * (kPBytes / 2) + (kk & 3) * 32, 16, 1024, kLayoutSW128),
                        umma_desc(va + kk * 1024, kAtomBytes, 512, kLayoutSW64), idesc_o, acc || kk != 0);
+#endif
         }
         umma_commit(&pv_done[x]);
         umma_commit(&v_empty[vs]);

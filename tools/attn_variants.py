@@ -10,11 +10,16 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "llava-reward_b200", "csrc")
 OUTDIR = os.path.join(ROOT, "llava-reward_b200", "lib", "variants")
-VARIANTS = [(0, 0), (0, 1), (1, 1), (2, 1), (1, 0), (3, 1)]  # (LR_ATTN_POLY_NUM, LR_ATTN_EARLY_SFREE)
+# (LR_ATTN_POLY_NUM, LR_ATTN_EARLY_SFREE, LR_ATTN_HOIST_DESC, LR_ATTN_AUX_REGS); r01 measured the first six (all slower
+# than the product (0, 0, 0, 40)); the last three are the MMA-issue-path experiments of DESIGN.md section 11
+VARIANTS = [(0, 0, 0, 40), (0, 1, 0, 40), (1, 1, 0, 40), (2, 1, 0, 40), (1, 0, 0, 40), (3, 1, 0, 40),
+            (0, 0, 1, 40), (0, 0, 0, 48), (0, 0, 1, 48)]
+if "--mma-only" in sys.argv:
+    VARIANTS = [v for v in VARIANTS if v[0] == 0 and v[1] == 0]
 
 
 def so_path(v):
-    return os.path.join(OUTDIR, f"libattn_p{v[0]}e{v[1]}.so")
+    return os.path.join(OUTDIR, f"libattn_p{v[0]}e{v[1]}h{v[2]}r{v[3]}.so")
 
 
 def build():
@@ -24,7 +29,8 @@ def build():
     for v in VARIANTS:
         cmd = ["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
                "-Xcompiler", "-fPIC", "--use_fast_math", "--prec-div=true", "--prec-sqrt=true", "--fmad=true",
-               f"-DLR_ATTN_POLY_NUM={v[0]}", f"-DLR_ATTN_EARLY_SFREE={v[1]}", "-shared", "-o", so_path(v), *srcs,
+               f"-DLR_ATTN_POLY_NUM={v[0]}", f"-DLR_ATTN_EARLY_SFREE={v[1]}", f"-DLR_ATTN_HOIST_DESC={v[2]}",
+               f"-DLR_ATTN_AUX_REGS={v[3]}", "-shared", "-o", so_path(v), *srcs,
                "-lcudart"]
         procs.append(subprocess.Popen(cmd))
     for p in procs:
@@ -80,7 +86,7 @@ def main():
                 torch.cuda.synchronize()
                 best = min(best, e0.elapsed_time(e1) / 10)
             err = ((o[:T].float() - ref).norm() / ref.norm()).item()
-            print(f"poly {v[0]}/4 early_sfree {v[1]} | {name}: {best:.3f} ms = {fl / best / 1e9:.0f} TF/s | rel L2 err vs fp32 "
+            print(f"poly {v[0]}/4 early_sfree {v[1]} hoist_desc {v[2]} aux_regs {v[3]} | {name}: {best:.3f} ms = {fl / best / 1e9:.0f} TF/s | rel L2 err vs fp32 "
                   f"{err:.3e}", flush=True)
 
 
