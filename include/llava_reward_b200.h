@@ -92,7 +92,8 @@ int lr_rmsnorm_bf16(const void* x, int ldx, const int* row_index, const void* w,
                     int cols, float eps, void* stream);
 
 /* y = LayerNorm(x) * w + b over the last dim (fp32 statistics, one rounding). Replaces nn.LayerNorm in
- * HF CLIPEncoderLayer / pre_layrnorm (modeling_clip.py). cols % 8 == 0, cols <= 8192. */
+ * HF CLIPEncoderLayer.layer_norm1 / layer_norm2 and CLIPVisionTransformer.pre_layrnorm (installed transformers 5.5
+ * modeling_clip.py:371, :380, :677; reached from the reference at modeling_phi3_v.py:208-219). cols % 8 == 0, cols <= 8192. */
 int lr_layernorm_bf16(const void* x, int ldx, const void* w, const void* b, void* y, int ldy, int rows, int cols,
                       float eps, void* stream);
 
