@@ -12,7 +12,9 @@ results are all-gathered (NCCL) inside the timed region.
   e2e   : pairs/s through the reference-shaped API with HOST (pinned) inputs: H2D of ids/mask/pixels and the
           D2H of the probabilities are inside the timed region
   roofline     : dominant kernel = the tcgen05 (CTA-pair) gate_up GEMM of the decoder, timed live with CUDA events
-  cpu_baseline : the oracle port (fp32, eager attention, all host cores) on a bounded sample, rank 0 only
+  cpu_baseline : the unmodified reference (baseline/_ref, fp32, eager attention, all host cores) at full depth on one
+                 sample, rank 0 at N=1 only
+  gpu_reference: the unmodified reference in bf16 with flash-attn 2 on the same B200, same 32-pair step (N=1 only)
 """
 from __future__ import annotations
 
@@ -79,63 +81,128 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port on the host cores, bounded sample
+# CPU arm: the UNMODIFIED reference (baseline/_ref through oracle/ref_harness.py) on the host cores, FULL depth
 # --------------------------------------------------------------------------------------------------
-CPU_SAMPLE = ("1 sample (13 crops, N_v=1921, S=2048, fp32, eager attention) through the oracle port at (CLIP,decoder) "
-              "depths (1,1),(3,1),(1,3), best of 2 after a warm-up pass, extrapolated linearly to (23,32) layers")
+CPU_SAMPLE = ("the unmodified reference (CustomRewardModel.custom_forward + preference_compute from baseline/_ref, fp32, "
+              "eager attention, torch.set_num_threads(all host cores)) at FULL depth (23 CLIP + 32 decoder layers, "
+              "4376 M params) on config-2 samples (17 crop slots as its processor pads them, N_v=1921, S=2048, B=1 per "
+              "forward as eval/simple_inference.py does); thread pool warmed by one small (336,336) sample")
 
 
-def cpu_sample_seconds(threads: int):
-    """Seconds per sample of the full-depth config-2-shaped workload on `threads` host cores, from reduced-depth
-    runs of the oracle ((clip,dec) layers = (1,1),(3,1),(1,3)) extrapolated linearly to (23,32) layers."""
-    import torch
-    from llava_reward_b200.config import RewardConfig
-    from llava_reward_b200.synth import SynthProvider, synth_batch
-    from oracle import reward_oracle as O
+class ReferenceCPU:
+    """The reference model on the CPU, built once per process. Weights come from the same counter-hash generator as
+    the engine's (generated on the GPU when one is visible - bit-identical to the CPU generator, seconds instead of
+    minutes - and copied to the host)."""
 
-    torch.set_num_threads(threads)
-    times = {}
-    for depth in ((1, 1), (3, 1), (1, 3)):
-        cfg = RewardConfig(clip_layers=depth[0], num_layers=depth[1])
-        P = O.Params(SynthProvider(cfg, seed=1234), dtype=torch.float32)
-        ids, mask, pix, sizes = synth_batch(cfg, 1, IMAGE_HW, SEQ_LEN, seed=7, tag="c", text_len_range=TEXT_LEN_RANGE)
-        for n in SynthProvider(cfg).names():
-            P(n)  # materialise weights outside the timed region
-        best = None
-        with torch.no_grad():
-            for rep in range(3 if depth == (1, 1) else 2):  # the very first pass also warms the thread pool
-                t0 = time.perf_counter()
-                O.custom_forward(P, cfg, ids, mask, pix[:, :13], sizes)  # 13 real crops (padded slots skipped)
-                dt = time.perf_counter() - t0
-                if not (depth == (1, 1) and rep == 0):
-                    best = dt if best is None else min(best, dt)
-        times[depth] = best
-        del P
-    d_clip = max(times[(3, 1)] - times[(1, 1)], 0.0) / 2
-    d_dec = max(times[(1, 3)] - times[(1, 1)], 0.0) / 2
-    fixed = max(times[(1, 1)] - d_clip - d_dec, 0.0)
-    return fixed + 23 * d_clip + 32 * d_dec, times
+    def __init__(self, threads: int):
+        import torch
+        from llava_reward_b200.config import RewardConfig
+        from oracle import ref_harness as RH
+
+        torch.set_num_threads(threads)
+        self.torch, self.RH, self.threads = torch, RH, threads
+        self.cfg = RewardConfig()
+        t0 = time.perf_counter()
+        gen = "cuda" if torch.cuda.is_available() else None
+        self.model = RH.build_reference_model(self.cfg, 1234, device="cpu", dtype=torch.float32, gen_device=gen,
+                                              verbose=False)
+        self.ral = RH.import_reference()[2]
+        self.args = RH.preference_args(self.cfg)
+        self.build_seconds = time.perf_counter() - t0
+        self.sample_seconds = []
+        self._forward(self._inputs("w", 0, (336, 336), None))   # warm-up: 1 crop + global view, S ~ 400
+
+    def _inputs(self, tag, idx, hw=IMAGE_HW, seq_len=SEQ_LEN):
+        from llava_reward_b200.synth import synth_batch
+        return synth_batch(self.cfg, 1, hw, seq_len, seed=7 + idx, tag=tag, text_len_range=TEXT_LEN_RANGE)
+
+    def _forward(self, inputs):
+        with self.torch.no_grad():
+            r, _ = self.model.custom_forward(*inputs)
+        return r
+
+    def sample(self, tag="c", idx=0):
+        inputs = self._inputs(tag, idx)
+        t0 = time.perf_counter()
+        r = self._forward(inputs)
+        self.sample_seconds.append(time.perf_counter() - t0)
+        return r
+
+    def pair(self, idx=0):
+        """one step of the reference arm: chosen + rejected forward + preference_compute -> seconds"""
+        t0 = time.perf_counter()
+        c, r = self.sample("c", idx), self.sample("r", idx)
+        prob = self.ral.preference_compute(self.args, c, r)
+        return time.perf_counter() - t0, float(prob[0])
 
 
 def run_reference_arm(a):
+    """bench.py --impl reference: the reference's own CPU implementation of the path, all host threads, full depth.
+    A step = ONE pair of the workload (the GPU arm's step is 32 such pairs); as many steps as fit in ~150 s
+    (at least one, at most --steps)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    per_sample = []
-    for _ in range(max(1, min(a.steps, 3))):
-        s, _ = cpu_sample_seconds(threads)
-        per_sample.append(s)
-    sec = sum(per_sample) / len(per_sample)
-    value = 1.0 / (2.0 * sec)
-    sample = CPU_SAMPLE + f"; {len(per_sample)} repetition(s)"
+    ref = ReferenceCPU(threads)
+    secs, probs = [], []
+    budget = float(os.environ.get("LR_REF_ARM_BUDGET_S", "150"))
+    while len(secs) < max(1, a.steps) and (not secs or sum(secs) + secs[-1] < budget):
+        dt, p = ref.pair(len(secs))
+        secs.append(dt)
+        probs.append(p)
+    sec = sum(secs) / len(secs)
+    value = 1.0 / sec
+    sample = CPU_SAMPLE + f"; {len(secs)} pair(s) timed, model build {ref.build_seconds:.0f} s not timed"
     line = {"impl": "reference", "metric": "text-image pairs scored/sec", "value": value, "unit": "pairs/s",
-            "n_gpus": a.gpus, "steps": len(per_sample), "warmup": 1, "ms_per_step": sec * 2 * PAIRS_PER_STEP * 1e3,
+            "n_gpus": a.gpus, "steps": len(secs), "warmup": 1, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(a.gpus),
-            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+            "config": dict(workload_config(a.gpus), pairs_per_step_per_gpu=1,
+                           step="one pair of the workload (bounded sample of the GPU arm's 32-pair step)"),
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "reference", "sample": sample,
+                             "seconds_per_sample": ref.sample_seconds, "probabilities": probs},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def gpu_reference_line(dev, steps: int = 2):
+    """The reference itself on the same B200: the unmodified model (baseline/_ref) in bf16 with its flash-attention-2
+    path (Phi3FlashAttention2 + CLIPAttentionFA2), torch eager + cuBLAS, on the same 32-pair config-2 step
+    (2 x custom_forward(32 samples) + preference_compute), inputs resident in HBM, CUDA events."""
+    import torch
+    from llava_reward_b200.config import RewardConfig
+    from llava_reward_b200.synth import synth_batch
+    from oracle import ref_harness as RH
+
+    cfg = RewardConfig()
+    model = RH.build_reference_model(cfg, 1234, device=dev, dtype=torch.bfloat16, verbose=False)
+    RH.set_attention(model, "flash_attention_2")
+    ral, args = RH.import_reference()[2], RH.preference_args(cfg)
+    batches = {tag: synth_batch(cfg, PAIRS_PER_STEP, IMAGE_HW, SEQ_LEN, seed=7, tag=tag, device=dev,
+                                text_len_range=TEXT_LEN_RANGE) for tag in ("c", "r")}
+
+    def step():
+        with torch.no_grad():
+            c, _ = model.custom_forward(*batches["c"])
+            r, _ = model.custom_forward(*batches["r"])
+        return ral.preference_compute(args, c, r)
+
+    step()
+    torch.cuda.synchronize()
+    peak0 = torch.cuda.max_memory_allocated()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del model
+    torch.cuda.empty_cache()
+    return {"value": PAIRS_PER_STEP / (ms / 1e3), "unit": "pairs/s", "ms_per_step": ms, "steps": steps, "warmup": 1,
+            "impl": "unmodified reference (baseline/_ref), bf16, flash-attn 2 (Phi3FlashAttention2 + CLIPAttentionFA2), "
+                    "torch eager + cuBLAS, same B200, same 32-pair step, inputs resident in HBM",
+            "peak_mem_gib": peak0 / 2 ** 30}
 
 
 def workload_config(n_gpus):
@@ -156,6 +223,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--profile-run", action="store_true", help="for ncu: 1 warm-up step, 1 device-timed step, nothing else")
     ap.add_argument("--layers", type=int, default=None, help="debug only: reduce decoder/CLIP depth (INVALID as a bench)")
     a = ap.parse_args()
@@ -362,6 +430,8 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "pair::gemm_pair_kernel<256,SWIGLU> (tcgen05 cta_group::2; decoder gate_up_proj + LoRA-B)",
                          "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": (ach / peaks["bf16_sustained"]) if ach else None, "traffic": traffic,
+                         "traffic_source": "static: one ncu --set full capture of this kernel at this shape "
+                                           "(profiles/r01_gate_up_traffic.json), not measured in this run",
                          "launches_timed": len(durs), "flops_per_launch": flops,
                          "rows_per_launch": (sum(rows) / len(rows)) if rows else None, "peak_source": peaks["source"]},
             "step_roofline": {"tflop_per_pair": TFLOP_PER_PAIR,
@@ -371,14 +441,21 @@ def main():
         }
         if a.layers is not None:
             line["INVALID"] = "reduced depth debug run"
+        if world == 1 and not a.no_gpu_reference:
+            try:
+                line["gpu_reference"] = gpu_reference_line(dev)
+            except Exception as ex:  # reported, never hidden: the engine's own numbers above do not depend on it
+                line["gpu_reference"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
         if world == 1 and not a.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            sec, times = cpu_sample_seconds(threads)
+            ref = ReferenceCPU(threads)
+            r = ref.sample("c", 0)
+            sec = ref.sample_seconds[-1]
             line["cpu_baseline"] = {
-                "value": 1.0 / (2.0 * sec), "unit": "pairs/s", "cores": threads, "kind": "port",
-                "sample": CPU_SAMPLE,
-                "seconds_per_sample_extrapolated": sec,
-                "raw_seconds": {f"{k[0]},{k[1]}": v for k, v in times.items()}}
+                "value": 1.0 / (2.0 * sec), "unit": "pairs/s", "cores": threads, "kind": "reference",
+                "sample": CPU_SAMPLE + "; ONE sample (half a pair) timed, value = 1 / (2 x seconds)",
+                "seconds_per_sample": sec, "model_build_seconds": ref.build_seconds,
+                "reward": r.flatten().tolist()}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -316,6 +316,13 @@ int lr_softmax_rows_bf16(void* scores, int lds, int rows, int n_valid, int n_tot
 int lr_masked_mean_rows_bf16(const void* x, int ldx, const int64_t* attention_mask, void* out, int ldo, int B, int S,
                              int H, void* stream);
 
+/* Synthetic weights: out[i] = fp32(s_i) * scale (+ mean), s_i = centred sum of the four 16-bit halves of two murmur3-
+ * finalised counters (2i, 2i+1) * 0x9E3779B1 + key - the counter-hash generator of llava_reward_b200/synth.py, bit-
+ * identical to its torch-on-CPU form. The reference has no counterpart (it loads hub checkpoints,
+ * eval/reward_adaptor_loader.py:31-42); BASELINE.json asks for random-init weights of the named architecture, and
+ * 4.4 G values are generated in place on the device instead of being shipped. out fp32 [n]. */
+int lr_synth_normal_f32(void* out, int64_t n, uint32_t key, float scale, float mean, int add_mean, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

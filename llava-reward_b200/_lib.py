@@ -58,6 +58,7 @@ SIGNATURES = {
     "lr_compact_rows_bf16": ([p, i32, p, p, p, i32, i32, i32, i32, p], i32),
     "lr_softmax_rows_bf16": ([p, i32, i32, i32, i32, f32, p], i32),
     "lr_masked_mean_rows_bf16": ([p, i32, p, p, i32, i32, i32, i32, p], i32),
+    "lr_synth_normal_f32": ([p, i64, C.c_uint32, f32, f32, i32, p], i32),
 }
 
 

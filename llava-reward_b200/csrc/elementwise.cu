@@ -286,3 +286,42 @@ extern "C" int lr_embed_scatter_bf16(const int64_t* input_ids, const int* img_or
       reinterpret_cast<bf16*>(hidden), ldh, S, H, V);
   return lr_launch_status();
 }
+
+// ---- synthetic-weight generator (random-init weights of the named architecture, BASELINE.json) ---------------------
+// Counter hash of synth.hash_normal: murmur3 finaliser of (2i, 2i+1) * golden + key, sum of the four 16-bit halves
+// (Irwin-Hall n=4), centred, ONE fp32 multiply (+ one fp32 add for norm weights) - integer work up to the last step, so
+// the values are bit-identical to the torch-on-CPU generator the reference-side goldens were made with.
+namespace {
+__device__ __forceinline__ uint32_t fmix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x85EBCA6Bu;
+  x ^= x >> 13;
+  x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
+}
+__global__ void synth_normal_kernel(float* __restrict__ out, long long n, uint32_t key, float scale, float mean,
+                                    int add_mean) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t lo = (uint32_t)(2ull * (unsigned long long)i);
+    const uint32_t a = fmix32(lo * 0x9E3779B1u + key);
+    const uint32_t b = fmix32((lo + 1u) * 0x9E3779B1u + key);
+    const int s = (int)((a & 0xFFFFu) + (a >> 16) + (b & 0xFFFFu) + (b >> 16)) - 131070;
+    float v = __fmul_rn((float)s, scale);   // no FMA contraction: torch multiplies, then adds
+    if (add_mean) v = __fadd_rn(v, mean);
+    out[i] = v;
+  }
+}
+}  // namespace
+
+extern "C" int lr_synth_normal_f32(void* out, int64_t n, uint32_t key, float scale, float mean, int add_mean,
+                                   void* stream) {
+  LR_CHECK_ARG(out && n > 0);
+  const int threads = 256;
+  long long blocks = (n + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  synth_normal_kernel<<<(int)blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<float*>(out), n, key, scale, mean, add_mean);
+  return lr_launch_status();
+}

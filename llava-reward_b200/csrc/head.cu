@@ -1,6 +1,8 @@
 // Reward head: SkipCA on the last-valid-token row, residual + RMSNorm, value head, preference probability.
 // The reference computes W_q/W_k/W_v, the S x N_v score matrix and the value head for all S rows and then
 // gathers one row per sample (rw_model_general_preference.py:376-386, 407-448); only that row is computed here.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace lr {
@@ -35,19 +37,29 @@ skipca_scores_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict
   if (lane == 0) scores[size_t(b) * max_nv + j] = (j < nv) ? bf16_round(bf16_round(acc) * inv_sqrt_d) : pad_score;
 }
 
-// One CTA (768 threads) per sample: softmax over max_nv scores, out = P V, y = x + out, RMSNorm, value head.
+// A CLUSTER of kHeadCluster CTAs per sample (one CTA without cross attention): every CTA recomputes the softmax
+// statistics of the sample's max_nv scores (7.7 KB, L2), takes a contiguous slice of the V rows and accumulates
+// P.V for it (two thread groups alternate rows, 4 rows = 64 B per thread in flight); the partial sums meet in the
+// shared memory of cluster rank 0 through DSMEM in a fixed order (bit-reproducible), which then does
+// y = x + out, RMSNorm, value head. 32 samples -> 256 CTAs instead of 32: the 378 MB of V rows of a config-2
+// forward stream at HBM speed instead of from 32 SMs.
 constexpr int kHeadThreads = 1024;  // two groups of H/8 threads split the P.V rows: H <= 4096 with SkipCA
 constexpr int kHeadMaxNv = 4096;
+constexpr int kHeadCluster = 8;
+constexpr int kHeadSlice = kHeadMaxNv / kHeadCluster;
 
 __global__ void __launch_bounds__(kHeadThreads)
 skipca_head_kernel(const float* __restrict__ scores, const bf16* __restrict__ kv, int ldkv,
                    const int* __restrict__ plan, const bf16* __restrict__ x, int ldx, const bf16* __restrict__ ln_w,
                    const bf16* __restrict__ vh_w, bf16* __restrict__ reward, int H, int max_nv, int vhd, float eps) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   __shared__ float red[32];
-  __shared__ float prob[kHeadMaxNv];
+  __shared__ float prob[kHeadSlice];
   extern __shared__ __align__(16) uint8_t hd_smem[];
-  float* part = reinterpret_cast<float*>(hd_smem);  // [2][H] partial PV sums, later the normalised row
-  const int b = blockIdx.x, tid = threadIdx.x;
+  float* part = reinterpret_cast<float*>(hd_smem);  // [2][H] partial PV sums of this CTA
+  const int ncta = cluster.num_blocks(), rank = cluster.block_rank();
+  const int b = blockIdx.x / ncta, tid = threadIdx.x;
   const int cpr = H >> 3;              // 16-byte chunks per row (384 for H=3072)
   const int grp = tid / cpr;           // 0 or 1 (threads >= 2*cpr idle in the PV loop)
   const int ch = tid % cpr;
@@ -59,34 +71,34 @@ skipca_head_kernel(const float* __restrict__ scores, const bf16* __restrict__ kv
     for (int j = tid; j < max_nv; j += kHeadThreads) mx = fmaxf(mx, sc[j]);
     mx = block_max(mx, red);
     float sum = 0.f;
-    for (int j = tid; j < max_nv; j += kHeadThreads) {
-      const float e = __expf(sc[j] - mx);
-      prob[j] = e;
-      sum += e;
-    }
+    for (int j = tid; j < max_nv; j += kHeadThreads) sum += __expf(sc[j] - mx);
     sum = block_sum(sum, red);
     const float inv = 1.f / sum;
-    for (int j = tid; j < max_nv; j += kHeadThreads) prob[j] = bf16_round(prob[j] * inv);  // softmax output is bf16
+    // this CTA's slice of the real rows (the zero-padded rows nv <= j < max_nv only feed the denominator)
+    const int per = (((nv + ncta - 1) / ncta) + 1) & ~1;
+    const int j0 = min(rank * per, nv), j1 = min(j0 + per, nv);
+    for (int j = j0 + tid; j < j1; j += kHeadThreads)
+      prob[j - j0] = bf16_round(__expf(sc[j] - mx) * inv);  // softmax output is bf16
     __syncthreads();
     if (grp < 2) {
       const bf16* vbase = kv + size_t(row_base) * ldkv + H + ch * 8;  // V = second half of the [K|V] row
-      int j = grp;
-      for (; j + 6 < nv; j += 8) {  // 4 rows in flight per thread
+      int j = j0 + grp;
+      for (; j + 6 < j1; j += 8) {  // 4 rows in flight per thread
         uint4 u[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) u[t] = ldg128(vbase + size_t(j + 2 * t) * ldkv);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          const float p = prob[j + 2 * t];
+          const float p = prob[j + 2 * t - j0];
           float2 f0 = unpack_bf16x2(u[t].x), f1 = unpack_bf16x2(u[t].y), f2 = unpack_bf16x2(u[t].z),
                  f3 = unpack_bf16x2(u[t].w);
           acc[0] += p * f0.x, acc[1] += p * f0.y, acc[2] += p * f1.x, acc[3] += p * f1.y;
           acc[4] += p * f2.x, acc[5] += p * f2.y, acc[6] += p * f3.x, acc[7] += p * f3.y;
         }
       }
-      for (; j < nv; j += 2) {
+      for (; j < j1; j += 2) {
         const uint4 u = ldg128(vbase + size_t(j) * ldkv);
-        const float p = prob[j];
+        const float p = prob[j - j0];
         float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
         acc[0] += p * f0.x, acc[1] += p * f0.y, acc[2] += p * f1.x, acc[3] += p * f1.y;
         acc[4] += p * f2.x, acc[5] += p * f2.y, acc[6] += p * f3.x, acc[7] += p * f3.y;
@@ -94,46 +106,58 @@ skipca_head_kernel(const float* __restrict__ scores, const bf16* __restrict__ kv
 #pragma unroll
       for (int e = 0; e < 8; ++e) part[grp * H + ch * 8 + e] = acc[e];
     }
-    __syncthreads();
+    cluster.sync();  // every CTA's partial sums are visible cluster-wide
   }
-  // y = bf16(x + bf16(attn_out)); RMSNorm; value head. Threads of group 0 own 8 columns each.
-  float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  float ss = 0.f;
-  if (grp == 0) {
-    const uint4 u = ldg128(x + size_t(b) * ldx + ch * 8);
-    float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-    y[0] = f0.x, y[1] = f0.y, y[2] = f1.x, y[3] = f1.y, y[4] = f2.x, y[5] = f2.y, y[6] = f3.x, y[7] = f3.y;
-    if (scores) {
+  if (rank == 0) {
+    // y = bf16(x + bf16(attn_out)); RMSNorm; value head. Threads of group 0 own 8 columns each.
+    float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float ss = 0.f;
+    if (grp == 0) {
+      const uint4 u = ldg128(x + size_t(b) * ldx + ch * 8);
+      float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+      y[0] = f0.x, y[1] = f0.y, y[2] = f1.x, y[3] = f1.y, y[4] = f2.x, y[5] = f2.y, y[6] = f3.x, y[7] = f3.y;
+      if (scores) {
+        float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int r = 0; r < ncta; ++r) {  // fixed order: rank 0 .. ncta-1, group 0 then group 1
+          const float* rp = cluster.map_shared_rank(part, r);
+          const float4 a0 = *reinterpret_cast<const float4*>(rp + ch * 8);
+          const float4 a1 = *reinterpret_cast<const float4*>(rp + ch * 8 + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(rp + H + ch * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(rp + H + ch * 8 + 4);
+          o[0] += a0.x + b0.x, o[1] += a0.y + b0.y, o[2] += a0.z + b0.z, o[3] += a0.w + b0.w;
+          o[4] += a1.x + b1.x, o[5] += a1.y + b1.y, o[6] += a1.z + b1.z, o[7] += a1.w + b1.w;
+        }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float o = bf16_round(part[ch * 8 + e] + part[H + ch * 8 + e]);
-        y[e] = bf16_round(y[e] + o);
-        ss += y[e] * y[e];
+        for (int e = 0; e < 8; ++e) {
+          y[e] = bf16_round(y[e] + bf16_round(o[e]));
+          ss += y[e] * y[e];
+        }
       }
     }
-  }
-  if (scores) {
-    ss = block_sum(ss, red);
-    const float rstd = rsqrtf(ss / float(H) + eps);
-    if (grp == 0) {
-      const uint4 u = ldg128(ln_w + ch * 8);
-      float2 g0 = unpack_bf16x2(u.x), g1 = unpack_bf16x2(u.y), g2 = unpack_bf16x2(u.z), g3 = unpack_bf16x2(u.w);
-      const float g[8] = {g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, g3.x, g3.y};
+    if (scores) {
+      ss = block_sum(ss, red);
+      const float rstd = rsqrtf(ss / float(H) + eps);
+      if (grp == 0) {
+        const uint4 u = ldg128(ln_w + ch * 8);
+        float2 g0 = unpack_bf16x2(u.x), g1 = unpack_bf16x2(u.y), g2 = unpack_bf16x2(u.z), g3 = unpack_bf16x2(u.w);
+        const float g[8] = {g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, g3.x, g3.y};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) y[e] = bf16_round(g[e] * bf16_round(y[e] * rstd));
+        for (int e = 0; e < 8; ++e) y[e] = bf16_round(g[e] * bf16_round(y[e] * rstd));
+      }
+    }
+    for (int d = 0; d < vhd; ++d) {
+      float dot = 0.f;
+      if (grp == 0) {
+        const uint4 u = ldg128(vh_w + size_t(d) * H + ch * 8);
+        float2 w0 = unpack_bf16x2(u.x), w1 = unpack_bf16x2(u.y), w2 = unpack_bf16x2(u.z), w3 = unpack_bf16x2(u.w);
+        dot = y[0] * w0.x + y[1] * w0.y + y[2] * w1.x + y[3] * w1.y + y[4] * w2.x + y[5] * w2.y + y[6] * w3.x +
+              y[7] * w3.y;
+      }
+      dot = block_sum(dot, red);
+      if (tid == 0) reward[size_t(b) * vhd + d] = __float2bfloat16_rn(dot);
     }
   }
-  for (int d = 0; d < vhd; ++d) {
-    float dot = 0.f;
-    if (grp == 0) {
-      const uint4 u = ldg128(vh_w + size_t(d) * H + ch * 8);
-      float2 w0 = unpack_bf16x2(u.x), w1 = unpack_bf16x2(u.y), w2 = unpack_bf16x2(u.z), w3 = unpack_bf16x2(u.w);
-      dot = y[0] * w0.x + y[1] * w0.y + y[2] * w1.x + y[3] * w1.y + y[4] * w2.x + y[5] * w2.y + y[6] * w3.x +
-            y[7] * w3.y;
-    }
-    dot = block_sum(dot, red);
-    if (tid == 0) reward[size_t(b) * vhd + d] = __float2bfloat16_rn(dot);
-  }
+  if (scores) cluster.sync();  // rank 0 has finished reading the other CTAs' shared memory
 }
 
 // bf16 arithmetic, one rounding per torch op of preference_compute
@@ -265,10 +289,24 @@ extern "C" int lr_skipca_head(const float* scores, const void* kv, int ldkv, con
   if (scores) LR_CHECK_ARG(kv && plan && ca_ln_w && max_nv > 0 && max_nv <= kHeadMaxNv);
   if ((ldx % 8) || !aligned16(x) || !aligned16(value_head_w) || (scores && ((ldkv % 8) || !aligned16(kv))))
     return LR_ERR_ALIGN;
-  skipca_head_kernel<<<B, kHeadThreads, scores ? 2 * H * sizeof(float) : 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      scores, reinterpret_cast<const bf16*>(kv), ldkv, plan, reinterpret_cast<const bf16*>(x), ldx,
-      reinterpret_cast<const bf16*>(ca_ln_w), reinterpret_cast<const bf16*>(value_head_w),
-      reinterpret_cast<bf16*>(reward), H, max_nv, vhd, eps);
+  cudaLaunchConfig_t cfg = {};
+  const int ncta = scores ? kHeadCluster : 1;
+  cfg.gridDim = dim3(B * ncta);
+  cfg.blockDim = dim3(kHeadThreads);
+  cfg.dynamicSmemBytes = scores ? 2 * H * sizeof(float) : 0;
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = ncta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, skipca_head_kernel, scores, reinterpret_cast<const bf16*>(kv), ldkv, plan,
+                                     reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(ca_ln_w),
+                                     reinterpret_cast<const bf16*>(value_head_w), reinterpret_cast<bf16*>(reward), H,
+                                     max_nv, vhd, eps);
+  if (e != cudaSuccess) return static_cast<int>(e);
   return lr_launch_status();
 }
 

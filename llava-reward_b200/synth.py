@@ -39,8 +39,16 @@ def hash_normal(name: str, shape, std: float, seed: int, device="cpu", mean: flo
     n = 1
     for s in shape:
         n *= int(s)
-    out = torch.empty(n, dtype=dtype, device=device)
     key = (zlib.crc32(name.encode()) ^ (seed * 0x9E3779B1)) & _M32
+    if torch.device(device).type == "cuda" and dtype == torch.float32:
+        # the same integer hash as one launch of the library's generator kernel (bit-identical, tested)
+        from . import _lib as L
+        out = torch.empty(n, dtype=torch.float32, device=device)
+        with torch.cuda.device(out.device):
+            L.call("lr_synth_normal_f32", out.data_ptr(), n, key, std / _IH_STD, mean, int(mean != 0.0),
+                   torch.cuda.current_stream().cuda_stream)
+        return out.view(*shape)
+    out = torch.empty(n, dtype=dtype, device=device)
     scale = torch.tensor(std / _IH_STD, dtype=torch.float32, device=device)
     for lo in range(0, n, chunk):
         hi = min(n, lo + chunk)

