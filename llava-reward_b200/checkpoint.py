@@ -8,11 +8,87 @@ from __future__ import annotations
 import glob
 import json
 import os
+import re
 from typing import Callable, Dict, Optional, Tuple
 
 import torch
 
 from .config import LlavaNextRewardConfig, QwenVLRewardConfig, RewardConfig
+
+
+_PHI3_DECODER_LORA = re.compile(r"^model\.layers\.\d+\.(self_attn\.(qkv_proj|o_proj)|mlp\.(gate_up_proj|down_proj))$")
+_LLAMA_DECODER_LORA = re.compile(r"^(language_model\.)?model\.layers\.\d+\.(self_attn\.[qkvo]_proj|mlp\.(gate|up|down)_proj)$")
+
+
+def _load_adapter(cfg, pm_path: str, canonical: Callable[[str], str]) -> Dict[str, torch.Tensor]:
+    """PEFT adapter of the reference's `save_model_lora` layout (<pm_path>/lora/adapter_model.{safetensors,bin} +
+    adapter_config.json, reference deepspeed.py:391-398) -> {canonical module name + '.lora_A.weight' / '.lora_B.weight'}.
+    Sets cfg.use_lora / lora_rank / lora_alpha. The reference's `model.load_adapter(...)`
+    (eval/reward_adaptor_loader.py:44) raises when the adapter is missing - so does this; adapter options whose
+    arithmetic the engine does not implement are rejected instead of being silently ignored."""
+    found = None
+    for cand in ("adapter_model.safetensors", "adapter_model.bin"):
+        pth = os.path.join(pm_path, "lora", cand)
+        if os.path.exists(pth):
+            found = pth
+            break
+    if found is None:
+        raise FileNotFoundError(f"no LoRA adapter under {os.path.join(pm_path, 'lora')!r} (adapter_model.safetensors / "
+                                "adapter_model.bin): the reference's load_adapter fails here as well")
+    out = {}
+    for k, v in _load_file(found).items():
+        out[canonical(k.replace("base_model.model.", "", 1).replace(".default", ""))] = v
+    cfg.use_lora = True
+    acfg = os.path.join(pm_path, "lora", "adapter_config.json")
+    if os.path.exists(acfg):
+        with open(acfg) as f:
+            a = json.load(f)
+        for opt in ("rank_pattern", "alpha_pattern"):
+            if a.get(opt):
+                raise NotImplementedError(f"adapter_config.json sets {opt}: per-module LoRA ranks / alphas are not "
+                                          "supported (the reference's create_lora_config* never sets them)")
+        for opt in ("use_dora", "bias"):
+            if a.get(opt) not in (None, False, "none"):
+                raise NotImplementedError(f"adapter_config.json sets {opt}={a.get(opt)!r}: not supported")
+        cfg.lora_rank = int(a.get("r", cfg.lora_rank))
+        cfg.lora_alpha = float(a.get("lora_alpha", cfg.lora_alpha))
+        if a.get("use_rslora"):
+            # peft: scaling = lora_alpha / sqrt(r); expressed through alpha so that cfg.lora_scale = alpha / r holds
+            cfg.lora_alpha = cfg.lora_alpha * (cfg.lora_rank ** 0.5)
+    ranks = {v.shape[0] for k, v in out.items() if k.endswith(".lora_A.weight")}
+    if len(ranks) > 1:
+        raise NotImplementedError(f"adapter holds LoRA matrices of different ranks {sorted(ranks)}")
+    if ranks and ranks != {cfg.lora_rank}:
+        raise ValueError(f"adapter rank {ranks.pop()} does not match adapter_config.json r={cfg.lora_rank}")
+    return out
+
+
+def _merge_adapter(tensors: Dict[str, torch.Tensor], adapter: Dict[str, torch.Tensor], scale: float, unmerged) -> None:
+    """Put the adapter into `tensors`. Modules matched by `unmerged` (the decoder linears) keep their lora_A / lora_B
+    matrices: the engine applies them un-merged through the K-extension of the GEMM, op for op like peft's
+    lora.Linear.forward. EVERY OTHER adapted module - the reference's default create_lora_config also targets the CLIP
+    q/k/v/out_proj/fc1/fc2 and img_projection.0/.2 (llava_reward/utils/utils.py:194-222; freeze_vision_model=False) - is
+    folded into its dense weight, W += (alpha/r) B A in fp32 (the merged form of the same linear map; it differs from
+    the un-merged bf16 evaluation only by rounding). A lora key without a base weight raises: nothing is dropped."""
+    mods = sorted({k[: -len(".lora_A.weight")] for k in adapter if k.endswith(".lora_A.weight")})
+    seen = set()
+    for m in mods:
+        ka, kb = m + ".lora_A.weight", m + ".lora_B.weight"
+        if kb not in adapter:
+            raise KeyError(f"adapter has {ka} but no {kb}")
+        seen.update((ka, kb))
+        base = m + ".weight"
+        if base not in tensors and m + ".base_layer.weight" in tensors:
+            tensors[base] = tensors.pop(m + ".base_layer.weight")
+        if base not in tensors:
+            raise KeyError(f"LoRA adapter targets {m!r} but the checkpoint has no {base!r}")
+        if unmerged.match(m):
+            tensors[ka], tensors[kb] = adapter[ka], adapter[kb]
+        else:
+            tensors[base] = tensors[base].float() + scale * (adapter[kb].float() @ adapter[ka].float())
+    extra = sorted(k for k in adapter if k not in seen)
+    if extra:
+        raise KeyError(f"adapter keys the loader does not understand: {extra[:5]}{' ...' if len(extra) > 5 else ''}")
 
 
 def _load_file(path: str) -> Dict[str, torch.Tensor]:
@@ -53,19 +129,7 @@ def checkpoint_provider(cfg: RewardConfig, pretrain_dir: str, pm_path: Optional[
     cfg.use_lora = False
     if pm_path:
         # LoRA adapter saved by PEFT: keys 'base_model.model.<module>.lora_A.weight' (maybe with '.default')
-        for cand in ("adapter_model.safetensors", "adapter_model.bin"):
-            p = os.path.join(pm_path, "lora", cand)
-            if os.path.exists(p):
-                for k, v in _load_file(p).items():
-                    k = k.replace("base_model.model.", "", 1).replace(".default", "")
-                    tensors[k] = v
-                cfg.use_lora = True
-                acfg = os.path.join(pm_path, "lora", "adapter_config.json")
-                if os.path.exists(acfg):
-                    with open(acfg) as f:
-                        a = json.load(f)
-                    cfg.lora_rank, cfg.lora_alpha = int(a.get("r", cfg.lora_rank)), float(a.get("lora_alpha", cfg.lora_alpha))
-                break
+        adapter = _load_adapter(cfg, pm_path, lambda k: k.replace("model.vision_embed_tokens.wte.", "model.embed_tokens."))
         heads = os.path.join(pm_path, "pytorch_model.bin")
         if os.path.exists(heads):
             sd = torch.load(heads, map_location="cpu", weights_only=True)
@@ -75,8 +139,12 @@ def checkpoint_provider(cfg: RewardConfig, pretrain_dir: str, pm_path: Optional[
                 for mod in ("value_head", "W_q", "W_k", "W_v", "ca_layernorm"):
                     if mod in k:
                         tensors[f"{mod}.{leaf}"] = v
-                if ft_projector and "img_projection" in k:
-                    tensors["model.vision_embed_tokens.img_projection." + ".".join(k.split(".")[-2:])] = v
+                if ft_projector and "img_projection" in k and ".lora_" not in k:
+                    # reference :57-59 keeps the last two name components ('0.weight'); a peft-wrapped projector saves
+                    # '<i>.base_layer.weight' (its lora_A/B live in the adapter file)
+                    parts = [x for x in k.split(".") if x != "base_layer"]
+                    tensors["model.vision_embed_tokens.img_projection." + ".".join(parts[-2:])] = v
+        _merge_adapter(tensors, adapter, cfg.lora_scale, _PHI3_DECODER_LORA)
 
     def get(name: str) -> torch.Tensor:
         if name not in tensors:
@@ -127,19 +195,7 @@ def llava_checkpoint_provider(cfg: LlavaNextRewardConfig, pretrain_dir: str, pm_
         tensors.update({_canonical_llava_name(k): v for k, v in _load_file(fpath).items()})
     cfg.use_lora = False
     if pm_path:
-        for cand in ("adapter_model.safetensors", "adapter_model.bin"):
-            p = os.path.join(pm_path, "lora", cand)
-            if os.path.exists(p):
-                for k, v in _load_file(p).items():
-                    k = _canonical_llava_name(k.replace("base_model.model.", "", 1).replace(".default", ""))
-                    tensors[k] = v
-                cfg.use_lora = True
-                acfg = os.path.join(pm_path, "lora", "adapter_config.json")
-                if os.path.exists(acfg):
-                    with open(acfg) as f:
-                        a = json.load(f)
-                    cfg.lora_rank, cfg.lora_alpha = int(a.get("r", cfg.lora_rank)), float(a.get("lora_alpha", cfg.lora_alpha))
-                break
+        adapter = _load_adapter(cfg, pm_path, _canonical_llava_name)
         heads = os.path.join(pm_path, "pytorch_model.bin")
         if os.path.exists(heads):
             sd = torch.load(heads, map_location="cpu", weights_only=True)
@@ -148,6 +204,7 @@ def llava_checkpoint_provider(cfg: LlavaNextRewardConfig, pretrain_dir: str, pm_
                     tensors["value_head." + k.split(".")[-1]] = v
                 if ft_projector and "multi_modal_projector" in k:
                     tensors["multi_modal_projector." + ".".join(k.split(".")[-2:])] = v
+        _merge_adapter(tensors, adapter, cfg.lora_scale, _LLAMA_DECODER_LORA)
 
     def get(name: str) -> torch.Tensor:
         if name not in tensors:
@@ -205,19 +262,7 @@ def qwen_checkpoint_provider(cfg: QwenVLRewardConfig, pretrain_dir: str, pm_path
         tensors.update({_canonical_qwen_name(k): val for k, val in _load_file(fpath).items()})
     cfg.use_lora = False
     if pm_path:
-        for cand in ("adapter_model.safetensors", "adapter_model.bin"):
-            p = os.path.join(pm_path, "lora", cand)
-            if os.path.exists(p):
-                for k, val in _load_file(p).items():
-                    k = _canonical_qwen_name(k.replace("base_model.model.", "", 1).replace(".default", ""))
-                    tensors[k] = val
-                cfg.use_lora = True
-                acfg = os.path.join(pm_path, "lora", "adapter_config.json")
-                if os.path.exists(acfg):
-                    with open(acfg) as f:
-                        a = json.load(f)
-                    cfg.lora_rank, cfg.lora_alpha = int(a.get("r", cfg.lora_rank)), float(a.get("lora_alpha", cfg.lora_alpha))
-                break
+        adapter = _load_adapter(cfg, pm_path, _canonical_qwen_name)
         heads = os.path.join(pm_path, "pytorch_model.bin")
         if os.path.exists(heads):
             sd = torch.load(heads, map_location="cpu", weights_only=True)
@@ -230,6 +275,7 @@ def qwen_checkpoint_provider(cfg: QwenVLRewardConfig, pretrain_dir: str, pm_path
                     # reference :93-103: keys are cut to their last two components ('ln_q.weight', '0.weight', ...)
                     tail = ".".join(k.split(".")[-2:])
                     tensors["visual.merger." + (tail if tail.startswith("ln_q") else "mlp." + tail)] = val
+        _merge_adapter(tensors, adapter, cfg.lora_scale, _LLAMA_DECODER_LORA)
 
     def get(name: str) -> torch.Tensor:
         if name not in tensors:

@@ -71,6 +71,23 @@ def _pack_clip(pw: PackedWeights, cfg, g, c: str, device) -> None:
         })
 
 
+def _pad128(n: int) -> int:
+    return (n + 127) // 128 * 128
+
+
+def _pad_rank(A: torch.Tensor, B: torch.Tensor):
+    """Zero-pad a LoRA pair (A [r, in], B [out, r]) to a rank that is a multiple of 128: the `x A^T` GEMM needs
+    N % 128 == 0 and the K-extension K % 64 == 0 (lr_gemm_bf16); zero rows of A times zero columns of B add exactly 0,
+    so adapters of any rank (peft r = 8, 16, 64, ...) run unchanged."""
+    r = A.shape[0]
+    rp = _pad128(r)
+    if rp == r:
+        return A, B
+    A = torch.cat([A, torch.zeros(rp - r, A.shape[1], dtype=A.dtype, device=A.device)], 0).contiguous()
+    B = torch.cat([B, torch.zeros(B.shape[0], rp - r, dtype=B.dtype, device=B.device)], 1).contiguous()
+    return A, B
+
+
 def _qk_interleave_perm(n_heads: int, head_dim: int, device) -> torch.Tensor:
     """Row permutation of a [n_heads*head_dim, *] q or k projection: inside every head new row 2i = old i,
     2i+1 = old i + head_dim/2 (RoPE pairs adjacent, see lr_gemm_rope_bf16)."""
@@ -103,6 +120,7 @@ def pack_weights(cfg: RewardConfig, get: Callable[[str], torch.Tensor], device="
             return W, None
         A = g(name + ".lora_A.weight")
         B = (get(name + ".lora_B.weight").to(device=device, dtype=torch.float32) * cfg.lora_scale).to(bf)
+        A, B = _pad_rank(A, B)
         return torch.cat([W, B], dim=1).contiguous(), A
 
     qkv_perm = torch.cat([_qk_interleave_perm(2 * cfg.num_heads, cfg.head_dim, device),  # q and k heads: 0,48,1,49,..
@@ -164,14 +182,19 @@ def pack_weights_llava(cfg: LlavaNextRewardConfig, get: Callable[[str], torch.Te
         if not cfg.use_lora:
             return torch.cat(Ws, 0).contiguous(), None
         k = len(names)
+        As = [g(n + ".lora_A.weight") for n in names]
+        r = As[0].shape[0]                      # the adapter's own rank (any value: the stack is zero-padded to 128)
+        kr = _pad128(k * r)
         blocks = []
         for j, n in enumerate(names):
             B = (get(n + ".lora_B.weight").to(device=device, dtype=torch.float32) * cfg.lora_scale).to(bf)
-            ext = torch.zeros(B.shape[0], k * r, dtype=bf, device=device)
+            ext = torch.zeros(B.shape[0], kr, dtype=bf, device=device)
             ext[:, j * r:(j + 1) * r] = B
             blocks.append(torch.cat([Ws[j], ext], dim=1))
-        A = torch.cat([g(n + ".lora_A.weight") for n in names], 0).contiguous()
-        return torch.cat(blocks, 0).contiguous(), A
+        A = torch.cat(As, 0)
+        if kr != k * r:
+            A = torch.cat([A, torch.zeros(kr - k * r, A.shape[1], dtype=bf, device=device)], 0)
+        return torch.cat(blocks, 0).contiguous(), A.contiguous()
 
     for i in range(cfg.num_layers):
         p = f"{lm}layers.{i}."
@@ -277,14 +300,19 @@ def pack_weights_qwen(cfg: QwenVLRewardConfig, get: Callable[[str], torch.Tensor
         if not cfg.use_lora:
             return torch.cat(Ws, 0).contiguous(), None
         k = len(names)
+        As = [g(n + ".lora_A.weight") for n in names]
+        r = As[0].shape[0]                      # the adapter's own rank (any value: the stack is zero-padded to 128)
+        kr = _pad128(k * r)
         blocks = []
         for j, n in enumerate(names):
             B = (get(n + ".lora_B.weight").to(device=device, dtype=torch.float32) * cfg.lora_scale).to(bf)
-            ext = torch.zeros(B.shape[0], k * r, dtype=bf, device=device)
+            ext = torch.zeros(B.shape[0], kr, dtype=bf, device=device)
             ext[:, j * r:(j + 1) * r] = B
             blocks.append(torch.cat([Ws[j], ext], dim=1))
-        A = torch.cat([g(n + ".lora_A.weight") for n in names], 0).contiguous()
-        return torch.cat(blocks, 0).contiguous(), A
+        A = torch.cat(As, 0)
+        if kr != k * r:
+            A = torch.cat([A, torch.zeros(kr - k * r, A.shape[1], dtype=bf, device=device)], 0)
+        return torch.cat(blocks, 0).contiguous(), A.contiguous()
 
     for i in range(cfg.num_layers):
         p = f"model.layers.{i}."
