@@ -233,6 +233,22 @@ class RewardEngine:
         hs = tuple(t.view(B, S, H) for t in hs) + (vis.view(B, max_nv, H),)
         return BaseModelOutputWithPast(last_hidden_state=hs[-2], past_key_values=None, hidden_states=hs, attentions=None)
 
+    def lm_outputs(self, taps: dict, B: int, S: int):
+        """The `outputs` object of custom_forward(return_output=True) for the llava / qwen branches (the reference
+        returns transformers' CausalLMOutputWithPast of `self.forward(**inputs_batch, output_hidden_states=True)`,
+        rw_model_general_preference.py:357, 374): hidden_states = (inputs_embeds, h_1 .. h_{L-1}, norm(h_L)) from a
+        forward run with `self.taps` set. `logits` is None: the vocabulary-wide lm_head GEMM the reference computes and
+        custom_forward never reads is not executed here."""
+        from transformers.modeling_outputs import CausalLMOutputWithPast
+
+        cfg, w = self.cfg, self.w
+        H, n = cfg.hidden_size, cfg.num_layers
+        last = torch.empty(B * S, H, dtype=torch.bfloat16, device=self.device)
+        ops.rmsnorm(taps[f"hidden_{n - 1}"] if n > 0 else taps["inputs_embeds"], w.head["norm"], last, B * S, H, cfg.rms_eps)
+        hs = [taps["inputs_embeds"]] + [taps[f"hidden_{i}"] for i in range(n - 1)] + [last]
+        return CausalLMOutputWithPast(loss=None, logits=None, past_key_values=None,
+                                      hidden_states=tuple(t.view(B, S, H) for t in hs), attentions=None)
+
     def _pack_valid_rows(self, hid, meta_h, B: int, S: int, pos_from_zero: bool):
         """Gather the valid rows of hid [B*S, H] back to back
         -> (hid_p [rows, H], pos_p, seq_base, eos_p, rows, longest, row index of every packed row).
@@ -252,8 +268,11 @@ class RewardEngine:
         return hid_p, pos_d, base_d, eos_d, rows, int(meta_h[B:2 * B].max()), idx_d
 
     def _can_pack(self, meta_h, B: int, S: int, last_position: bool, mean_pool: bool) -> bool:
+        # a sample with an all-zero attention mask has no rows to pack (packed_row_plan would point its head row at the
+        # previous sample): the slot layout then reads row S-1 of that sample, as the reference does
         return (self.pack_rows and self.taps is None and not last_position and not mean_pool and
-                self.attn_impl != L.ATTN_MMA_SYNC and int(meta_h[B:2 * B].sum()) < B * S)
+                self.attn_impl != L.ATTN_MMA_SYNC and int(meta_h[B:2 * B].sum()) < B * S and
+                int(meta_h[B:2 * B].min()) > 0)
 
     def _resolve_layer_id(self, layer_id):
         """-> (decoder layers to run, apply the final norm). The reference takes `last_hidden_state` for layer_id 32 and
@@ -328,12 +347,24 @@ class RewardEngine:
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, pixel_values: torch.Tensor,
-                image_sizes, layer_id=None, last_position: bool = False, mean_pool: bool = False) -> torch.Tensor:
-        """layer_id / last_position / mean_pool = the reference's `layer_id`, `training` and `mean_hidden_state`
-        attributes (rw_model_general_preference.py:327-333); the defaults are the eval-mode scoring path."""
+                image_sizes, layer_id=None, last_position: bool = False, mean_pool: bool = False,
+                vision_layer_id: int = -1) -> torch.Tensor:
+        """layer_id / last_position / mean_pool / vision_layer_id = the reference's `layer_id`, `training`,
+        `mean_hidden_state` and `vision_layer_id` attributes (rw_model_general_preference.py:327-333, 349-353); the
+        defaults are the eval-mode scoring path."""
         cfg, w, dev = self.cfg, self.w, self.device
         bf = torch.bfloat16
         n_run, final_norm = self._resolve_layer_id(layer_id)
+        vis_from_layer = None
+        if cfg.add_cross_attention and vision_layer_id not in (-1, cfg.num_layers + 1):
+            # SkipCA keys/values = hidden_states[vision_layer_id][:, :N_v_max] instead of the projected image tokens
+            # (:353). Analysis mode: every layer output is captured like for return_output.
+            if mean_pool or n_run != cfg.num_layers:
+                raise NotImplementedError("vision_layer_id together with mean_hidden_state / an early layer_id")
+            vis_from_layer = range(cfg.num_layers + 2)[vision_layer_id]   # python indexing of the hidden_states tuple
+            own_taps = self.taps is None
+            if own_taps:
+                self.taps = {}
         launches0 = L.launch_count()
         B, S = input_ids.shape
         H = cfg.hidden_size
@@ -420,7 +451,35 @@ class RewardEngine:
         xe = self._final_rows(hid, hid_e, head_row, B, final_norm)
         vhd = cfg.vhd
         reward = torch.empty(B, vhd, dtype=bf, device=dev)
-        if cfg.add_cross_attention:
+        if cfg.add_cross_attention and vis_from_layer is not None:
+            # rows [0, N_v_max) of every sample of the chosen hidden state, as the reference slices them (:353); all of
+            # them are "real" rows for the softmax (no zero padding in this form)
+            n = cfg.num_layers
+            if vis_from_layer == 0:
+                src = self.taps["inputs_embeds"]
+            elif vis_from_layer < n:
+                src = self.taps[f"hidden_{vis_from_layer - 1}"]
+            else:
+                src = torch.empty(M, H, dtype=bf, device=dev)
+                ops.rmsnorm(self.taps[f"hidden_{n - 1}"], w.head["norm"], src, M, H, cfg.rms_eps)
+            if own_taps:
+                self.taps = None
+            idx = (torch.arange(B, device=dev, dtype=torch.int32)[:, None] * S +
+                   torch.arange(max_nv, device=dev, dtype=torch.int32)[None, :]).reshape(-1).contiguous()
+            vis = self.buf("ca_vis_layer", (B * max_nv, H))
+            ops.gather_rows(src, idx, vis, B * max_nv, H)
+            plan2_h = np.zeros((B, L.PLAN_STRIDE), dtype=np.int32)
+            plan2_h[:, L.PLAN_ROW_BASE] = np.arange(B, dtype=np.int32) * max_nv
+            plan2_h[:, L.PLAN_NV] = max_nv
+            plan2 = torch.from_numpy(plan2_h.reshape(-1)).to(dev)
+            q = self.buf("ca_q", (B, H))
+            self._gemm(xe, w.head["wq"], q, B, H, H)
+            kv = self.buf("ca_kv_layer", (B * max_nv, 2 * H))
+            self._gemm(vis, w.head["wkv"], kv, B * max_nv, 2 * H, H)
+            scores = self.buf("ca_scores", (B, max_nv), torch.float32)
+            ops.skipca_scores(q, kv, plan2, scores, B, H, max_nv)
+            ops.skipca_head(scores, kv, plan2, xe, w.head["ca_ln"], w.head["vh"], reward, B, H, max_nv, vhd, cfg.rms_eps)
+        elif cfg.add_cross_attention:
             q = self.buf("ca_q", (B, H))
             self._gemm(xe, w.head["wq"], q, B, H, H)
             kv = self.buf("ca_kv", (sum_nv, 2 * H))

@@ -43,28 +43,41 @@ class DevicePrefetcher:
         if self.device.type != "cuda":
             raise RuntimeError("DevicePrefetcher feeds a CUDA device (there is no CPU path in this package)")
         self.stream = torch.cuda.Stream(device=self.device)
-        self._pinned: List[Dict[Tuple, List[torch.Tensor]]] = [dict() for _ in range(self.depth)]
+        # one pinned byte arena per staging set, grown to the largest batch seen (ragged batches - Qwen's
+        # [sum_patches, 1176] pixels, varying S - reuse it through views instead of pinning a new buffer per shape)
+        self._arena: List[torch.Tensor] = [torch.empty(0, dtype=torch.uint8) for _ in range(self.depth)]
         self._copied = [None] * self.depth   # event: the H2D copies out of staging set i have finished
         self.h2d_bytes = 0
+
+    @property
+    def pinned_bytes(self) -> int:
+        return sum(a.numel() for a in self._arena)
 
     def _stage(self, k: int, batch):
         s = k % self.depth
         if self._copied[s] is not None:
             self._copied[s].synchronize()
-        used: Dict[Tuple, int] = {}
+        need = [0]
+
+        def measure(t: torch.Tensor):
+            if not t.is_cuda:
+                need[0] += (t.numel() * t.element_size() + 255) // 256 * 256
+            return t
+
+        _map_tensors(batch, measure)
+        if need[0] > self._arena[s].numel():
+            self._arena[s] = torch.empty(need[0] + need[0] // 4, dtype=torch.uint8).pin_memory()
+        arena, off = self._arena[s], [0]
 
         def to_dev(t: torch.Tensor):
             if t.is_cuda:
                 return t
-            key = (tuple(t.shape), t.dtype)
-            pool = self._pinned[s].setdefault(key, [])
-            i = used.get(key, 0)
-            used[key] = i + 1
-            if i == len(pool):
-                pool.append(torch.empty(t.shape, dtype=t.dtype).pin_memory())
-            pool[i].copy_(t)
-            self.h2d_bytes += t.numel() * t.element_size()
-            return pool[i].to(self.device, non_blocking=True)
+            nbytes = t.numel() * t.element_size()
+            stage = arena[off[0]: off[0] + nbytes].view(t.dtype).view(t.shape)
+            off[0] += (nbytes + 255) // 256 * 256
+            stage.copy_(t)
+            self.h2d_bytes += nbytes
+            return stage.to(self.device, non_blocking=True)
 
         with torch.cuda.stream(self.stream):
             out = _map_tensors(batch, to_dev)

@@ -79,15 +79,13 @@ class B200RewardModel:
             raise RuntimeError("call .to('cuda') before custom_forward (weights are packed on the device)")
         if inputs_batch is not None:
             raise NotImplementedError("inputs_batch is the qwen/llava calling convention; this build covers phi3v")
-        if self.vision_layer_id != -1:
-            raise NotImplementedError("vision_layer_id other than -1 (the vision_embeds entry of hidden_states)")
         if input_ids is None or attention_mask is None:
             raise ValueError("input_ids and attention_mask are required")
         if pixel_values is None or image_sizes is None:
             # the reference path is image-only by construction (UnboundLocalError at modeling_phi3_v.py:252)
             raise ValueError("pixel_values and image_sizes are required (the scoring path is image-only)")
         kw = dict(layer_id=self.layer_id, last_position=bool(self.training) and not self.mean_hidden_state,
-                  mean_pool=bool(self.mean_hidden_state))
+                  mean_pool=bool(self.mean_hidden_state), vision_layer_id=int(self.vision_layer_id))
         with torch.cuda.device(self.device):
             if not return_output:
                 reward = self.engine.forward(input_ids, attention_mask, pixel_values, image_sizes, **kw)
@@ -135,17 +133,23 @@ class B200LlavaNextRewardModel(B200RewardModel):
         if inputs_batch is None:
             # the reference reads inputs_batch['attention_mask'] unconditionally in this branch (:373)
             raise TypeError("model_type 'llava' is called as custom_forward(inputs_batch=processor_output)")
-        if return_output:
-            raise NotImplementedError("return_output=True (HF LlavaNextCausalLMOutputWithPast) is not produced by the fused path")
         for k in ("input_ids", "attention_mask", "pixel_values", "image_sizes"):
             if k not in inputs_batch:
                 raise KeyError(k)
+        outputs = None
         with torch.cuda.device(self.device):   # `layer_id` is not read by the reference in this branch (:372-375)
-            reward = self.engine.forward(inputs_batch["input_ids"], inputs_batch["attention_mask"],
-                                         inputs_batch["pixel_values"], inputs_batch["image_sizes"],
-                                         last_position=bool(self.training) and not self.mean_hidden_state,
-                                         mean_pool=bool(self.mean_hidden_state))
-        return self._shape_like_reference(reward), None
+            if return_output:
+                self.engine.taps = {}
+            try:
+                reward = self.engine.forward(inputs_batch["input_ids"], inputs_batch["attention_mask"],
+                                             inputs_batch["pixel_values"], inputs_batch["image_sizes"],
+                                             last_position=bool(self.training) and not self.mean_hidden_state,
+                                             mean_pool=bool(self.mean_hidden_state))
+                if return_output:   # hidden_states of every layer; logits stay None (lm_head is not executed)
+                    outputs = self.engine.lm_outputs(self.engine.taps, *inputs_batch["input_ids"].shape)
+            finally:
+                self.engine.taps = None
+        return self._shape_like_reference(reward), outputs
 
     __call__ = custom_forward
 
@@ -170,18 +174,24 @@ class B200QwenRewardModel(B200RewardModel):
         if inputs_batch is None:
             # the reference reads inputs_batch['attention_mask'] unconditionally in this branch (:355)
             raise TypeError("model_type 'qwen' is called as custom_forward(inputs_batch=processor_output)")
-        if return_output:
-            raise NotImplementedError("return_output=True (HF Qwen2_5_VLCausalLMOutputWithPast) is not produced by the fused path")
         for k in ("input_ids", "attention_mask", "pixel_values", "image_grid_thw"):
             if k not in inputs_batch:
                 raise KeyError(k)
         if inputs_batch.get("pixel_values_videos") is not None:
             raise NotImplementedError("video inputs: the reference's reward datasets are image-only")
+        outputs = None
         with torch.cuda.device(self.device):
-            reward = self.engine.forward(inputs_batch["input_ids"], inputs_batch["attention_mask"],
-                                         inputs_batch["pixel_values"], inputs_batch["image_grid_thw"],
-                                         last_position=bool(self.training) and not self.mean_hidden_state,
-                                         mean_pool=bool(self.mean_hidden_state))
-        return self._shape_like_reference(reward), None
+            if return_output:
+                self.engine.taps = {}
+            try:
+                reward = self.engine.forward(inputs_batch["input_ids"], inputs_batch["attention_mask"],
+                                             inputs_batch["pixel_values"], inputs_batch["image_grid_thw"],
+                                             last_position=bool(self.training) and not self.mean_hidden_state,
+                                             mean_pool=bool(self.mean_hidden_state))
+                if return_output:   # hidden_states of every layer; logits stay None (lm_head is not executed)
+                    outputs = self.engine.lm_outputs(self.engine.taps, *inputs_batch["input_ids"].shape)
+            finally:
+                self.engine.taps = None
+        return self._shape_like_reference(reward), outputs
 
     __call__ = custom_forward

@@ -57,8 +57,15 @@ CASES = {
                           use_lora=False), [("c", 2, [(1344, 1344), (336, 336)], None, (1600, 1700)),
                                             ("r", 2, [(1344, 1344), (336, 336)], None, (1600, 1700))]),
 }
+CASES["slim_gpm_b1"] = (dict(num_layers=2, clip_layers=2), [("c", 1, [(336, 672)], None), ("r", 1, [(672, 336)], None)])
 SEED_W, SEED_X = 1234, 7
-ATTR_CASES = ("slim_gpm", "slim_bt")
+ATTR_CASES = ("slim_gpm", "slim_bt", "slim_gpm_b1")
+# `vision_layer_id` (rw_model_general_preference.py:353): SkipCA keys/values = hidden_states[id][:, :N_v_max] with
+# hidden_states = (inputs_embeds, h_1, norm(h_2), vision_embeds) at 2 layers. Batches of ONE sample: no padded positions,
+# whose hidden states differ between the reference's eager and flash-attention paths.
+VL_VARIANTS = {"vision_layer_id_0": {"vision_layer_id": 0}, "vision_layer_id_1": {"vision_layer_id": 1},
+               "vision_layer_id_2": {"vision_layer_id": 2}, "vision_layer_id_-2": {"vision_layer_id": -2},
+               "vision_layer_id_-3": {"vision_layer_id": -3}}
 ATTR_VARIANTS = {"layer_id_1": {"layer_id": 1}, "layer_id_0": {"layer_id": 0}, "training": {"training": True},
                  "mean": {"mean_hidden_state": True}, "mean_layer_id_1": {"mean_hidden_state": True, "layer_id": 1}}
 
@@ -100,7 +107,7 @@ def run_case(name: str, refmods):
             # the reference model object exactly as a caller would; dropout probabilities are 0 in these configs, so
             # the top-level `training` flag only switches the gather rule
             entry["attrs"] = {}
-            for key, attrs in ATTR_VARIANTS.items():
+            for key, attrs in (VL_VARIANTS if name == "slim_gpm_b1" else ATTR_VARIANTS).items():
                 saved = {k: getattr(model, k) for k in attrs}
                 for k, v in attrs.items():
                     setattr(model, k, v)

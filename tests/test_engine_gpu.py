@@ -587,3 +587,33 @@ def test_packed_valid_rows_are_output_identical(case, tmp_path_factory):
     finally:
         eng.pack_rows = True
     # left- and right-padded forms of the same samples agree as well (positions count from the first valid token)
+
+
+def test_vision_layer_id_vs_reference_golden(tmp_path_factory):
+    """`vision_layer_id` (rw_model_general_preference.py:353): SkipCA keys / values taken from
+    hidden_states[vision_layer_id][:, :N_v_max] instead of the projected image tokens. Goldens: the attribute set on the
+    reference model (tests/golden/make_golden.py: slim_gpm_b1, batches of one sample = no padded positions)."""
+    fx = load_fixture("slim_gpm_b1")
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    assert model.vision_layer_id == -1
+    try:
+        for entry in fx["batches"]:
+            ids, mask, pix, sizes = fixture_batch(fx, entry, cfg, device="cuda")
+            model.vision_layer_id = -1
+            r0, _ = model.custom_forward(ids, mask, pix, sizes)
+            base_err = (r0.float().cpu() - entry["reward"]).abs().max().item()
+            for key, g in entry["attrs"].items():
+                model.vision_layer_id = int(key.rsplit("_", 1)[1])
+                r, _ = model.custom_forward(ids, mask, pix, sizes)
+                err = (r.float().cpu() - g).abs().max().item()
+                print(f"{entry['tag']}/{key}: engine {r.float().flatten().tolist()} ref {g.flatten().tolist()} err {err:.4g} "
+                      f"(default path err {base_err:.4g})")
+                assert tuple(r.shape) == tuple(g.shape)
+                assert err < REWARD_TOL + 2.0 * base_err, key
+            assert model.engine.taps is None
+            # index cfg.num_layers + 1 is the vision_embeds entry itself (= -1)
+            model.vision_layer_id = cfg.num_layers + 1
+            r1, _ = model.custom_forward(ids, mask, pix, sizes)
+            assert torch.equal(r1, r0)
+    finally:
+        model.vision_layer_id = -1

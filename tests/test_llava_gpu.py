@@ -473,3 +473,29 @@ def test_llava_packed_valid_rows_are_output_identical(case, tmp_path_factory):
             assert torch.equal(rp, rs)
     finally:
         eng.pack_rows = True
+
+
+def test_return_output_hidden_states_inputs_batch_branch(tmp_path_factory):
+    """custom_forward(inputs_batch=..., return_output=True): the reference returns `self.forward(..., output_hidden_states=
+    True)` (rw_model_general_preference.py:357, 374); the engine returns the same hidden_states tuple (inputs_embeds, h_1
+    .. h_{L-1}, norm(h_L)) with logits None (the lm_head GEMM custom_forward never reads is not executed)."""
+    fx = load_fixture("llava_slim_bt")
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    entry = fx["batches"][0]
+    batch = {k: v.to(DEV) for k, v in llava_fixture_batch(fx, entry, cfg).items()}
+    r0, none = model.custom_forward(inputs_batch=batch)
+    r, out = model.custom_forward(inputs_batch=batch, return_output=True)
+    assert none is None and model.engine.taps is None and out.logits is None
+    assert (r.float() - r0.float()).abs().max().item() < 2e-2
+    hs = out["hidden_states"]
+    assert len(hs) == cfg.num_layers + 1
+    valid = batch["attention_mask"].bool()[:, :, None]
+    for name, t in (("inputs_embeds", hs[0]), ("hidden_0", hs[1]), ("last_hidden", hs[-1])):
+        g = entry["taps"][name]
+        assert list(t.shape) == g["shape"], name
+        tt = torch.where(valid.expand_as(t), t, torch.zeros_like(t))
+        a = tt.float().flatten()[:: g["stride"]][:2048].cpu()
+        w = valid.expand_as(t).float().flatten()[:: g["stride"]][:2048].cpu()
+        rel = ((a - g["vals"] * w).norm() / (g["vals"] * w).norm()).item()
+        print(f"return_output {name}: rel L2 err vs reference fp32 {rel:.4g}")
+        assert rel < 3e-2, name
