@@ -24,6 +24,7 @@
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tmap_cache.cuh"
 
 namespace lr {
 
@@ -88,6 +89,32 @@ constexpr uint32_t kLayoutSW128 = 2, kLayoutSW64 = 4;
 #ifndef LR_ATTN_AUX_REGS
 #define LR_ATTN_AUX_REGS 40
 #endif
+// Softmax-side experiments of round 2 (default = the measured best; tools/attn_variants.py builds and times them):
+// LR_ATTN_PIPE_LD 1 loads the S row from TMEM in four 32-column chunks and folds the (mask +) running max of chunk c
+// under the tcgen05.ld of chunk c+1 instead of waiting for the whole row first; LR_ATTN_MAX3 1 uses the three-input
+// FMNMX3 (max.f32 d, a, b, c) - 64 instead of 128 ALU-pipe instructions per row.
+#ifndef LR_ATTN_PIPE_LD
+#define LR_ATTN_PIPE_LD 0
+#endif
+#ifndef LR_ATTN_MAX3
+#define LR_ATTN_MAX3 0
+#endif
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// tcgen05.wait::ld that names the registers of the load it completes as in/out operands: the compiler may not move
+// their consumers above the wait nor the wait above the load (needed once loads and uses are interleaved).
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 __device__ __forceinline__ float exp2_fma_pipe(float x) {
   x = fmaxf(x, -127.f);
   float r;
@@ -425,7 +452,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
   }
   } else {
     if constexpr (NT == 1) {
-      asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");  // 2 CTAs/SM: 2 x (128 x 208 + 128 x 40) <= 64 K
+      // 2 CTAs/SM: the CTA's 256 x 128 registers are re-split 128 x AUX + 128 x (256 - AUX) (40 + 208 leaves 8 unused)
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(LR_ATTN_AUX_REGS <= 48 ? 208 : 256 - LR_ATTN_AUX_REGS));
     } else if constexpr (SPLIT == 1) {
       asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     } else {
@@ -462,32 +490,57 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       const bool need_mask = seg || (kv0 + 128 > kv_end[x]) || (CAUSAL && kv0 + 127 > m0 + x * 128);
       // whole S row -> registers, then give the TMEM buffer back to the MMA warp
       uint32_t sv[NCH][32];
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) tmem_ld_32x32(tm_S[x] + lane_addr + (h * NCH + c) * 32, sv[c]);
-      tmem_ld_wait();
-      if constexpr (SPLIT == 1 && LR_ATTN_EARLY_SFREE) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[x]);
-      }
-      if (tr) ATTN_TRACE(1 + x, 2, j);
-      if (need_mask) {
-#pragma unroll
-        for (int c = 0; c < NCH; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int col = kv0 + (h * NCH + c) * 32 + i;
-            const bool ok = seg ? (col >= my_lo && col < my_hi) : (col < kv_end[x] && (!CAUSAL || col <= row_abs));
-            sv[c][i] = ok ? sv[c][i] : 0xff800000u;  // -inf
-          }
-      }
       float mxc[8];  // 8 independent chains instead of one long dependent FMNMX chain
 #pragma unroll
       for (int c = 0; c < 8; ++c) mxc[c] = -INFINITY;
+      auto mask_chunk = [&](int c) {
 #pragma unroll
-      for (int c = 0; c < NCH; ++c)
+        for (int i = 0; i < 32; ++i) {
+          const int col = kv0 + (h * NCH + c) * 32 + i;
+          const bool ok = seg ? (col >= my_lo && col < my_hi) : (col < kv_end[x] && (!CAUSAL || col <= row_abs));
+          sv[c][i] = ok ? sv[c][i] : 0xff800000u;  // -inf
+        }
+      };
+      auto max_chunk = [&](int c) {
+#if LR_ATTN_MAX3
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float& m = mxc[(c * 4 + (i & 3)) & 7];
+          m = fmax3(m, __uint_as_float(sv[c][2 * i]), __uint_as_float(sv[c][2 * i + 1]));
+        }
+#else
 #pragma unroll
         for (int i = 0; i < 32; ++i) mxc[(c * 2 + (i >> 4)) & 7] = fmaxf(mxc[(c * 2 + (i >> 4)) & 7], __uint_as_float(sv[c][i]));
+#endif
+      };
+      if constexpr (SPLIT == 1 && LR_ATTN_PIPE_LD) {
+        // chunk c+1 is in flight while chunk c is masked and reduced
+        tmem_ld_32x32(tm_S[x] + lane_addr, sv[0]);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          tmem_ld_wait_dep(sv[c]);
+          if (c + 1 < NCH) tmem_ld_32x32(tm_S[x] + lane_addr + (c + 1) * 32, sv[c + 1]);
+          if (need_mask) mask_chunk(c);
+          max_chunk(c);
+        }
+        if (tr) ATTN_TRACE(1 + x, 2, j);
+      } else {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) tmem_ld_32x32(tm_S[x] + lane_addr + (h * NCH + c) * 32, sv[c]);
+        tmem_ld_wait();
+        if constexpr (SPLIT == 1 && LR_ATTN_EARLY_SFREE) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[x]);
+        }
+        if (tr) ATTN_TRACE(1 + x, 2, j);
+        if (need_mask) {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) mask_chunk(c);
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) max_chunk(c);
+      }
       float mx = fmaxf(fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3])), fmaxf(fmaxf(mxc[4], mxc[5]), fmaxf(mxc[6], mxc[7])));
       if constexpr (SPLIT == 2) {
         // The other 64 columns of this row live in a thread of the partner warpgroup: exchange the partial maxima
@@ -663,17 +716,11 @@ static int launch_attn_tc(const void* base, int total_rows, int ld_qkv, int q_co
   EncodeTiledFn fn = attn_encode_fn();
   if (!fn) return LR_ERR_NO_DRIVER;
   CUtensorMap tm;
-  cuuint64_t dims[2] = {cuuint64_t(ld_qkv), cuuint64_t(total_rows)};
-  cuuint64_t strides[1] = {cuuint64_t(ld_qkv) * 2};
-  cuuint32_t box[2] = {32, 128};
-  cuuint32_t estr[2] = {1, 1};
-  if (fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return LR_ERR_BAD_ARG;
+  if (!cached_tmap_bf16(fn, &tm, base, total_rows, ld_qkv, ld_qkv, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B)) return LR_ERR_BAD_ARG;
   auto kern = attn_tc_kernel<HD, CAUSAL, SPLIT, NT>;
-  {  // per-device attribute; setting it on every launch keeps multi-device processes correct
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  {  // per-device attribute, set once per (kernel, device)
+    static bool attr_done[64] = {};   // one array per instantiation of this launch template = per kernel
+    cudaError_t e = ensure_smem_attr(kern, Cfg::kSmemBytes, attr_done);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
   // several query tiles per CTA (see the kernel): single-stage K/V ring only, not for the segment layout

@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tmap_cache.cuh"
 
 namespace lr {
 
@@ -281,14 +282,7 @@ static int make_tmap(CUtensorMap* map, const void* ptr, int rows, int cols, int 
   if (rows <= 0 || cols <= 0) return LR_ERR_BAD_ARG;
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return LR_ERR_NO_DRIVER;
-  cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
-  cuuint64_t strides[1] = {cuuint64_t(ld) * 2};
-  cuuint32_t box[2] = {cuuint32_t(kBK), cuuint32_t(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? LR_OK : LR_ERR_BAD_ARG;
+  return cached_tmap_bf16(fn, map, ptr, rows, cols, ld, kBK, box_rows, CU_TENSOR_MAP_SWIZZLE_128B) ? LR_OK : LR_ERR_BAD_ARG;
 }
 
 static int sm_count() {
@@ -312,8 +306,9 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, void* C, 
   st = make_tmap(&tc, C, M, EPI == LR_EPI_SWIGLU ? N / 2 : N, ldc, 32);
   if (st != LR_OK) return st;
   auto kern = gemm_tcgen05_kernel<BN, EPI>;
-  {  // per-device attribute; setting it on every launch keeps multi-device processes correct
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  {  // per-device attribute, set once per (kernel, device)
+    static bool attr_done[64] = {};   // one array per instantiation of this launch template = per kernel
+    cudaError_t e = ensure_smem_attr(kern, Cfg::kSmemBytes, attr_done);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
   const int num_tiles = ((M + kBM - 1) / kBM) * (N / BN);

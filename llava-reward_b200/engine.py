@@ -27,6 +27,7 @@ class RewardEngine:
         self.attn_impl = attn_impl
         self._bufs: Dict[Tuple[str, Tuple[int, ...], torch.dtype], torch.Tensor] = {}
         self._rope: Dict[Tuple[int, bool], Tuple[torch.Tensor, torch.Tensor]] = {}
+        self._pinned: Dict[str, torch.Tensor] = {}
         self.launches = 0        # C-ABI calls issued by the last forward (= kernel launches, see _lib.launch_count)
         self.taps: Optional[dict] = None  # set to {} to capture intermediates (tests)
         self.profile: Optional[dict] = None  # {"gate_up": []} -> CUDA-event pairs around that GEMM (bench roofline)
@@ -51,6 +52,18 @@ class RewardEngine:
             t = torch.empty(*shape, dtype=dtype, device=self.device)
             self._bufs[key] = t
         return t
+
+    def _h2d(self, name: str, host: torch.Tensor, dev: torch.Tensor) -> None:
+        """dev.copy_(host) through a persistent pinned staging buffer (grown on demand) instead of a fresh
+        `pin_memory()` allocation per call. Safe to reuse: every forward starts with a blocking D2H read of the token
+        plan, so the previous forward's copy out of this buffer has completed before it is rewritten."""
+        n = host.numel()
+        st = self._pinned.get(name)
+        if st is None or st.numel() < n or st.dtype != host.dtype:
+            st = torch.empty(max(n, 1) * 2, dtype=host.dtype).pin_memory()
+            self._pinned[name] = st
+        st[:n].copy_(host.reshape(-1))
+        dev.reshape(-1)[:n].copy_(st[:n], non_blocking=True)
 
     def rope_tables(self, n_pos: int, long: bool):
         """cos/sin [n_pos, head_dim/2] bf16, computed like Phi3SuScaledRotaryEmbedding.forward
@@ -260,7 +273,7 @@ class RewardEngine:
         rows = int(idx.shape[0])
         host = torch.from_numpy(np.concatenate([idx, posv, base, last]))
         dev = self.buf("pack_plan", (2 * B * S + 2 * B,), torch.int32)[: host.numel()]
-        dev.copy_(host.pin_memory(), non_blocking=True)
+        self._h2d("pack_plan", host, dev)
         idx_d, pos_d = dev[:rows], dev[rows:2 * rows]
         base_d, eos_d = dev[2 * rows:2 * rows + B], dev[2 * rows + B:]
         hid_p = self.buf("hidden_packed", (B * S, H))[:rows]
@@ -297,10 +310,14 @@ class RewardEngine:
         return self._last_rows
 
     def _mean_head(self, hid, mask, B: int, S: int, final_norm: bool, img=None, plan_h=None, max_nv: int = 0,
-                   cross_attention=None):
+                   cross_attention=None, masked_pad: bool = False, ca_eps=None):
         """`mean_hidden_state` pooling (rw_model_general_preference.py:376-386 for ALL rows, then :398-406 and the value
         head): final norm of every row, the S x N_v cross attention of every sample as GEMMs on the zero-padded
-        vision rows, residual + ca_layernorm, masked mean, value head."""
+        vision rows, residual + ca_layernorm, masked mean, value head.
+        masked_pad = the qwen arm (:387-397): the padded vision rows are masked with -1e4 before the softmax (exp
+        underflows to exactly 0, i.e. the softmax runs over the sample's own rows) instead of taking part in it with a
+        score of 0 as in the phi3v arm; a sample without any vision row gets attn_o = 0 (uniform weights over zero
+        rows of V). ca_eps: epsilon of ca_layernorm (the qwen loader builds it with 1e-6)."""
         cfg, w = self.cfg, self.w
         M, H = B * S, cfg.hidden_size
         if final_norm:
@@ -309,7 +326,14 @@ class RewardEngine:
         else:
             xa = hid
         self._tap("last_hidden_all", xa)
-        if cfg.add_cross_attention if cross_attention is None else cross_attention:
+        ca_eps = cfg.rms_eps if ca_eps is None else ca_eps
+        use_ca = cfg.add_cross_attention if cross_attention is None else cross_attention
+        if use_ca and max_nv == 0:
+            # no vision row in the whole batch (qwen arm): vision_pad is [B, 0, H], attn_o = 0 -> ca_layernorm(x + 0)
+            y2 = self.buf("ca_y2", (M, H))
+            ops.rmsnorm(xa, w.head["ca_ln"], y2, M, H, ca_eps)
+            xa = y2
+        elif use_ca:
             NVP = (max_nv + 255) // 256 * 256
             idx_h = np.full((B, NVP), -1, dtype=np.int32)  # -1 = the reference's zero-padded vision rows
             for b in range(B):
@@ -330,12 +354,20 @@ class RewardEngine:
             for b in range(B):
                 self._gemm(q[b * S:(b + 1) * S], kp[b * NVP:(b + 1) * NVP], sc[b * S:(b + 1) * S], S, NVP, H)
                 self._gemm(wv, vis[b * NVP:(b + 1) * NVP], vt[b * H:(b + 1) * H], H, NVP, H)
-            ops.softmax_rows(sc, M, max_nv, NVP, 1.0 / math.sqrt(H))
+            if masked_pad:
+                for b in range(B):
+                    nv = int(plan_h[b, L.PLAN_NV])
+                    if nv > 0:
+                        ops.softmax_rows(sc[b * S:(b + 1) * S], S, nv, NVP, 1.0 / math.sqrt(H))
+                    else:
+                        sc[b * S:(b + 1) * S].zero_()
+            else:
+                ops.softmax_rows(sc, M, max_nv, NVP, 1.0 / math.sqrt(H))
             for b in range(B):
                 self._gemm(sc[b * S:(b + 1) * S], vt[b * H:(b + 1) * H], y[b * S:(b + 1) * S], S, H, NVP,
                            L.EPI_RESIDUAL, None, xa[b * S:(b + 1) * S])
             y2 = self.buf("ca_y2", (M, H))
-            ops.rmsnorm(y, w.head["ca_ln"], y2, M, H, cfg.rms_eps)
+            ops.rmsnorm(y, w.head["ca_ln"], y2, M, H, ca_eps)
             xa = y2
             self._tap("skipca_all", xa)
         pooled = self.buf("pooled", (B, H))
@@ -410,7 +442,7 @@ class RewardEngine:
         max_len = int(meta_h[B:2 * B].max())
         host = torch.from_numpy(np.concatenate([plan_h.reshape(-1), np.asarray(crop_src, dtype=np.int32)]))
         dev_plan = self.buf("plan", (host.numel(),), torch.int32)
-        dev_plan.copy_(host.pin_memory() if dev.type == "cuda" else host, non_blocking=True)
+        self._h2d("plan", host, dev_plan)
         plan = dev_plan[: B * L.PLAN_STRIDE]
         crop_idx = dev_plan[B * L.PLAN_STRIDE:]
 
@@ -573,7 +605,7 @@ class LlavaNextRewardEngine(RewardEngine):
         n_patches = patch_base
         host = torch.from_numpy(np.concatenate([plan_h.reshape(-1), np.asarray(patch_src, dtype=np.int32)]))
         dev_plan = self.buf("plan", (host.numel(),), torch.int32)
-        dev_plan.copy_(host.pin_memory() if dev.type == "cuda" else host, non_blocking=True)
+        self._h2d("plan", host, dev_plan)
         plan = dev_plan[: B * L.PLAN_STRIDE]
         patch_idx = dev_plan[B * L.PLAN_STRIDE:]
 
@@ -810,7 +842,7 @@ class QwenVLRewardEngine(RewardEngine):
         sum_pad, max_pad = int(n_pad.sum()), int(n_pad.max()) if B else 0
         host = torch.from_numpy(plan_h.reshape(-1))
         dev_plan = self.buf("plan", (host.numel(),), torch.int32)
-        dev_plan.copy_(host.pin_memory() if dev.type == "cuda" else host, non_blocking=True)
+        self._h2d("plan", host, dev_plan)
         plan, pad_plan = dev_plan[: B * L.PLAN_STRIDE], dev_plan[B * L.PLAN_STRIDE:]
 
         # 2. vision tower + merger, 3. embeddings
@@ -825,8 +857,6 @@ class QwenVLRewardEngine(RewardEngine):
             ops.compact_rows(hid, pad_ord, pad_plan, kv_src, B, S, H)
 
         # 4. decoder (per-token M-RoPE rows: position_ids = None)
-        if mean_pool and ca:
-            raise NotImplementedError("mean_hidden_state together with the qwen SkipCA arm")
         head_row = self._head_rows(eos_row, B, S, last_position)
         if self._can_pack(meta_h, B, S, last_position, mean_pool):
             # per-token M-RoPE rows travel with their tokens: the same gather on the cos / sin tables
@@ -841,7 +871,11 @@ class QwenVLRewardEngine(RewardEngine):
             hid_e = self._decoder(hid, B, S, None, seq_start, seq_len, cos_tok, sin_tok,
                                   None if mean_pool else head_row)
         if mean_pool:
-            reward = self._mean_head(hid, mask, B, S, True, cross_attention=False)
+            if ca:   # all-rows form of the qwen SkipCA arm on the compacted token-id-151643 rows of hidden_states[0]
+                reward = self._mean_head(hid, mask, B, S, True, kv_src, plan_h[B:], max_pad if sum_pad > 0 else 0,
+                                         cross_attention=True, masked_pad=True, ca_eps=1e-6)
+            else:
+                reward = self._mean_head(hid, mask, B, S, True, cross_attention=False)
             self.launches = L.launch_count() - launches0
             return reward
 

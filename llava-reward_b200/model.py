@@ -148,7 +148,8 @@ class B200LlavaNextRewardModel(B200RewardModel):
                 if return_output:   # hidden_states of every layer; logits stay None (lm_head is not executed)
                     outputs = self.engine.lm_outputs(self.engine.taps, *inputs_batch["input_ids"].shape)
             finally:
-                self.engine.taps = None
+                if return_output:
+                    self.engine.taps = None
         return self._shape_like_reference(reward), outputs
 
     __call__ = custom_forward
@@ -191,7 +192,8 @@ class B200QwenRewardModel(B200RewardModel):
                 if return_output:   # hidden_states of every layer; logits stay None (lm_head is not executed)
                     outputs = self.engine.lm_outputs(self.engine.taps, *inputs_batch["input_ids"].shape)
             finally:
-                self.engine.taps = None
+                if return_output:
+                    self.engine.taps = None
         return self._shape_like_reference(reward), outputs
 
     __call__ = custom_forward

@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
-from oracle.ref_harness import build_reference_model, import_reference  # noqa: E402  (the harness shared with
+from oracle.ref_harness import LoraWrapped, build_reference_model, import_reference  # noqa: E402,F401  (the harness shared with
 # bench.py's reference arm and tests/test_reference_gpu.py)
 
 

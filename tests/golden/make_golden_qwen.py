@@ -42,7 +42,7 @@ SEED_W, SEED_X = 1234, 7
 SLIM = dict(hidden_size=512, intermediate_size=1024, num_heads=4, num_kv_heads=2, num_layers=2, vit_depth=4,
             vit_hidden=640, vit_intermediate=856, vit_heads=8, vit_fullatt=[1, 3], vocab_size=152064)
 ATTR_VARIANTS = {"training": {"training": True}, "mean": {"mean_hidden_state": True}}
-ATTR_CASES = {"qwen_slim_bt": ("training", "mean"), "qwen_slim_gpm": ("training",)}
+ATTR_CASES = {"qwen_slim_bt": ("training", "mean"), "qwen_slim_gpm": ("training", "mean")}
 CASES = {
     # name: (cfg overrides, batches [(tag, (h, w) patch grids, seq_len, padding_side)])
     "qwen_slim_bt": (dict(SLIM), [("c", [(16, 24), (22, 10)], None, "left"), ("r", [(8, 8), (34, 18)], None, "left")]),

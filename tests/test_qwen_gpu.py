@@ -631,7 +631,8 @@ def test_qwen_eval_loops_from_uint8_images(tmp_path_factory):
 
 @pytest.mark.parametrize("case", ["qwen_slim_bt", "qwen_slim_gpm"])
 def test_qwen_attribute_variants_vs_reference_golden(case, tmp_path_factory):
-    """`training` (reward read at position S-1) and `mean_hidden_state` (masked mean before the value head) set on the
+    """`training` (reward read at position S-1) and `mean_hidden_state` (masked mean before the value head; with the qwen
+    SkipCA arm: the S x N_pad cross attention of every row, padded keys masked with -1e4, :387-397) set on the
     model object as on the reference's (rw_model_general_preference.py:327-333, 398-448); goldens made by setting them
     on the reference model (tests/golden/make_golden_qwen.py). Right-padded batches are skipped for `training`: position S-1
     is a padded row there, which is not defined behaviour."""
@@ -662,13 +663,7 @@ def test_qwen_attribute_variants_vs_reference_golden(case, tmp_path_factory):
             assert err < REWARD_TOL + 3.0 * floor, key
             checked += 1
     assert checked >= 1
-    if cfg.add_cross_attention:   # the all-rows form of the qwen SkipCA arm is not built: loud, not silent
-        model.mean_hidden_state = True
-        try:
-            with pytest.raises(NotImplementedError):
-                model.custom_forward(inputs_batch=batch)
-        finally:
-            model.mean_hidden_state = None
+    assert model.mean_hidden_state in (None, False)
 
 
 @pytest.mark.parametrize("case", ["qwen_slim_bt", "qwen_slim_gpm", "qwen_wide_gpm"])

@@ -10,16 +10,25 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "llava-reward_b200", "csrc")
 OUTDIR = os.path.join(ROOT, "llava-reward_b200", "lib", "variants")
-# (LR_ATTN_POLY_NUM, LR_ATTN_EARLY_SFREE, LR_ATTN_HOIST_DESC, LR_ATTN_AUX_REGS); r01 measured the first six (all slower
-# than the product (0, 0, 0, 40)); the last three are the MMA-issue-path experiments of DESIGN.md section 11
-VARIANTS = [(0, 0, 0, 40), (0, 1, 0, 40), (1, 1, 0, 40), (2, 1, 0, 40), (1, 0, 0, 40), (3, 1, 0, 40),
-            (0, 0, 1, 40), (0, 0, 0, 48), (0, 0, 1, 48)]
+# (LR_ATTN_POLY_NUM, LR_ATTN_EARLY_SFREE, LR_ATTN_HOIST_DESC, LR_ATTN_AUX_REGS, LR_ATTN_PIPE_LD, LR_ATTN_MAX3, extra -D
+# string); r01 measured the first six (all slower than (0, 0, 0, 40)); then the MMA-issue-path experiments of DESIGN.md
+# section 11; --r02 = the softmax-side experiments of round 2
+VARIANTS = [(0, 0, 0, 40, 0, 0), (0, 1, 0, 40, 0, 0), (1, 1, 0, 40, 0, 0), (2, 1, 0, 40, 0, 0), (1, 0, 0, 40, 0, 0),
+            (3, 1, 0, 40, 0, 0), (0, 0, 1, 40, 0, 0), (0, 0, 0, 48, 0, 0), (0, 0, 1, 48, 0, 0)]
 if "--mma-only" in sys.argv:
     VARIANTS = [v for v in VARIANTS if v[0] == 0 and v[1] == 0]
+if "--r02" in sys.argv:
+    VARIANTS = [(0, 0, 0, 40, 0, 0), (0, 0, 0, 40, 1, 0), (0, 0, 0, 40, 0, 1), (0, 0, 0, 40, 1, 1), (0, 0, 1, 48, 1, 1),
+                (0, 0, 0, 48, 1, 1), (1, 0, 0, 48, 1, 1)]
+for a in sys.argv:
+    if a.startswith("--only="):   # --only=p,e,h,r,l,m[;p,e,h,r,l,m...]
+        VARIANTS = [tuple(int(x) for x in t.split(",")) for t in a[len("--only="):].split(";")]
+EXTRA = [a[len("--define="):] for a in sys.argv if a.startswith("--define=")]
 
 
 def so_path(v):
-    return os.path.join(OUTDIR, f"libattn_p{v[0]}e{v[1]}h{v[2]}r{v[3]}.so")
+    tag = "".join("_" + e.replace("=", "") for e in EXTRA)
+    return os.path.join(OUTDIR, f"libattn_p{v[0]}e{v[1]}h{v[2]}r{v[3]}l{v[4]}m{v[5]}{tag}.so")
 
 
 def build():
@@ -30,7 +39,8 @@ def build():
         cmd = ["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
                "-Xcompiler", "-fPIC", "--use_fast_math", "--prec-div=true", "--prec-sqrt=true", "--fmad=true",
                f"-DLR_ATTN_POLY_NUM={v[0]}", f"-DLR_ATTN_EARLY_SFREE={v[1]}", f"-DLR_ATTN_HOIST_DESC={v[2]}",
-               f"-DLR_ATTN_AUX_REGS={v[3]}", "-shared", "-o", so_path(v), *srcs,
+               f"-DLR_ATTN_AUX_REGS={v[3]}", f"-DLR_ATTN_PIPE_LD={v[4]}", f"-DLR_ATTN_MAX3={v[5]}",
+               *[f"-D{e}" for e in EXTRA], "-shared", "-o", so_path(v), *srcs,
                "-lcudart"]
         procs.append(subprocess.Popen(cmd))
     for p in procs:
@@ -86,7 +96,7 @@ def main():
                 torch.cuda.synchronize()
                 best = min(best, e0.elapsed_time(e1) / 10)
             err = ((o[:T].float() - ref).norm() / ref.norm()).item()
-            print(f"poly {v[0]}/4 early_sfree {v[1]} hoist_desc {v[2]} aux_regs {v[3]} | {name}: {best:.3f} ms = {fl / best / 1e9:.0f} TF/s | rel L2 err vs fp32 "
+            print(f"poly {v[0]}/4 early_sfree {v[1]} hoist_desc {v[2]} aux_regs {v[3]} pipe_ld {v[4]} max3 {v[5]} {' '.join(EXTRA)} | {name}: {best:.3f} ms = {fl / best / 1e9:.0f} TF/s | rel L2 err vs fp32 "
                   f"{err:.3e}", flush=True)
 
 

@@ -58,9 +58,24 @@ def measure(args, model, B, hw, seq_len, iters):
         ts.append((time.perf_counter() - t0) * 1e3)
     launches = (L.launch_count() - n0) // iters
     S = host["c"][0].shape[1]
+    # where the time of ONE forward goes: host time until custom_forward returns (it blocks once, on the token-plan
+    # D2H at its top, then only enqueues) vs the device time between two events around it
+    dev_in = tuple(t.to("cuda") for t in host["c"][:3]) + (host["c"][3],)
+    host_ms, gpu_ms = [], []
+    for _ in range(max(5, iters // 2)):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t0 = time.perf_counter()
+        model.custom_forward(*dev_in)
+        host_ms.append((time.perf_counter() - t0) * 1e3)
+        e1.record()
+        torch.cuda.synchronize()
+        gpu_ms.append(e0.elapsed_time(e1))
     return {"batch_pairs": B, "image_hw": list(hw), "S": S, "ms_per_call_median": statistics.median(ts),
             "ms_min": min(ts), "ms_max": max(ts), "pairs_per_s": B * 1e3 / statistics.median(ts),
-            "launches_per_call": launches}
+            "launches_per_call": launches, "forward_host_enqueue_ms": statistics.median(host_ms),
+            "forward_device_ms": statistics.median(gpu_ms)}
 
 
 def main():

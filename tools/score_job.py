@@ -2,6 +2,10 @@
 (Phi-3.5-V + SkipCA + LoRA r128 + GPM, (1008,1344), max_len 2048) sharded round-robin over the ranks, micro-batches fed
 from pinned host memory, ONE NCCL all-gather of [pairs, 2*vhd+1] at the end. Timing excludes the model
 build and one warm-up micro-batch, includes every H2D copy and the final gather; max over ranks.
+--feed uint8 (default): the host holds uint8 600x800 RGB images (what a JPEG decoder produces; 1.44 MB per image), the
+HD preprocessing runs on the GPU (Phi3VImageProcessorB200: lr_resample_u8 + lr_hd_pack_f32) - 46 MB of H2D per
+32-sample forward. --feed fp32: the reference's layout, [B,17,3,336,336] fp32 pixel_values made on the host
+(1.48 GB per forward; eight processes stacking that on one host is what held r01's job at 7.07x on 8 GPUs).
 Host memory holds a pool of `--pool` distinct micro-batches that the job cycles through (4096 distinct pairs of fp32
 pixels would be 190 GB), so pair i uses pool entry (i // micro) % pool; rank 0 re-scores a few pairs owned by other
 ranks and checks that the gathered rows are bit-identical to its own result.
@@ -31,6 +35,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=4096)
     ap.add_argument("--micro", type=int, default=32)
     ap.add_argument("--pool", type=int, default=2)
+    ap.add_argument("--feed", choices=["uint8", "fp32"], default="uint8")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -49,14 +54,33 @@ def main():
     cfg, eng = model.config, model.engine
 
     # pool of micro-batches in pinned host memory; identical on every rank (seeded by pool slot, not by rank)
+    u8 = a.feed == "uint8"
+    src_h, src_w = 600, 800   # HD_transform -> (1008, 1344): 13 crops / 1921 image tokens, the shape of the fp32 feed
+    if u8:
+        from llava_reward_b200.processing import Phi3VImageProcessorB200
+        from llava_reward_b200.synth import hash_randint
+        proc = Phi3VImageProcessorB200(num_crops=cfg.num_crops, device=dev)
+        pix_slot = torch.empty(a.micro, cfg.num_crops + 1, 3, cfg.image_size, cfg.image_size, dtype=torch.float32,
+                               device=dev)
     pool = []
     for k in range(a.pool):
         entry = {}
         for tag in ("c", "r"):
             ids, mask, pix, sizes = synth_batch(cfg, a.micro, (1008, 1344), 2048, seed=100 + k, tag=tag, device=dev,
                                                 text_len_range=(35, 123))
+            if u8:   # column 2 = the images as uint8 HWC instead of preprocessed fp32 crops
+                pix = hash_randint(f"img.{tag}.{k}", a.micro * src_h * src_w * 3, 0, 256, 7, device=dev) \
+                    .to(torch.uint8).view(a.micro, src_h, src_w, 3)
             entry[tag] = tuple(t.cpu().pin_memory() for t in (ids, mask, pix)) + (sizes.cpu(),)
         pool.append(entry)
+
+    def forward(ids, mask, px, sizes):
+        if u8:   # GPU preprocessing of the n images of this forward into the fp32 crop slot, then the scoring forward
+            n = px.shape[0]
+            pp = proc.preprocess([px[i] for i in range(n)], return_tensors="pt", out=pix_slot[:n])
+            return model.custom_forward(ids, mask, pp["pixel_values"], pp["image_sizes"])[0]
+        return model.custom_forward(ids, mask, px, sizes)[0]
+
     h2d = {"bytes": 0}
     # Double-buffered feeding (the bench's e2e scheme): two pinned staging sets and two device input slots; the rows of
     # the NEXT forward are stacked into pinned memory and copied on a side stream while the current forward runs.
@@ -100,12 +124,12 @@ def main():
             cur.wait_event(slot_ready[s])
             n = len(idx)
             sizes = torch.stack([pool[(i // a.micro) % a.pool][tag][3][i % a.micro] for i in idx])
-            r, _ = model.custom_forward(slots[s][0][:n], slots[s][1][:n], slots[s][2][:n], sizes)
+            r = forward(slots[s][0][:n], slots[s][1][:n], slots[s][2][:n], sizes)
             slot_free[s].record(cur)
             return r
         cols = [torch.stack([pool[(i // a.micro) % a.pool][tag][j][i % a.micro] for i in idx]).to(dev) for j in range(3)]
         sizes = torch.stack([pool[(i // a.micro) % a.pool][tag][3][i % a.micro] for i in idx])
-        return model.custom_forward(*cols, sizes)[0]
+        return forward(*cols, sizes)
 
     def score_batch(pair_idx):
         """pairs `pair_idx` (global indices) -> rewards / probabilities; pair i = row (i % micro) of pool entry
@@ -138,6 +162,7 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": "text-image pairs scored/sec (job)", "value": a.pairs / dt.item(), "unit": "pairs/s",
                           "n_gpus": world, "pairs": a.pairs, "micro_batch_pairs": a.micro, "seconds": dt.item(),
+                          "feed": a.feed, "h2d_gb_per_s_rank0": h2d["bytes"] / dt.item() / 1e9,
                           "h2d_bytes_rank0": h2d["bytes"], "collective": "one all_gather of [pairs, 2*vhd+1] fp32",
                           "gathered_rows_match_local_rescoring": ok, "prob_mean": prob_h.mean().item(),
                           "decisions_chosen": int((prob_h > 0.5).sum())}))
