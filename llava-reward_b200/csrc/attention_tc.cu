@@ -96,6 +96,21 @@ constexpr uint32_t kLayoutSW128 = 2, kLayoutSW64 = 4;
 #ifndef LR_ATTN_PIPE_LD
 #define LR_ATTN_PIPE_LD 0
 #endif
+// LR_ATTN_P_TMEM 1 (head_dim 64, one tile per CTA): P never touches shared memory - the softmax threads write the bf16
+// P row into 64 TMEM columns of their own (tcgen05.st) and the P.V MMA takes its A operand from TMEM
+// (tcgen05.mma ... [d], [a_tmem], b_desc); S 128 + P 64 + O 64 = the CTA's 256 columns, so the row sums move to
+// registers (no ones columns), the P smem buffer, its 16 STS.128 per row and the async-proxy fence disappear and the
+// CTA's shared memory drops from 88 KB to 48 KB. head_dim 96 does not fit (128 + 64 + 96 > 256).
+#ifndef LR_ATTN_P_TMEM
+#define LR_ATTN_P_TMEM 0
+#endif
+// Knock-out experiments (WRONG results, timing only; tools/attn_variants.py --define=LR_ATTN_KO=n): bit 0 replaces the
+// MUFU exponential by one FMUL, bit 1 skips the P stores + the async-proxy fence, bit 2 skips the running max,
+// bit 4 skips the P.V MMAs (commits only), bit 5 skips the S MMAs. They show which resource the product kernel's time
+// is actually sensitive to (profiles/r02_attention_knockouts.txt).
+#ifndef LR_ATTN_KO
+#define LR_ATTN_KO 0
+#endif
 #ifndef LR_ATTN_MAX3
 #define LR_ATTN_MAX3 0
 #endif
@@ -126,7 +141,11 @@ __device__ __forceinline__ float exp2_fma_pipe(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
 }
 __device__ __forceinline__ float softmax_exp2(float x, int idx) {  // idx is a constant after unrolling
+#if LR_ATTN_KO & 1
+  return x * 0.001f;
+#else
   return ((idx & 3) < LR_ATTN_POLY_NUM) ? exp2_fma_pipe(x) : exp2f(x);
+#endif
 }
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -141,6 +160,26 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]: A = 128 lanes x (K/2) 32-bit columns of packed bf16 pairs (K-major), one CTA.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 // NT = query tiles per CTA. NT = 2: one CTA per SM, K/V shared by both tiles, 2-stage rings.
 // NT = 1: one tile per CTA, single-stage K/V, 112 KB of smem and 256 TMEM columns -> TWO CTAs per SM, which de-phases
@@ -153,14 +192,15 @@ struct AttnTcCfg {
   // head_dim 128 with two tiles: S_A, S_B, O_A, O_B take all 512 TMEM columns, so there is no room for the 16 row-sum
   // columns of the ones trick - the softmax threads keep the row sums in registers instead (fp32 sum of the un-rounded
   // exponentials, like flash-attention 2) - and 227 KB of smem allow only a single K/V stage.
-  static constexpr bool kOnes = !(HD == 128 && NT == 2);
+  static constexpr bool kPTmem = LR_ATTN_P_TMEM && HD == 64 && NT == 1;
+  static constexpr bool kOnes = !(HD == 128 && NT == 2) && !kPTmem;
   static constexpr int kStages = !kOnePerSm ? 1 : (kOnes ? 2 : 1);
   static constexpr int kTmemCols = kOnePerSm ? 512 : 256;
   static constexpr int kAtoms = HD / 32;
   static constexpr int kTileBytes = kAtoms * kAtomBytes;         // one Q / K tile, and the TMA-loaded part of a V tile
   static constexpr int kVTileBytes = (kAtoms + (kOnes ? 1 : 0)) * kAtomBytes;  // V tile + one atom of ones (row sums via the MMA)
   static constexpr int kSmemBytes = NT * kTileBytes /*Q*/ + kStages * kTileBytes /*K*/ + kStages * kVTileBytes /*V*/ +
-                                    NT * kPBytes + 256 /*barriers*/ + (NT == 2 ? 2048 : 0) /*row-max exchange*/;
+                                    (kPTmem ? 0 : NT * kPBytes) + 256 /*barriers*/ + (NT == 2 ? 2048 : 0) /*row-max exchange*/;
 };
 
 // SPLIT = threads per query row in the softmax: 1 -> one thread owns the whole 128-column S row (2 warpgroups,
@@ -189,7 +229,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
   uint8_t* sK = sQ + NT * TILE;          // [NS][TILE]
   uint8_t* sV = sK + NS * TILE;          // [NS][VTILE]
   uint8_t* sP = sV + NS * VTILE;         // [NT][kPBytes]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NT * kPBytes);
+  constexpr bool PTMEM = Cfg::kPTmem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (PTMEM ? 0 : NT * kPBytes));
   uint64_t* q_full = bars;               // [1]
   uint64_t* k_full = bars + 1;           // [2]
   uint64_t* k_empty = bars + 3;          // [2]
@@ -291,7 +332,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
   const uint32_t tmem_base = *tmem_slot;
   // NT = 2: S_A 0, S_B 128, O_A 256, O_B 384;  NT = 1: S 0, O 128
   const uint32_t tm_S[2] = {tmem_base, tmem_base + 128};
-  const uint32_t tm_O[2] = {tmem_base + (NT == 2 ? 256 : 128), tmem_base + 384};
+  const uint32_t tm_O[2] = {tmem_base + (NT == 2 ? 256 : (PTMEM ? 192 : 128)), tmem_base + 384};
+  const uint32_t tm_P = tmem_base + 128;   // PTMEM: 64 columns of packed bf16 pairs
 
   // register re-allocation between warpgroups: the softmax threads keep a whole 128-column S row in registers
   if (warp < 4) {
@@ -370,7 +412,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         const uint64_t qd = umma_desc(qa, 16, 512, kLayoutSW64), kd = umma_desc(ka, 16, 512, kLayoutSW64);
 #endif
 #pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk) {
+        for (int kk = 0; kk < ((LR_ATTN_KO & 32) ? 0 : HD / 16); ++kk) {
           const uint32_t off = (kk >> 1) * kAtomBytes + (kk & 1) * 32;
 #if LR_ATTN_HOIST_DESC
           // the start-address field holds (addr >> 4) in 14 bits; shared memory ends below 2^18, so the add cannot carry
@@ -384,12 +426,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         umma_commit(&k_empty[ks]);
       };
       auto issue_pv = [&](int vs, bool acc) {  // O_x += P_x V : A = P (K-major, SW128), B = V (MN-major, SW64)
+        if constexpr (PTMEM) {   // A = P from TMEM: MMA kk consumes keys [16 kk, 16 kk + 16) = 8 packed columns
+          const uint32_t va = smem_u32(sV + vs * VTILE);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16_ts(tm_O[x], tm_P + kk * 8, umma_desc(va + kk * 1024, kAtomBytes, 512, kLayoutSW64), idesc_o,
+                         acc || kk != 0);
+          umma_commit(&pv_done[x]);
+          umma_commit(&v_empty[vs]);
+          return;
+        }
         const uint32_t pa = smem_u32(sP + x * kPBytes), va = smem_u32(sV + vs * VTILE);
 #if LR_ATTN_HOIST_DESC
         const uint64_t pd = umma_desc(pa, 16, 1024, kLayoutSW128), vd = umma_desc(va, kAtomBytes, 512, kLayoutSW64);
 #endif
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
+        for (int kk = 0; kk < ((LR_ATTN_KO & 16) ? 0 : 8); ++kk) {
 #if LR_ATTN_HOIST_DESC
           umma_bf16_ss(tm_O[x], pd + (((kk >> 2) * (kPBytes / 2) + (kk & 3) * 32) >> 4), vd + ((kk * 1024) >> 4), idesc_o,
                        acc || kk != 0);
@@ -521,7 +573,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
           tmem_ld_wait_dep(sv[c]);
           if (c + 1 < NCH) tmem_ld_32x32(tm_S[x] + lane_addr + (c + 1) * 32, sv[c + 1]);
           if (need_mask) mask_chunk(c);
-          max_chunk(c);
+          if (!(LR_ATTN_KO & 4)) max_chunk(c);
         }
         if (tr) ATTN_TRACE(1 + x, 2, j);
       } else {
@@ -539,7 +591,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
           for (int c = 0; c < NCH; ++c) mask_chunk(c);
         }
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) max_chunk(c);
+        for (int c = 0; c < NCH; ++c)
+          if (!(LR_ATTN_KO & 4)) max_chunk(c);
       }
       float mx = fmaxf(fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3])), fmaxf(fmaxf(mxc[4], mxc[5]), fmaxf(mxc[6], mxc[7])));
       if constexpr (SPLIT == 2) {
@@ -607,14 +660,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
           pk[i] = pack_bf16x2(p0, p1);
         }
         const int cg = h * NCH + c;  // chunk index inside the 128-column row
+        if constexpr (PTMEM) {   // 32 keys = 16 packed columns of this thread's own TMEM lane
+          tmem_st_32x16(tm_P + lane_addr + cg * 16, pk);
+          continue;
+        }
         uint8_t* base = prow + (cg >> 1) * (kPBytes / 2);
+#if LR_ATTN_KO & 2
+        if (pk[0] == 0x12345678u && pk[15] == 0x9abcdef0u) *reinterpret_cast<uint4*>(base) = make_uint4(pk[0], pk[5], pk[9], pk[15]);
+#else
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int chunk = ((cg & 1) * 4 + t) ^ (r & 7);
           *reinterpret_cast<uint4*>(base + (chunk << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
         }
+#endif
       }
-      fence_proxy_async_smem();  // P (generic-proxy stores) must be visible to the tensor core's async proxy
+#if !(LR_ATTN_KO & 2)
+      if constexpr (PTMEM) tmem_st_wait();   // the tcgen05.st of the P row have landed
+      else fence_proxy_async_smem();  // P (generic-proxy stores) must be visible to the tensor core's async proxy
+#endif
       if (tr) ATTN_TRACE(1 + x, 5, j);
       tc_fence_before();
       __syncwarp();
@@ -627,6 +691,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     bf16* orow = o + size_t(slot_row0 + row_abs) * ld_o + head * HD;
     if (nx > 0) {
       mbar_wait(&o_final[x], tq & 1);
+      // the last block's pv_done phase completed together with o_final (same commit point); observing it here keeps
+      // every phase of that barrier waited-on before the next tile arrives on it again (compute-sanitizer synccheck)
+      mbar_wait(&pv_done[x], (g + nx - 1) & 1);
       tc_fence_after();
       float inv;
       if constexpr (!ONES) {

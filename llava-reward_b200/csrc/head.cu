@@ -37,18 +37,19 @@ skipca_scores_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict
   if (lane == 0) scores[size_t(b) * max_nv + j] = (j < nv) ? bf16_round(bf16_round(acc) * inv_sqrt_d) : pad_score;
 }
 
-// A CLUSTER of kHeadCluster CTAs per sample (one CTA without cross attention): every CTA recomputes the softmax
-// statistics of the sample's max_nv scores (7.7 KB, L2), takes a contiguous slice of the V rows and accumulates
-// P.V for it (two thread groups alternate rows, 4 rows = 64 B per thread in flight); the partial sums meet in the
-// shared memory of cluster rank 0 through DSMEM in a fixed order (bit-reproducible), which then does
-// y = x + out, RMSNorm, value head. 32 samples -> 256 CTAs instead of 32: the 378 MB of V rows of a config-2
-// forward stream at HBM speed instead of from 32 SMs.
-constexpr int kHeadThreads = 1024;  // two groups of H/8 threads split the P.V rows: H <= 4096 with SkipCA
+// A CLUSTER of kHeadCluster CTAs per sample (one CTA without cross attention), H/8 threads each (one thread per
+// 16-byte chunk of a row): every CTA recomputes the softmax statistics of the sample's max_nv scores (7.7 KB, L2),
+// takes a contiguous slice of the V rows and accumulates P.V for it with 8 rows = 128 B per thread in flight; the
+// partial sums meet in cluster rank 0 through DSMEM in a fixed order (bit-reproducible), which then does
+// y = x + out, RMSNorm, value head. 32 samples -> 256 CTAs of 384 threads (several per SM, one wave) instead of 32
+// CTAs: the 378 MB of V rows of a config-2 forward stream at HBM speed instead of from 32 SMs.
+constexpr int kHeadMaxThreads = 1024;  // H <= 8192
 constexpr int kHeadMaxNv = 4096;
 constexpr int kHeadCluster = 8;
-constexpr int kHeadSlice = kHeadMaxNv / kHeadCluster;
+constexpr int kHeadSlice = kHeadMaxNv / kHeadCluster + 2;
+constexpr int kHeadRows = 8;           // V rows in flight per thread
 
-__global__ void __launch_bounds__(kHeadThreads)
+__global__ void __launch_bounds__(kHeadMaxThreads)
 skipca_head_kernel(const float* __restrict__ scores, const bf16* __restrict__ kv, int ldkv,
                    const int* __restrict__ plan, const bf16* __restrict__ x, int ldx, const bf16* __restrict__ ln_w,
                    const bf16* __restrict__ vh_w, bf16* __restrict__ reward, int H, int max_nv, int vhd, float eps) {
@@ -57,75 +58,71 @@ skipca_head_kernel(const float* __restrict__ scores, const bf16* __restrict__ kv
   __shared__ float red[32];
   __shared__ float prob[kHeadSlice];
   extern __shared__ __align__(16) uint8_t hd_smem[];
-  float* part = reinterpret_cast<float*>(hd_smem);  // [2][H] partial PV sums of this CTA
+  float* part = reinterpret_cast<float*>(hd_smem);  // [H] partial PV sums of this CTA
   const int ncta = cluster.num_blocks(), rank = cluster.block_rank();
-  const int b = blockIdx.x / ncta, tid = threadIdx.x;
-  const int cpr = H >> 3;              // 16-byte chunks per row (384 for H=3072)
-  const int grp = tid / cpr;           // 0 or 1 (threads >= 2*cpr idle in the PV loop)
-  const int ch = tid % cpr;
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int b = blockIdx.x / ncta, tid = threadIdx.x, nthr = blockDim.x;
+  const bool own = tid < (H >> 3);     // this thread owns columns [8 tid, 8 tid + 8)
   if (scores) {
     const int row_base = plan[b * LR_PLAN_STRIDE + LR_PLAN_ROW_BASE], nv = plan[b * LR_PLAN_STRIDE + LR_PLAN_NV];
     const float* sc = scores + size_t(b) * max_nv;
     float mx = -INFINITY;
-    for (int j = tid; j < max_nv; j += kHeadThreads) mx = fmaxf(mx, sc[j]);
+    for (int j = tid; j < max_nv; j += nthr) mx = fmaxf(mx, sc[j]);
     mx = block_max(mx, red);
     float sum = 0.f;
-    for (int j = tid; j < max_nv; j += kHeadThreads) sum += __expf(sc[j] - mx);
+    for (int j = tid; j < max_nv; j += nthr) sum += __expf(sc[j] - mx);
     sum = block_sum(sum, red);
     const float inv = 1.f / sum;
     // this CTA's slice of the real rows (the zero-padded rows nv <= j < max_nv only feed the denominator)
-    const int per = (((nv + ncta - 1) / ncta) + 1) & ~1;
+    const int per = (nv + ncta - 1) / ncta;
     const int j0 = min(rank * per, nv), j1 = min(j0 + per, nv);
-    for (int j = j0 + tid; j < j1; j += kHeadThreads)
+    for (int j = j0 + tid; j < j1; j += nthr)
       prob[j - j0] = bf16_round(__expf(sc[j] - mx) * inv);  // softmax output is bf16
     __syncthreads();
-    if (grp < 2) {
-      const bf16* vbase = kv + size_t(row_base) * ldkv + H + ch * 8;  // V = second half of the [K|V] row
-      int j = j0 + grp;
-      for (; j + 6 < j1; j += 8) {  // 4 rows in flight per thread
-        uint4 u[4];
+    if (own) {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const bf16* vbase = kv + size_t(row_base) * ldkv + H + tid * 8;  // V = second half of the [K|V] row
+      int j = j0;
+      for (; j + kHeadRows <= j1; j += kHeadRows) {
+        uint4 u[kHeadRows];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) u[t] = ldg128(vbase + size_t(j + 2 * t) * ldkv);
+        for (int t = 0; t < kHeadRows; ++t) u[t] = ldg128(vbase + size_t(j + t) * ldkv);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float p = prob[j + 2 * t - j0];
+        for (int t = 0; t < kHeadRows; ++t) {
+          const float p = prob[j + t - j0];
           float2 f0 = unpack_bf16x2(u[t].x), f1 = unpack_bf16x2(u[t].y), f2 = unpack_bf16x2(u[t].z),
                  f3 = unpack_bf16x2(u[t].w);
           acc[0] += p * f0.x, acc[1] += p * f0.y, acc[2] += p * f1.x, acc[3] += p * f1.y;
           acc[4] += p * f2.x, acc[5] += p * f2.y, acc[6] += p * f3.x, acc[7] += p * f3.y;
         }
       }
-      for (; j < j1; j += 2) {
+      for (; j < j1; ++j) {
         const uint4 u = ldg128(vbase + size_t(j) * ldkv);
         const float p = prob[j - j0];
         float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
         acc[0] += p * f0.x, acc[1] += p * f0.y, acc[2] += p * f1.x, acc[3] += p * f1.y;
         acc[4] += p * f2.x, acc[5] += p * f2.y, acc[6] += p * f3.x, acc[7] += p * f3.y;
       }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) part[grp * H + ch * 8 + e] = acc[e];
+      *reinterpret_cast<float4*>(part + tid * 8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(part + tid * 8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
     cluster.sync();  // every CTA's partial sums are visible cluster-wide
   }
   if (rank == 0) {
-    // y = bf16(x + bf16(attn_out)); RMSNorm; value head. Threads of group 0 own 8 columns each.
+    // y = bf16(x + bf16(attn_out)); RMSNorm; value head. Owning threads hold 8 columns each.
     float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float ss = 0.f;
-    if (grp == 0) {
-      const uint4 u = ldg128(x + size_t(b) * ldx + ch * 8);
+    if (own) {
+      const uint4 u = ldg128(x + size_t(b) * ldx + tid * 8);
       float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
       y[0] = f0.x, y[1] = f0.y, y[2] = f1.x, y[3] = f1.y, y[4] = f2.x, y[5] = f2.y, y[6] = f3.x, y[7] = f3.y;
       if (scores) {
         float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int r = 0; r < ncta; ++r) {  // fixed order: rank 0 .. ncta-1, group 0 then group 1
+        for (int r = 0; r < ncta; ++r) {  // fixed order: rank 0 .. ncta-1
           const float* rp = cluster.map_shared_rank(part, r);
-          const float4 a0 = *reinterpret_cast<const float4*>(rp + ch * 8);
-          const float4 a1 = *reinterpret_cast<const float4*>(rp + ch * 8 + 4);
-          const float4 b0 = *reinterpret_cast<const float4*>(rp + H + ch * 8);
-          const float4 b1 = *reinterpret_cast<const float4*>(rp + H + ch * 8 + 4);
-          o[0] += a0.x + b0.x, o[1] += a0.y + b0.y, o[2] += a0.z + b0.z, o[3] += a0.w + b0.w;
-          o[4] += a1.x + b1.x, o[5] += a1.y + b1.y, o[6] += a1.z + b1.z, o[7] += a1.w + b1.w;
+          const float4 a0 = *reinterpret_cast<const float4*>(rp + tid * 8);
+          const float4 a1 = *reinterpret_cast<const float4*>(rp + tid * 8 + 4);
+          o[0] += a0.x, o[1] += a0.y, o[2] += a0.z, o[3] += a0.w;
+          o[4] += a1.x, o[5] += a1.y, o[6] += a1.z, o[7] += a1.w;
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -137,8 +134,8 @@ skipca_head_kernel(const float* __restrict__ scores, const bf16* __restrict__ kv
     if (scores) {
       ss = block_sum(ss, red);
       const float rstd = rsqrtf(ss / float(H) + eps);
-      if (grp == 0) {
-        const uint4 u = ldg128(ln_w + ch * 8);
+      if (own) {
+        const uint4 u = ldg128(ln_w + tid * 8);
         float2 g0 = unpack_bf16x2(u.x), g1 = unpack_bf16x2(u.y), g2 = unpack_bf16x2(u.z), g3 = unpack_bf16x2(u.w);
         const float g[8] = {g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, g3.x, g3.y};
 #pragma unroll
@@ -147,8 +144,8 @@ skipca_head_kernel(const float* __restrict__ scores, const bf16* __restrict__ kv
     }
     for (int d = 0; d < vhd; ++d) {
       float dot = 0.f;
-      if (grp == 0) {
-        const uint4 u = ldg128(vh_w + size_t(d) * H + ch * 8);
+      if (own) {
+        const uint4 u = ldg128(vh_w + size_t(d) * H + tid * 8);
         float2 w0 = unpack_bf16x2(u.x), w1 = unpack_bf16x2(u.y), w2 = unpack_bf16x2(u.z), w3 = unpack_bf16x2(u.w);
         dot = y[0] * w0.x + y[1] * w0.y + y[2] * w1.x + y[3] * w1.y + y[4] * w2.x + y[5] * w2.y + y[6] * w3.x +
               y[7] * w3.y;
@@ -282,18 +279,16 @@ extern "C" int lr_skipca_scores(const void* q, int ldq, const void* kv, int ldkv
 extern "C" int lr_skipca_head(const float* scores, const void* kv, int ldkv, const int* plan, const void* x, int ldx,
                               const void* ca_ln_w, const void* value_head_w, void* reward, int B, int H, int max_nv,
                               int vhd, float eps, void* stream) {
-  // with cross-attention two thread groups split the P.V rows (H <= 4096); the value-head-only form needs one
-  // thread per 8 columns (H <= 8192: the 4096 / 5120 wide Vicuna decoders of the LLaVA-v1.6 branch)
-  LR_CHECK_ARG(x && value_head_w && reward && B > 0 && H > 0 && H % 8 == 0 && vhd > 0 &&
-               (H / 8) * (scores ? 2 : 1) <= kHeadThreads);
+  // one thread per 8 columns: H <= 8192 (the 4096 / 5120 wide Vicuna decoders of the LLaVA-v1.6 branch included)
+  LR_CHECK_ARG(x && value_head_w && reward && B > 0 && H > 0 && H % 8 == 0 && vhd > 0 && H / 8 <= kHeadMaxThreads);
   if (scores) LR_CHECK_ARG(kv && plan && ca_ln_w && max_nv > 0 && max_nv <= kHeadMaxNv);
   if ((ldx % 8) || !aligned16(x) || !aligned16(value_head_w) || (scores && ((ldkv % 8) || !aligned16(kv))))
     return LR_ERR_ALIGN;
   cudaLaunchConfig_t cfg = {};
   const int ncta = scores ? kHeadCluster : 1;
   cfg.gridDim = dim3(B * ncta);
-  cfg.blockDim = dim3(kHeadThreads);
-  cfg.dynamicSmemBytes = scores ? 2 * H * sizeof(float) : 0;
+  cfg.blockDim = dim3((H / 8 + 31) / 32 * 32);
+  cfg.dynamicSmemBytes = scores ? H * sizeof(float) : 0;
   cfg.stream = reinterpret_cast<cudaStream_t>(stream);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;

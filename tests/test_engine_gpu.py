@@ -617,3 +617,22 @@ def test_vision_layer_id_vs_reference_golden(tmp_path_factory):
             assert torch.equal(r1, r0)
     finally:
         model.vision_layer_id = -1
+
+
+def test_device_prefetcher_pinned_memory_is_bounded_for_ragged_batches():
+    """ragged inputs (a new shape almost every batch) must not grow the pinned staging memory without
+    bound - one byte arena per staging set, grown to the largest batch seen."""
+    from llava_reward_b200.feed import DevicePrefetcher
+    g = torch.Generator().manual_seed(0)
+    sizes = [int(x) for x in torch.randint(1000, 200000, (40,), generator=g)]
+    batches = [{"a": torch.randn(n, generator=g), "b": (torch.arange(n // 7, dtype=torch.int64), "meta")} for n in sizes]
+    pf = DevicePrefetcher(batches, device="cuda", depth=2)
+    seen = 0
+    for ref, out in zip(batches, pf):
+        assert out["a"].is_cuda and torch.equal(out["a"].cpu(), ref["a"]) and torch.equal(out["b"][0].cpu(), ref["b"][0])
+        assert out["b"][1] == "meta"
+        seen += 1
+    assert seen == len(batches)
+    biggest = max(n * 4 + (n // 7) * 8 for n in sizes)
+    assert pf.pinned_bytes <= 2 * (1.25 * biggest + 1024), (pf.pinned_bytes, biggest)
+    assert pf.h2d_bytes == sum(n * 4 + (n // 7) * 8 for n in sizes)
