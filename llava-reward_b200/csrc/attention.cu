@@ -3,6 +3,8 @@
 //   head_dim 96, causal     : Phi-3 decoder, one contiguous valid run per (left-padded) sequence slot
 // Round-1 kernel: 128 query rows per CTA (8 warps x 16 rows), 64-row K/V tiles double-buffered with cp.async,
 // QK^T and PV on mma.sync.m16n8k16 (bf16, fp32 accumulate), ldmatrix from padded (conflict-free) smem rows.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace lr {
@@ -270,6 +272,10 @@ extern "C" int lr_attention_bf16(const void* q, const void* k, const void* v, vo
     // 4 = the one-tile pipeline walking several query tiles per CTA
     int variant = impl == LR_ATTN_TCGEN05_SPLIT ? 2 : (impl == LR_ATTN_TCGEN05_2TILE ? 1 : 3);
     if (impl == LR_ATTN_TCGEN05_MULTITILE || impl == LR_ATTN_TCGEN05) variant = head_dim == 128 ? kHd128Product : 4;
+    if (const char* e = getenv("LR_ATTN_VARIANT")) {  // kernel experiments only (tools/attn_variants.py)
+      const int v = atoi(e);
+      if (v > 0) variant = v;
+    }
     return attention_tc(q, k, v, o, ld_qkv, ld_o, n_seq * rows_per_seq, n_seq, rows_per_seq, nullptr, seq_start, seq_len,
                         n_heads, n_heads, head_dim, causal, scale, variant, s);
   }

@@ -102,11 +102,12 @@ constexpr uint32_t kLayoutSW128 = 2, kLayoutSW64 = 4;
 // registers (no ones columns), the P smem buffer, its 16 STS.128 per row and the async-proxy fence disappear and the
 // CTA's shared memory drops from 88 KB to 48 KB. head_dim 96 does not fit (128 + 64 + 96 > 256).
 #ifndef LR_ATTN_P_TMEM
-#define LR_ATTN_P_TMEM 0
+#define LR_ATTN_P_TMEM 1   // product since r02: CLIP attention 1.265 -> 1.199 ms (profiles/r02_attention_knockouts.txt)
 #endif
 // Knock-out experiments (WRONG results, timing only; tools/attn_variants.py --define=LR_ATTN_KO=n): bit 0 replaces the
 // MUFU exponential by one FMUL, bit 1 skips the P stores + the async-proxy fence, bit 2 skips the running max,
-// bit 4 skips the P.V MMAs (commits only), bit 5 skips the S MMAs. They show which resource the product kernel's time
+// bit 4 skips the P.V MMAs (commits only), bit 5 skips the S MMAs, bit 6 keeps the P stores but drops the async-proxy
+// fence, bit 7 loads K / V by TMA only for the first block of a tile (later blocks reuse the stale tile: no L2 traffic). They show which resource the product kernel's time
 // is actually sensitive to (profiles/r02_attention_knockouts.txt).
 #ifndef LR_ATTN_KO
 #define LR_ATTN_KO 0
@@ -370,18 +371,26 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
                                 slot_row0 + m0 + x * 128);
             }
             const int s = (g + kj) % NS;
-            mbar_arrive_expect_tx(&k_full[s], TILE);
-            for (int a = 0; a < NA; ++a)
-              tma_load_2d(sK + s * TILE + a * kAtomBytes, &tm_qkv, &k_full[s], k_col0 + kv_head * HD + a * 32,
-                          slot_row0 + start + kj * 128);
+            if ((LR_ATTN_KO & 128) && kj > 0) {
+              mbar_arrive(&k_full[s]);
+            } else {
+              mbar_arrive_expect_tx(&k_full[s], TILE);
+              for (int a = 0; a < NA; ++a)
+                tma_load_2d(sK + s * TILE + a * kAtomBytes, &tm_qkv, &k_full[s], k_col0 + kv_head * HD + a * 32,
+                            slot_row0 + start + kj * 128);
+            }
             ++kj;
           }
           if (vj < n && vj < kj && mbar_test_wait(&v_empty[(g + vj) % NS], (((g + vj) / NS) & 1) ^ 1)) {
             const int s = (g + vj) % NS;
-            mbar_arrive_expect_tx(&v_full[s], TILE);
-            for (int a = 0; a < NA; ++a)
-              tma_load_2d(sV + s * VTILE + a * kAtomBytes, &tm_qkv, &v_full[s], v_col0 + kv_head * HD + a * 32,
-                          slot_row0 + start + vj * 128);
+            if ((LR_ATTN_KO & 128) && vj > 0) {
+              mbar_arrive(&v_full[s]);
+            } else {
+              mbar_arrive_expect_tx(&v_full[s], TILE);
+              for (int a = 0; a < NA; ++a)
+                tma_load_2d(sV + s * VTILE + a * kAtomBytes, &tm_qkv, &v_full[s], v_col0 + kv_head * HD + a * 32,
+                            slot_row0 + start + vj * 128);
+            }
             ++vj;
           }
         }
@@ -503,7 +512,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     __syncwarp();
   }
   } else {
-    if constexpr (NT == 1) {
+    if constexpr (NT == 1 && SPLIT == 2) {
+      // experiment (tools/attn_variants.py --split): two threads per row, 384 threads x 80 registers at launch,
+      // re-split 128 x 40 + 256 x 96
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+    } else if constexpr (NT == 1) {
       // 2 CTAs/SM: the CTA's 256 x 128 registers are re-split 128 x AUX + 128 x (256 - AUX) (40 + 208 leaves 8 unused)
       asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(LR_ATTN_AUX_REGS <= 48 ? 208 : 256 - LR_ATTN_AUX_REGS));
     } else if constexpr (SPLIT == 1) {
@@ -666,7 +679,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         }
         uint8_t* base = prow + (cg >> 1) * (kPBytes / 2);
 #if LR_ATTN_KO & 2
-        if (pk[0] == 0x12345678u && pk[15] == 0x9abcdef0u) *reinterpret_cast<uint4*>(base) = make_uint4(pk[0], pk[5], pk[9], pk[15]);
+        {  // keep every exponential and pack alive (XOR of all packed words), store (practically) never
+          uint32_t live = 0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) live ^= pk[i];
+          if (live == 0x12345678u) *reinterpret_cast<uint4*>(base) = make_uint4(pk[0], pk[5], pk[9], live);
+        }
 #else
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -675,7 +693,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         }
 #endif
       }
-#if !(LR_ATTN_KO & 2)
+#if !(LR_ATTN_KO & 2) && !(LR_ATTN_KO & 64)
       if constexpr (PTMEM) tmem_st_wait();   // the tcgen05.st of the P row have landed
       else fence_proxy_async_smem();  // P (generic-proxy stores) must be visible to the tensor core's async proxy
 #endif
@@ -787,7 +805,7 @@ static int launch_attn_tc(const void* base, int total_rows, int ld_qkv, int q_co
   auto kern = attn_tc_kernel<HD, CAUSAL, SPLIT, NT>;
   {  // per-device attribute, set once per (kernel, device)
     static bool attr_done[64] = {};   // one array per instantiation of this launch template = per kernel
-    cudaError_t e = ensure_smem_attr(kern, Cfg::kSmemBytes, attr_done);
+    cudaError_t e = ensure_smem_attr(kern, Cfg::kSmemBytes + ((SPLIT == 2 && NT == 1) ? 1024 : 0), attr_done);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
   // several query tiles per CTA (see the kernel): single-stage K/V ring only, not for the segment layout
@@ -807,7 +825,8 @@ static int launch_attn_tc(const void* base, int total_rows, int ld_qkv, int q_co
     }
   }
   dim3 grid(gx, n_heads, n_seq);
-  kern<<<grid, 128 + 128 * NT * SPLIT, Cfg::kSmemBytes, stream>>>(tm, reinterpret_cast<bf16*>(o), ld_o, rows_per_seq, seq_base,
+  constexpr int kSmem = Cfg::kSmemBytes + ((SPLIT == 2 && NT == 1) ? 1024 : 0);   // row-max exchange of the experiment
+  kern<<<grid, 128 + 128 * NT * SPLIT, kSmem, stream>>>(tm, reinterpret_cast<bf16*>(o), ld_o, rows_per_seq, seq_base,
                                                       seq_start, seq_len, q_col0, k_col0, v_col0, kv_group,
                                                       scale * 1.4426950408889634f, row_lo, row_hi, tile_mode);
   return lr_launch_status();
@@ -829,6 +848,7 @@ int attention_tc(const void* q, const void* k, const void* v, void* o, int ld_qk
     if (split == 2) return launch_attn_tc<HD_, CAUSAL_, 2, 2>(LR_ATTN_ARGS);           \
     if (split == 3) return launch_attn_tc<HD_, CAUSAL_, 1, 1>(LR_ATTN_ARGS);           \
     if (split == 4) return launch_attn_tc<HD_, CAUSAL_, 1, 1>(LR_ATTN_ARGS, nullptr, nullptr, true); \
+    if (split == 6) return launch_attn_tc<HD_, CAUSAL_, 2, 1>(LR_ATTN_ARGS, nullptr, nullptr, true); \
     return launch_attn_tc<HD_, CAUSAL_, 1, 2>(LR_ATTN_ARGS);                           \
   }
   LR_ATTN_CASE(64, false)

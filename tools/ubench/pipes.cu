@@ -48,6 +48,41 @@ __global__ void __launch_bounds__(512) k(float* out, int iters, long long* cycle
         unsigned short r;
         asm volatile("cvt.rn.bf16.f32 %0, %1;" : "=h"(r) : "f"(a[i]));
         acc ^= r;
+      } else if (MODE == 8) {  // MUFU.EX2 on packed f16x2 (two exponentials per instruction)
+        uint32_t& u = reinterpret_cast<uint32_t&>(a[i]);
+        asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(u));
+      } else if (MODE == 9) {  // MUFU.EX2 on packed bf16x2
+        uint32_t& u = reinterpret_cast<uint32_t&>(a[i]);
+        asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(u));
+      } else if (MODE == 10) {  // HFMA2 (f16x2)
+        uint32_t& u = reinterpret_cast<uint32_t&>(a[i]);
+        asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(u) : "r"(0x3c003c00u), "r"(0x38003800u));
+      } else if (MODE == 11) {  // HMNMX2 (f16x2 max)
+        uint32_t& u = reinterpret_cast<uint32_t&>(a[i]);
+        asm volatile("max.f16x2 %0, %0, %1;" : "+r"(u) : "r"(reinterpret_cast<uint32_t&>(a[(i + 1) & 15])));
+      } else if (MODE == 12) {  // cvt.rn.f16x2.f32 pack
+        uint32_t r;
+        asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a[i]), "f"(a[(i + 1) & 15]));
+        acc ^= r;
+      } else if (MODE == 13) {  // the f16x2 softmax mix per PAIR of elements: pack + max + fma + ex2
+        uint32_t r;
+        asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a[i]), "f"(a[(i + 1) & 15]));
+        asm volatile("max.f16x2 %0, %0, %1;" : "+r"(acc) : "r"(r));
+        asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(r) : "r"(0x3c003c00u), "r"(0xb800b800u));
+        asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(r));
+        acc ^= r;
+      } else if (MODE == 14) {  // the f32 softmax mix per PAIR of elements: 2 max + 2 ffma + 2 ex2 + 1 pack
+        float x0 = a[i], x1 = a[(i + 1) & 15];
+        float m = __uint_as_float(acc);
+        asm volatile("max.f32 %0, %0, %1;" : "+f"(m) : "f"(x0));
+        asm volatile("max.f32 %0, %0, %1;" : "+f"(m) : "f"(x1));
+        asm volatile("fma.rn.ftz.f32 %0, %0, %1, %2;" : "+f"(x0) : "f"(1.0001f), "f"(-0.5f));
+        asm volatile("fma.rn.ftz.f32 %0, %0, %1, %2;" : "+f"(x1) : "f"(1.0001f), "f"(-0.5f));
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x0));
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x1));
+        uint32_t r;
+        asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x0), "f"(x1));
+        acc = __float_as_uint(m) ^ (r & 1u);
       }
     }
   }
@@ -90,6 +125,13 @@ int main() {
   run<3>("MUFU + F2FP 2:1, per exp", 1);
   run<4>("MUFU + int pack 2:1, per exp", 1);
   run<6>("FFMA + MUFU 1:1, per exp", 1);
+  run<8>("ex2.approx.f16x2, per INSTR (2 exps)", 1);
+  run<9>("ex2.approx.ftz.bf16x2, per INSTR (2 exps)", 1);
+  run<10>("fma.rn.f16x2 (HFMA2), per instr", 1);
+  run<11>("max.f16x2 (HMNMX2), per instr", 1);
+  run<12>("cvt.rn.f16x2.f32 pack, per instr", 1);
+  run<13>("f16x2 softmax mix, per PAIR of elements", 1);
+  run<14>("f32 softmax mix, per PAIR of elements", 1);
   printf("cuda status %d\n", (int)cudaGetLastError());
   return 0;
 }
