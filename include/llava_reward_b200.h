@@ -323,6 +323,42 @@ int lr_masked_mean_rows_bf16(const void* x, int ldx, const int64_t* attention_ma
  * 4.4 G values are generated in place on the device instead of being shipped. out fp32 [n]. */
 int lr_synth_normal_f32(void* out, int64_t n, uint32_t key, float scale, float mean, int add_mean, void* stream);
 
+/* ---- fp32 verification path (csrc/f32_verify.cu) -------------------------------------------------------------------
+ * Plain fp32 CUDA-core kernels WITHOUT any bf16 rounding point, used by RewardEngine(precision="fp32") to show the
+ * engine's dataflow, layouts and index work against the reference's fp32 outputs at 1e-4 (north_star; SURVEY 8d
+ * parity gates). All tensors fp32, same operand layouts as the bf16 entries they mirror (W is [N, K] row-major, the
+ * LoRA K-extension, head-interleaved q/k rows, [gate128|up128] blocks). Debug only: not a scoring path.
+ * The byte-moving product kernels serve fp32 rows unchanged: lr_gather_rows_bf16 / lr_embed_scatter_bf16 are called
+ * with every width and leading dimension doubled; lr_f32_hd_gather is hd_gather_kernel on 2048 two-byte units. */
+int lr_f32_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K, int epilogue,
+                const void* bias, const void* R, int ldr, void* stream); /* NONE, BIAS, BIAS_QUICKGELU, BIAS_GELU,
+                                                                            RESIDUAL, BIAS_RESIDUAL */
+int lr_f32_swiglu(const void* raw, int ldr, void* out, int ldo, int M, int N, void* stream); /* out[:, N/2] from the
+                                                   packed [gate128|up128] columns of raw (Phi3MLP, modeling_phi3_v.py:566-572) */
+int lr_f32_rope(void* x, int ld, const int* position_ids, const void* cos_tab, const void* sin_tab, int rows,
+                int rope_cols, int head_dim, void* stream); /* in place, head-interleaved pairs, fp32 tables [pos, hd/2]
+                                                               (apply_rotary_pos_emb, :529-553) */
+int lr_f32_rmsnorm(const void* x, int ldx, const int* row_index, const void* w, void* y, int ldy, int rows, int cols,
+                   float eps, void* stream);
+int lr_f32_layernorm(const void* x, int ldx, const void* w, const void* b, void* y, int ldy, int rows, int cols, float eps,
+                     void* stream);
+int lr_f32_clip_im2col(const float* pixels, const int* crop_src, void* A, int n_crops, void* stream);
+int lr_f32_clip_embed_ln(const void* patch, const void* class_emb, const void* pos_emb, const void* ln_w, const void* ln_b,
+                         void* tokens, int n_crops, float eps, void* stream);
+int lr_f32_attention(const void* q, const void* k, const void* v, void* o, int ld_qkv, int ld_o, int n_seq,
+                     int rows_per_seq, const int* seq_base, const int* seq_start, const int* seq_len, int n_heads,
+                     int n_kv_heads, int head_dim, int causal, float scale, void* stream); /* exact softmax; slot layout
+                                                   (seq_base NULL) or packed sequences, like lr_attention_ex_bf16 */
+int lr_f32_hd_gather(const void* clip_tokens, const int* plan, const void* sub_gn, const void* glb_gn, void* rows, int B,
+                     int max_nv, void* stream);
+int lr_f32_skipca_scores(const void* q, int ldq, const void* kv, int ldkv, const int* plan, void* scores, int B, int H,
+                         int max_nv, void* stream);
+int lr_f32_skipca_head(const void* scores, const void* kv, int ldkv, const int* plan, const void* x, int ldx,
+                       const void* ca_ln_w, const void* value_head_w, void* reward, int B, int H, int max_nv, int vhd,
+                       float eps, void* stream);
+int lr_f32_preference(const void* chosen, const void* reject, void* prob, int n, int vhd, int is_gpm, float tau,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

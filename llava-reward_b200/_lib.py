@@ -59,6 +59,19 @@ SIGNATURES = {
     "lr_softmax_rows_bf16": ([p, i32, i32, i32, i32, f32, p], i32),
     "lr_masked_mean_rows_bf16": ([p, i32, p, p, i32, i32, i32, i32, p], i32),
     "lr_synth_normal_f32": ([p, i64, C.c_uint32, f32, f32, i32, p], i32),
+    # fp32 verification path (csrc/f32_verify.cu)
+    "lr_f32_gemm": ([p, i32, p, i32, p, i32, i32, i32, i32, i32, p, p, i32, p], i32),
+    "lr_f32_swiglu": ([p, i32, p, i32, i32, i32, p], i32),
+    "lr_f32_rope": ([p, i32, p, p, p, i32, i32, i32, p], i32),
+    "lr_f32_rmsnorm": ([p, i32, p, p, p, i32, i32, i32, f32, p], i32),
+    "lr_f32_layernorm": ([p, i32, p, p, p, i32, i32, i32, f32, p], i32),
+    "lr_f32_clip_im2col": ([p, p, p, i32, p], i32),
+    "lr_f32_clip_embed_ln": ([p, p, p, p, p, p, i32, f32, p], i32),
+    "lr_f32_attention": ([p, p, p, p, i32, i32, i32, i32, p, p, p, i32, i32, i32, i32, f32, p], i32),
+    "lr_f32_hd_gather": ([p, p, p, p, p, i32, i32, p], i32),
+    "lr_f32_skipca_scores": ([p, i32, p, i32, p, p, i32, i32, i32, p], i32),
+    "lr_f32_skipca_head": ([p, p, i32, p, p, i32, p, p, p, i32, i32, i32, i32, f32, p], i32),
+    "lr_f32_preference": ([p, p, p, i32, i32, i32, f32, p], i32),
 }
 
 

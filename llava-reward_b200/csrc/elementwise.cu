@@ -120,10 +120,13 @@ rope_su_kernel(bf16* __restrict__ qkv, int ld, const int* __restrict__ position_
 
 // ---------------------------------------------------------------- HD feature transform gather
 // grid (max_nv, B), 256 threads: output row r of sample b = 4 x 1024 bf16 (2x2 merged tokens) or a separator.
+// D = width of a CLIP token row in 2-byte units: 1024 (bf16 rows) or 2048 (the same index code moving fp32 rows
+// byte-wise for the fp32 verification path, lr_f32_hd_gather).
+template <int D>
 __global__ void __launch_bounds__(256)
 hd_gather_kernel(const bf16* __restrict__ clip, const int* __restrict__ plan, const bf16* __restrict__ sub_gn,
                  const bf16* __restrict__ glb_gn, bf16* __restrict__ rows) {
-  constexpr int D = 1024, T = 577;
+  constexpr int T = 577;
   const int b = blockIdx.y, r = blockIdx.x;
   const int* pl = plan + b * LR_PLAN_STRIDE;
   const int hc = pl[LR_PLAN_HCROP], wc = pl[LR_PLAN_WCROP], crop_base = pl[LR_PLAN_CROP_BASE];
@@ -269,7 +272,17 @@ extern "C" int lr_hd_gather_bf16(const void* clip_tokens, const int* plan, const
                                  void* rows, int B, int max_nv, void* stream) {
   LR_CHECK_ARG(clip_tokens && plan && sub_gn && glb_gn && rows && B > 0 && max_nv > 0);
   if (!aligned16(clip_tokens) || !aligned16(sub_gn) || !aligned16(glb_gn) || !aligned16(rows)) return LR_ERR_ALIGN;
-  hd_gather_kernel<<<dim3(max_nv, B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  hd_gather_kernel<1024><<<dim3(max_nv, B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(clip_tokens), plan, reinterpret_cast<const bf16*>(sub_gn),
+      reinterpret_cast<const bf16*>(glb_gn), reinterpret_cast<bf16*>(rows));
+  return lr_launch_status();
+}
+
+extern "C" int lr_f32_hd_gather(const void* clip_tokens, const int* plan, const void* sub_gn, const void* glb_gn,
+                                void* rows, int B, int max_nv, void* stream) {
+  LR_CHECK_ARG(clip_tokens && plan && sub_gn && glb_gn && rows && B > 0 && max_nv > 0);
+  if (!aligned16(clip_tokens) || !aligned16(sub_gn) || !aligned16(glb_gn) || !aligned16(rows)) return LR_ERR_ALIGN;
+  hd_gather_kernel<2048><<<dim3(max_nv, B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(clip_tokens), plan, reinterpret_cast<const bf16*>(sub_gn),
       reinterpret_cast<const bf16*>(glb_gn), reinterpret_cast<bf16*>(rows));
   return lr_launch_status();

@@ -21,10 +21,17 @@ from .weights import PackedWeights
 
 class RewardEngine:
     def __init__(self, cfg: RewardConfig, weights: PackedWeights, device="cuda", gemm_impl: int = L.GEMM_TCGEN05,
-                 attn_impl: int = L.ATTN_TCGEN05):
+                 attn_impl: int = L.ATTN_TCGEN05, precision: str = "bf16"):
         L.load()
         self.cfg, self.w, self.device, self.gemm_impl = cfg, weights, torch.device(device), gemm_impl
         self.attn_impl = attn_impl
+        # "fp32" = the verification path (csrc/f32_verify.cu): the same dataflow, layouts, plans and index kernels with
+        # every floating-point kernel in plain fp32 and no bf16 rounding point; the weights must have been packed with
+        # pack_weights(dtype=torch.float32). Debug configuration for the 1e-4 parity gate, never used for scoring.
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision {precision!r}: expected 'bf16' or 'fp32'")
+        self.precision = precision
+        self.dtype = torch.float32 if precision == "fp32" else torch.bfloat16
         self._bufs: Dict[Tuple[str, Tuple[int, ...], torch.dtype], torch.Tensor] = {}
         self._rope: Dict[Tuple[int, bool], Tuple[torch.Tensor, torch.Tensor]] = {}
         self._pinned: Dict[str, torch.Tensor] = {}
@@ -42,7 +49,8 @@ class RewardEngine:
         self.pack_rows = True
 
     # ------------------------------------------------------------------ helpers
-    def buf(self, name: str, shape, dtype=torch.bfloat16) -> torch.Tensor:
+    def buf(self, name: str, shape, dtype=None) -> torch.Tensor:
+        dtype = self.dtype if dtype is None else dtype
         key = (name, tuple(shape), dtype)
         t = self._bufs.get(key)
         if t is None:
@@ -77,8 +85,8 @@ class RewardEngine:
             inv_freq = 1.0 / (ext * cfg.rope_theta ** expo)
             ang = torch.arange(n_pos, dtype=torch.int64, device=self.device).float()[:, None] * inv_freq[None, :]
             s = cfg.rope_scaling_factor
-            self._rope = {key: ((ang.cos() * s).to(torch.bfloat16).contiguous(),
-                                (ang.sin() * s).to(torch.bfloat16).contiguous())}
+            self._rope = {key: ((ang.cos() * s).to(self.dtype).contiguous(),
+                                (ang.sin() * s).to(self.dtype).contiguous())}
         return self._rope[key]
 
     def _gemm(self, A, W, C, M, N, K, epi=L.EPI_NONE, bias=None, R=None):
@@ -231,7 +239,7 @@ class RewardEngine:
 
         cfg, w = self.cfg, self.w
         H, n = cfg.hidden_size, cfg.num_layers
-        last = torch.empty(B * S, H, dtype=torch.bfloat16, device=self.device)
+        last = torch.empty(B * S, H, dtype=self.dtype, device=self.device)
         src = taps[f"hidden_{n - 1}"] if n > 0 else taps["inputs_embeds"]
         ops.rmsnorm(src, w.head["norm"], last, B * S, H, cfg.rms_eps)
         plan_h, max_nv = self._last_plan
@@ -240,7 +248,7 @@ class RewardEngine:
             nv = int(plan_h[b, L.PLAN_NV])
             idx_h[b, :nv] = int(plan_h[b, L.PLAN_ROW_BASE]) + np.arange(nv, dtype=np.int32)
         idx = torch.from_numpy(idx_h.reshape(-1)).to(self.device)
-        vis = torch.empty(B * max_nv, H, dtype=torch.bfloat16, device=self.device)
+        vis = torch.empty(B * max_nv, H, dtype=self.dtype, device=self.device)
         ops.gather_rows(taps["img_proj"], idx, vis, B * max_nv, H)
         hs = [taps["inputs_embeds"]] + [taps[f"hidden_{i}"] for i in range(n - 1)] + [last]
         hs = tuple(t.view(B, S, H) for t in hs) + (vis.view(B, max_nv, H),)
@@ -372,7 +380,7 @@ class RewardEngine:
             self._tap("skipca_all", xa)
         pooled = self.buf("pooled", (B, H))
         ops.masked_mean_rows(xa, mask, pooled, B, S, H)
-        reward = torch.empty(B, cfg.vhd, dtype=torch.bfloat16, device=self.device)
+        reward = torch.empty(B, cfg.vhd, dtype=self.dtype, device=self.device)
         ops.skipca_head(None, None, None, pooled, None, w.head["vh"], reward, B, H, 0, cfg.vhd, cfg.rms_eps)
         return reward
 
@@ -385,7 +393,9 @@ class RewardEngine:
         `mean_hidden_state` and `vision_layer_id` attributes (rw_model_general_preference.py:327-333, 349-353); the
         defaults are the eval-mode scoring path."""
         cfg, w, dev = self.cfg, self.w, self.device
-        bf = torch.bfloat16
+        bf = self.dtype
+        if self.precision == "fp32" and mean_pool:
+            raise NotImplementedError("mean_hidden_state in the fp32 verification path")
         n_run, final_norm = self._resolve_layer_id(layer_id)
         vis_from_layer = None
         if cfg.add_cross_attention and vision_layer_id not in (-1, cfg.num_layers + 1):
@@ -530,7 +540,7 @@ class RewardEngine:
         cfg = self.cfg
         n = chosen.shape[0]
         prob = torch.empty(n, dtype=torch.float32, device=self.device)
-        ops.preference(chosen.to(torch.bfloat16).contiguous(), reject.to(torch.bfloat16).contiguous(), prob, n,
+        ops.preference(chosen.to(self.dtype).contiguous(), reject.to(self.dtype).contiguous(), prob, n,
                        chosen.shape[1], cfg.is_general_preference, cfg.general_preference_tau)
         return prob
 

@@ -33,6 +33,8 @@ class B200RewardModel:
         self.is_general_preference = cfg.is_general_preference
         self.device = torch.device("cpu")
         self.dtype = torch.bfloat16
+        # "fp32" selects the verification path (engine.py / csrc/f32_verify.cu); set before .to('cuda')
+        self.precision = "bf16"
 
     # --- nn.Module-like plumbing used by the reference's callers (eval/simple_inference.py:17-18)
     def to(self, device=None, *args, **kwargs):
@@ -49,7 +51,10 @@ class B200RewardModel:
         return self
 
     def _build_engine(self, device):
-        return RewardEngine(self.config, pack_weights(self.config, self._provider, device=device), device=device)
+        dt = torch.float32 if self.precision == "fp32" else torch.bfloat16
+        self.dtype = dt
+        return RewardEngine(self.config, pack_weights(self.config, self._provider, device=device, dtype=dt), device=device,
+                            precision=self.precision)
 
     def cuda(self, device=None):
         return self.to("cuda" if device is None else device)
@@ -123,6 +128,8 @@ class B200LlavaNextRewardModel(B200RewardModel):
         self.layer_id = cfg.num_layers
 
     def _build_engine(self, device):
+        if self.precision != "bf16":
+            raise NotImplementedError("the fp32 verification path covers the phi3v backbone")
         return LlavaNextRewardEngine(self.config, pack_weights_llava(self.config, self._provider, device=device),
                                      device=device)
 
@@ -165,6 +172,8 @@ class B200QwenRewardModel(B200RewardModel):
         self.layer_id = cfg.num_layers
 
     def _build_engine(self, device):
+        if self.precision != "bf16":
+            raise NotImplementedError("the fp32 verification path covers the phi3v backbone")
         return QwenVLRewardEngine(self.config, pack_weights_qwen(self.config, self._provider, device=device),
                                   device=device)
 

@@ -91,6 +91,7 @@ def load_reward_adaptor(args, model_type, reward_config_path, load_tokenizer=Fal
         cfg, provider = checkpoint_provider(cfg, pretrain, getattr(args, "pm_path", None),
                                             ft_projector=bool(getattr(args, "ft_projector", False)))
     model = B200RewardModel(cfg, provider)
+    model.precision = str(getattr(args, "precision", "bf16"))   # "fp32" = verification path (tests only)
     if load_tokenizer:
         from .processing import load_processor
         processor, tokenizer = load_processor(pretrain, cfg, cache_dir=getattr(args, "cache_dir", None),
@@ -125,7 +126,9 @@ def preference_compute(args, chosen_rewards, reject_rewards):
     n, vhd = chosen_rewards.shape
     prob = torch.empty(n, dtype=torch.float32, device=chosen_rewards.device)
     with torch.cuda.device(chosen_rewards.device):
-        ops.preference(chosen_rewards.to(torch.bfloat16).contiguous(), reject_rewards.to(torch.bfloat16).contiguous(),
+        # rewards keep the dtype custom_forward produced them in: bf16 (product) or fp32 (verification path)
+        dt = torch.float32 if chosen_rewards.dtype == torch.float32 else torch.bfloat16
+        ops.preference(chosen_rewards.to(dt).contiguous(), reject_rewards.to(dt).contiguous(),
                        prob, n, vhd, bool(args.is_general_preference) and int(args.value_head_dim) == 2,
                        float(args.general_preference_tau))
     return prob.cpu().numpy()

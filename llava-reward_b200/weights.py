@@ -43,9 +43,9 @@ class PackedWeights:
         return tot + self.embed.numel() * self.embed.element_size()
 
 
-def _pack_clip(pw: PackedWeights, cfg, g, c: str, device) -> None:
-    """CLIP ViT-L/14-336 tower (shared by the Phi-3-V and LLaVA-v1.6 branches; `c` = state_dict prefix)."""
-    bf = torch.bfloat16
+def _pack_clip(pw: PackedWeights, cfg, g, c: str, device, bf=torch.bfloat16) -> None:
+    """CLIP ViT-L/14-336 tower (shared by the Phi-3-V and LLaVA-v1.6 branches; `c` = state_dict prefix).
+    `bf` = storage dtype (bf16; fp32 for the verification path)."""
     D = cfg.clip_hidden
     pe = g(c + "embeddings.patch_embedding.weight").reshape(D, -1)  # [1024, 588], (ch, ky, kx) order
     patch_w = torch.zeros(D, 640, dtype=bf, device=device)
@@ -95,14 +95,16 @@ def _qk_interleave_perm(n_heads: int, head_dim: int, device) -> torch.Tensor:
     return (torch.arange(n_heads)[:, None] * head_dim + inter[None, :]).reshape(-1).to(device)
 
 
-def pack_weights(cfg: RewardConfig, get: Callable[[str], torch.Tensor], device="cuda") -> PackedWeights:
-    bf = torch.bfloat16
+def pack_weights(cfg: RewardConfig, get: Callable[[str], torch.Tensor], device="cuda",
+                 dtype=torch.bfloat16) -> PackedWeights:
+    """`dtype` = torch.float32 packs the SAME layouts in fp32 for the verification path (RewardEngine precision="fp32")."""
+    bf = dtype
 
     def g(name):
         return get(name).to(device=device, dtype=bf).contiguous()
 
     pw = PackedWeights()
-    _pack_clip(pw, cfg, g, CLIP_PREFIX, device)
+    _pack_clip(pw, cfg, g, CLIP_PREFIX, device, bf)
     pw.proj = {
         "p0_w": g(VE + "img_projection.0.weight"), "p0_b": g(VE + "img_projection.0.bias"),
         "p2_w": g(VE + "img_projection.2.weight"), "p2_b": g(VE + "img_projection.2.bias"),
