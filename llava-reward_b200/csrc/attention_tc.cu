@@ -52,7 +52,10 @@ __device__ long long* g_attn_trace = nullptr;
 
 constexpr int kAtomBytes = 128 * 64;      // [128 rows x 32 bf16], 64B swizzle
 constexpr int kPBytes = 128 * 128 * 2;    // P tile: two [128 x 64 bf16] 128B-swizzled atoms
-constexpr long long kStaggerCycles = 1100;
+#ifndef LR_ATTN_NT2_STAGGER
+#define LR_ATTN_NT2_STAGGER 1100
+#endif
+constexpr long long kStaggerCycles = LR_ATTN_NT2_STAGGER;
 constexpr float kRescaleThreshold = 8.f;  // log2 units: P stays <= 2^8 between rescales
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
@@ -65,6 +68,19 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes,
   return d;
 }
 constexpr uint32_t kLayoutSW128 = 2, kLayoutSW64 = 4;
+// the same descriptor as two 32-bit words: lo = start address | leading byte offset, hi = stride byte offset | version
+// | layout (a compile-time constant per operand kind); a byte offset inside the tile is one add of (offset >> 4) to lo
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t addr, uint32_t lbo_bytes) {
+  return ((addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes, uint32_t layout) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+}
+__device__ __forceinline__ uint64_t desc_join(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
 
 // Softmax exponentials: LR_ATTN_POLY_NUM of every 4 elements of a row are computed on the FMA pipe instead of the
 // MUFU (16 ex2/clk/SM is the scarcest pipe of this kernel): Cody-Waite split 2^x = 2^floor(x) * 2^frac with a
@@ -115,6 +131,65 @@ constexpr uint32_t kLayoutSW128 = 2, kLayoutSW64 = 4;
 #ifndef LR_ATTN_MAX3
 #define LR_ATTN_MAX3 0
 #endif
+// Hand-off experiments of the second half of round 2 (tools/attn_ab.py, interleaved A/B timing):
+// LR_ATTN_P_HALF 1: the softmax warps arrive on a second barrier (p_half) once the first 64 keys of the P row are
+// stored, and the MMA thread issues the first four P.V MMAs then - half of the P.V issue latency moves under the
+// exponentials of the second half instead of sitting between p_full and pv_done.
+// LR_ATTN_EXP_FIRST 1: the exponentials of the first 32 keys are computed BEFORE the wait on pv_done(j-1) (they only
+// need registers), so that wait overlaps useful work.
+// LR_ATTN_DESC32 1: the MMA thread builds every shared-memory descriptor as {base_lo + constant, constant hi} with one
+// 32-bit add instead of masking / shifting the address per tcgen05.mma (4 live registers instead of 28 descriptors).
+// LR_ATTN_KV2 1 (head_dim 64 with P in TMEM: 80 KB per CTA): two-stage K / V ring with two CTAs per SM.
+#ifndef LR_ATTN_P_HALF
+#define LR_ATTN_P_HALF 1
+#endif
+#ifndef LR_ATTN_EXP_FIRST
+#define LR_ATTN_EXP_FIRST 1
+#endif
+#ifndef LR_ATTN_DESC32
+#define LR_ATTN_DESC32 1
+#endif
+#ifndef LR_ATTN_KV2
+#define LR_ATTN_KV2 0
+#endif
+// LR_ATTN_STAGGER = D > 0 (two CTAs per SM): the SECOND CTA that lands on an SM starts its pipeline D cycles late.
+// Two co-resident CTAs that start together run their MUFU-bound exponential phases at the same time, each at half
+// rate, and - the phase offset of two equal loops that share one pipe is neutrally stable - stay that way for the
+// whole kernel; an initial offset of about one exponential phase lets each CTA's exponentials run under the other's
+// S load / max / hand-offs. Mode 1: "second" = linear CTA index in [#SMs, 2 #SMs) (the hardware fills the SMs
+// breadth-first); mode 2: an atomic per-SM arrival counter tagged with a per-launch epoch.
+// LR_ATTN_MMA_WARP 1: the MMA-issuing warp stays CONVERGED - all 32 lanes walk the event loop (barrier probes are
+// made warp-uniform with a vote) and one elected lane (elect.sync) issues tcgen05.mma / tcgen05.commit. Under
+// `if (lane == 0)` the compiler cannot know that a single lane is active and wraps every UTCHMMA in an ELECT /
+// BRA.U.ANY loop, with the descriptors moved from vector to uniform registers (R2UR) each time.
+// 0 = off, 1 = every configuration, 2 = only with two query tiles per CTA (one CTA per SM), where it measured faster.
+#ifndef LR_ATTN_MMA_WARP
+#define LR_ATTN_MMA_WARP 2
+#endif
+// kMmaWarp is a constexpr bool of the kernel (the macro value resolved against NT)
+#define LR_MMA_VOTE(x) (kMmaWarp ? __all_sync(0xffffffffu, (x)) : (x))
+#define LR_MMA_LEAD_BEGIN if (!kMmaWarp || elect_one()) {
+#define LR_MMA_LEAD_END            \
+  }                                \
+  if constexpr (kMmaWarp) __syncwarp();
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+#ifndef LR_ATTN_STAGGER
+#define LR_ATTN_STAGGER 0
+#endif
+#ifndef LR_ATTN_STAGGER_MODE
+#define LR_ATTN_STAGGER_MODE 1
+#endif
+__device__ unsigned long long g_attn_sm_arrivals[1024];   // [%smid] = epoch << 32 | CTAs of that launch seen so far
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -195,7 +270,7 @@ struct AttnTcCfg {
   // exponentials, like flash-attention 2) - and 227 KB of smem allow only a single K/V stage.
   static constexpr bool kPTmem = LR_ATTN_P_TMEM && HD == 64 && NT == 1;
   static constexpr bool kOnes = !(HD == 128 && NT == 2) && !kPTmem;
-  static constexpr int kStages = !kOnePerSm ? 1 : (kOnes ? 2 : 1);
+  static constexpr int kStages = !kOnePerSm ? ((kPTmem && LR_ATTN_KV2) ? 2 : 1) : (kOnes ? 2 : 1);
   static constexpr int kTmemCols = kOnePerSm ? 512 : 256;
   static constexpr int kAtoms = HD / 32;
   static constexpr int kTileBytes = kAtoms * kAtomBytes;         // one Q / K tile, and the TMA-loaded part of a V tile
@@ -215,7 +290,7 @@ __global__ void __launch_bounds__(128 + 128 * NT * SPLIT, AttnTcCfg<HD, NT>::kOn
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o, int ld_o, int rows_per_seq,
                const int* __restrict__ seq_base, const int* __restrict__ seq_start, const int* __restrict__ seq_len,
                int q_col0, int k_col0, int v_col0, int kv_group, float scale_log2,
-               const int* __restrict__ row_lo, const int* __restrict__ row_hi, int tile_mode) {
+               const int* __restrict__ row_lo, const int* __restrict__ row_hi, int tile_mode, unsigned epoch) {
   using Cfg = AttnTcCfg<HD, NT>;
   constexpr int NS = Cfg::kStages;
   constexpr int NA = Cfg::kAtoms;
@@ -231,6 +306,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
   uint8_t* sV = sK + NS * TILE;          // [NS][VTILE]
   uint8_t* sP = sV + NS * VTILE;         // [NT][kPBytes]
   constexpr bool PTMEM = Cfg::kPTmem;
+  constexpr bool kMmaWarp = LR_ATTN_MMA_WARP == 1 || (LR_ATTN_MMA_WARP == 2 && NT == 2);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (PTMEM ? 0 : NT * kPBytes));
   uint64_t* q_full = bars;               // [1]
   uint64_t* k_full = bars + 1;           // [2]
@@ -243,6 +319,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
   uint64_t* pv_done = bars + 15;         // [2] per tile  MMA -> softmax : O_x += P_x(j) V_j retired
   uint64_t* o_final = bars + 17;         // [2] per tile
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* p_half = bars + 20;          // [2] per tile  softmax -> MMA : the first 64 keys of P_x(j) are stored (LR_ATTN_P_HALF)
   float* mbuf = reinterpret_cast<float*>(bars + 32);  // [2 tiles][2 halves][128] row-max exchange (SPLIT == 2)
   constexpr int kThreads = 128 + 128 * NT * SPLIT;
 
@@ -311,6 +388,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       mbar_init(&s_full[i], 1);
       mbar_init(&s_free[i], 4 * SPLIT);
       mbar_init(&p_full[i], 4 * SPLIT);
+      mbar_init(&p_half[i], 4 * SPLIT);
       mbar_init(&pv_done[i], 1);
       mbar_init(&o_final[i], 1);
     }
@@ -326,6 +404,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     *reinterpret_cast<uint4*>(sV + st * VTILE + NA * kAtomBytes + o16 * 16) =
         make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
   }
+#if LR_ATTN_STAGGER > 0
+  if (!Cfg::kOnePerSm && warp == 3 && lane == 0) {   // warp 3 has no role in the one-tile configuration
+    bool second;
+    if (LR_ATTN_STAGGER_MODE == 1) {
+      unsigned nsm;
+      asm volatile("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+      const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+      second = lin >= nsm && lin < 2 * nsm;
+    } else {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      unsigned long long* slot = &g_attn_sm_arrivals[smid & 1023];
+      unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(slot), seen;
+      do {
+        seen = old;
+        const unsigned long long next = (seen >> 32) == epoch ? seen + 1 : ((unsigned long long)(epoch) << 32) | 1ull;
+        old = atomicCAS(slot, seen, next);
+      } while (old != seen);
+      second = (seen >> 32) == epoch && (seen & 0xffffffffull) == 1ull;
+    }
+    if (second) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < LR_ATTN_STAGGER) {
+      }
+    }
+  }
+#endif
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -359,8 +464,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         while (kj < n || vj < n) {
           if (kj < n && mbar_test_wait(&k_empty[(g + kj) % NS], (((g + kj) / NS) & 1) ^ 1)) {
             if (kj == 0) {
-              // Q of this tile. For a later tile (single-stage ring only) the wait above also says that every S MMA
-              // of the previous tile - the only readers of the Q buffer - has retired.
+              // Q of this tile. For a later tile the Q buffer is free once every S MMA of the previous tile - its only
+              // readers - has retired: with a single-stage ring the wait above says exactly that; with two stages
+              // the commit of the previous tile's LAST S MMA (block g - 1) is awaited explicitly.
+              if (NS > 1 && g > 0) mbar_wait(&k_empty[(g - 1) % NS], ((g - 1) / NS) & 1);
               const uint32_t q_bytes = (nblk[0] > 0 ? TILE : 0) + (nblk[1] > 0 ? TILE : 0);
               mbar_arrive_expect_tx(q_full, q_bytes);
 #pragma unroll
@@ -406,9 +513,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     // registers, O_x += P_x(j) V_j the moment P_x(j) is in smem. A K (V) stage goes back to the producer when both
     // threads have arrived on its `empty` barrier (tcgen05.commit after the last MMA that reads it, or a plain arrive
     // for blocks a tile does not need).
-    if (lane == 0) {
+    if (kMmaWarp || lane == 0) {
       const int x = warp == 1 ? 0 : 1;
       int g = 0, tq = 0;  // K/V blocks / non-empty tiles already processed by this CTA
+#if LR_ATTN_DESC32
+      // descriptor low words of the four operand buffers, made opaque so that they stay in four registers instead of
+      // being re-derived from the shared-memory base (shift + mask + or) in front of every tcgen05.mma
+      uint32_t q_lo0 = umma_desc_lo(smem_u32(sQ + x * TILE), 16), k_lo0 = umma_desc_lo(smem_u32(sK), 16);
+      uint32_t p_lo0 = umma_desc_lo(smem_u32(sP + x * kPBytes), 16), v_lo0 = umma_desc_lo(smem_u32(sV), kAtomBytes);
+      asm volatile("" : "+r"(q_lo0), "+r"(k_lo0), "+r"(p_lo0), "+r"(v_lo0));
+#endif
       for (int ti = 0; ti < n_tiles; ++ti) {
       set_tile(ti);
       if (n == 0) continue;
@@ -420,10 +534,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
 #if LR_ATTN_HOIST_DESC
         const uint64_t qd = umma_desc(qa, 16, 512, kLayoutSW64), kd = umma_desc(ka, 16, 512, kLayoutSW64);
 #endif
+#if LR_ATTN_DESC32
+        const uint32_t q_lo = q_lo0, k_lo = k_lo0 + ks * (TILE >> 4);
+#endif
 #pragma unroll
         for (int kk = 0; kk < ((LR_ATTN_KO & 32) ? 0 : HD / 16); ++kk) {
           const uint32_t off = (kk >> 1) * kAtomBytes + (kk & 1) * 32;
-#if LR_ATTN_HOIST_DESC
+#if LR_ATTN_DESC32
+          constexpr uint32_t hi = umma_desc_hi(512, kLayoutSW64);
+          umma_bf16_ss(tm_S[x], desc_join(q_lo + (off >> 4), hi), desc_join(k_lo + (off >> 4), hi), idesc_s, kk != 0);
+#elif LR_ATTN_HOIST_DESC
           // the start-address field holds (addr >> 4) in 14 bits; shared memory ends below 2^18, so the add cannot carry
           umma_bf16_ss(tm_S[x], qd + (off >> 4), kd + (off >> 4), idesc_s, kk != 0);
 #else
@@ -434,24 +554,44 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         umma_commit(&s_full[x]);
         umma_commit(&k_empty[ks]);
       };
-      auto issue_pv = [&](int vs, bool acc) {  // O_x += P_x V : A = P (K-major, SW128), B = V (MN-major, SW64)
+      // kk0 .. kk1: the k-steps (16 keys each) to issue; the commits follow the last one (kk1 == 8)
+      auto issue_pv = [&](int vs, bool acc, int kk0, int kk1) {  // O_x += P_x V : A = P (K-major, SW128), B = V (MN-major, SW64)
         if constexpr (PTMEM) {   // A = P from TMEM: MMA kk consumes keys [16 kk, 16 kk + 16) = 8 packed columns
           const uint32_t va = smem_u32(sV + vs * VTILE);
+#if LR_ATTN_DESC32
+          const uint32_t v_lo = v_lo0 + vs * (VTILE >> 4);
+#endif
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
+          for (int kk = 0; kk < 8; ++kk) {
+            if (kk < kk0 || kk >= kk1) continue;
+#if LR_ATTN_DESC32
+            umma_bf16_ts(tm_O[x], tm_P + kk * 8, desc_join(v_lo + ((kk * 1024) >> 4), umma_desc_hi(512, kLayoutSW64)),
+                         idesc_o, acc || kk != 0);
+#else
             umma_bf16_ts(tm_O[x], tm_P + kk * 8, umma_desc(va + kk * 1024, kAtomBytes, 512, kLayoutSW64), idesc_o,
                          acc || kk != 0);
-          umma_commit(&pv_done[x]);
-          umma_commit(&v_empty[vs]);
+#endif
+          }
+          if (kk1 == 8) {
+            umma_commit(&pv_done[x]);
+            umma_commit(&v_empty[vs]);
+          }
           return;
         }
         const uint32_t pa = smem_u32(sP + x * kPBytes), va = smem_u32(sV + vs * VTILE);
 #if LR_ATTN_HOIST_DESC
         const uint64_t pd = umma_desc(pa, 16, 1024, kLayoutSW128), vd = umma_desc(va, kAtomBytes, 512, kLayoutSW64);
 #endif
+#if LR_ATTN_DESC32
+        const uint32_t p_lo = p_lo0, v_lo = v_lo0 + vs * (VTILE >> 4);
+#endif
 #pragma unroll
         for (int kk = 0; kk < ((LR_ATTN_KO & 16) ? 0 : 8); ++kk) {
-#if LR_ATTN_HOIST_DESC
+          if (kk < kk0 || kk >= kk1) continue;
+#if LR_ATTN_DESC32
+          umma_bf16_ss(tm_O[x], desc_join(p_lo + (((kk >> 2) * (kPBytes / 2) + (kk & 3) * 32) >> 4), umma_desc_hi(1024, kLayoutSW128)),
+                       desc_join(v_lo + ((kk * 1024) >> 4), umma_desc_hi(512, kLayoutSW64)), idesc_o, acc || kk != 0);
+#elif LR_ATTN_HOIST_DESC
           umma_bf16_ss(tm_O[x], pd + (((kk >> 2) * (kPBytes / 2) + (kk & 3) * 32) >> 4), vd + ((kk * 1024) >> 4), idesc_o,
                        acc || kk != 0);
 #else
@@ -459,8 +599,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
                        umma_desc(va + kk * 1024, kAtomBytes, 512, kLayoutSW64), idesc_o, acc || kk != 0);
 #endif
         }
-        umma_commit(&pv_done[x]);
-        umma_commit(&v_empty[vs]);
+        if (kk1 == 8) {
+          umma_commit(&pv_done[x]);
+          umma_commit(&v_empty[vs]);
+        }
       };
       if (nx > 0) {
         mbar_wait(q_full, tq & 1);
@@ -475,22 +617,48 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
           }
         }
         tc_fence_after();
+        LR_MMA_LEAD_BEGIN
         issue_s(g % NS);
+        LR_MMA_LEAD_END
         int s_next = 1, pv_next = 0;
+        [[maybe_unused]] bool half_issued = false;
         while (pv_next < nx) {
-          if (s_next < nx && mbar_test_wait(&s_free[x], (g + s_next - 1) & 1) &&
-              mbar_test_wait(&k_full[(g + s_next) % NS], ((g + s_next) / NS) & 1)) {
+          if (s_next < nx && LR_MMA_VOTE(mbar_test_wait(&s_free[x], (g + s_next - 1) & 1) &&
+                                         mbar_test_wait(&k_full[(g + s_next) % NS], ((g + s_next) / NS) & 1))) {
             tc_fence_after();
             ATTN_TRACE(0, x * 4 + 0, s_next - 1);
+            LR_MMA_LEAD_BEGIN
             issue_s((g + s_next) % NS);
+            LR_MMA_LEAD_END
             ++s_next;
           }
-          if (mbar_test_wait(&p_full[x], (g + pv_next) & 1) &&
-              mbar_test_wait(&v_full[(g + pv_next) % NS], ((g + pv_next) / NS) & 1)) {
+          bool pv_ready;
+          if constexpr (LR_ATTN_P_HALF && SPLIT == 1) {
+            if (!half_issued && LR_MMA_VOTE(mbar_test_wait(&p_half[x], (g + pv_next) & 1) &&
+                                            mbar_test_wait(&v_full[(g + pv_next) % NS], ((g + pv_next) / NS) & 1))) {
+              tc_fence_after();
+              LR_MMA_LEAD_BEGIN
+              issue_pv((g + pv_next) % NS, pv_next > 0, 0, 4);   // keys 0..63 of P_x(j) are stored (and O_x rescaled)
+              LR_MMA_LEAD_END
+              half_issued = true;
+            }
+            pv_ready = half_issued && LR_MMA_VOTE(mbar_test_wait(&p_full[x], (g + pv_next) & 1));
+          } else {
+            pv_ready = LR_MMA_VOTE(mbar_test_wait(&p_full[x], (g + pv_next) & 1) &&
+                                   mbar_test_wait(&v_full[(g + pv_next) % NS], ((g + pv_next) / NS) & 1));
+          }
+          if (pv_ready) {
             tc_fence_after();
             ATTN_TRACE(0, x * 4 + 1, pv_next);
-            issue_pv((g + pv_next) % NS, pv_next > 0);
+            LR_MMA_LEAD_BEGIN
+            if constexpr (LR_ATTN_P_HALF && SPLIT == 1) {
+              issue_pv((g + pv_next) % NS, true, 4, 8);
+            } else {
+              issue_pv((g + pv_next) % NS, pv_next > 0, 0, 8);
+            }
             if (pv_next + 1 == nx) umma_commit(&o_final[x]);
+            LR_MMA_LEAD_END
+            half_issued = false;
             ATTN_TRACE(0, x * 4 + 2, pv_next);
             ++pv_next;
           }
@@ -502,8 +670,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
           mbar_wait(&k_empty[st], ((j - NS) / NS) & 1);
           mbar_wait(&v_empty[st], ((j - NS) / NS) & 1);
         }
+        LR_MMA_LEAD_BEGIN
         mbar_arrive(&k_empty[st]);
         mbar_arrive(&v_empty[st]);
+        LR_MMA_LEAD_END
       }
       g += n;
       ++tq;
@@ -638,6 +808,45 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         }
       }
       if (tr) ATTN_TRACE(1 + x, 3, j);
+      // P = exp2(S*scale - m_ref) (masked entries: exp2(-inf) = 0) -> bf16, 32 columns (one chunk) at a time
+      auto exp_chunk = [&](int c, uint32_t (&pk)[16]) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = softmax_exp2(fmaf(__uint_as_float(sv[c][2 * i]), scale_log2, -msafe), 2 * i);
+          const float p1 = softmax_exp2(fmaf(__uint_as_float(sv[c][2 * i + 1]), scale_log2, -msafe), 2 * i + 1);
+          if constexpr (!ONES) {
+            l_reg[(2 * i) & 3] += p0;
+            l_reg[(2 * i + 1) & 3] += p1;
+          }
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+      };
+      // -> smem (or this thread's TMEM lane), so the stores issue under the MUFU-bound exponentials of the next chunk.
+      // 128 columns = 2 atoms x 8 chunks of 16 B; chunk position XOR (row & 7) = the 128B swizzle.
+      auto store_chunk = [&](int c, const uint32_t (&pk)[16]) {
+        const int cg = h * NCH + c;  // chunk index inside the 128-column row
+        if constexpr (PTMEM) {   // 32 keys = 16 packed columns of this thread's own TMEM lane
+          tmem_st_32x16(tm_P + lane_addr + cg * 16, pk);
+          return;
+        }
+        uint8_t* base = prow + (cg >> 1) * (kPBytes / 2);
+#if LR_ATTN_KO & 2
+        {  // keep every exponential and pack alive (XOR of all packed words), store (practically) never
+          uint32_t live = 0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) live ^= pk[i];
+          if (live == 0x12345678u) *reinterpret_cast<uint4*>(base) = make_uint4(pk[0], pk[5], pk[9], live);
+        }
+#else
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int chunk = ((cg & 1) * 4 + t) ^ (r & 7);
+          *reinterpret_cast<uint4*>(base + (chunk << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+        }
+#endif
+      };
+      [[maybe_unused]] uint32_t pk_first[16];
+      if constexpr (LR_ATTN_EXP_FIRST != 0) exp_chunk(0, pk_first);   // registers only: runs under the wait below
       // P_x buffer and O_x may be touched only after O_x += P_x(j-1) V_(j-1) has retired
       if (j > 0) {
         mbar_wait(&pv_done[x], (g + j - 1) & 1);
@@ -656,42 +865,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         }
       }
       if (tr) ATTN_TRACE(1 + x, 4, j);
-      // P = exp2(S*scale - m_ref) (masked entries: exp2(-inf) = 0) -> bf16 -> smem, 32 columns at a time so the
-      // stores issue under the MUFU-bound exponentials. 128 columns = 2 atoms x 8 chunks of 16 B; chunk position
-      // XOR (row & 7) = the 128B swizzle.
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = softmax_exp2(fmaf(__uint_as_float(sv[c][2 * i]), scale_log2, -msafe), 2 * i);
-          const float p1 = softmax_exp2(fmaf(__uint_as_float(sv[c][2 * i + 1]), scale_log2, -msafe), 2 * i + 1);
-          if constexpr (!ONES) {
-            l_reg[(2 * i) & 3] += p0;
-            l_reg[(2 * i + 1) & 3] += p1;
-          }
-          pk[i] = pack_bf16x2(p0, p1);
+        if (LR_ATTN_EXP_FIRST != 0 && c == 0) {
+          store_chunk(0, pk_first);
+        } else {
+          uint32_t pk[16];
+          exp_chunk(c, pk);
+          store_chunk(c, pk);
         }
-        const int cg = h * NCH + c;  // chunk index inside the 128-column row
-        if constexpr (PTMEM) {   // 32 keys = 16 packed columns of this thread's own TMEM lane
-          tmem_st_32x16(tm_P + lane_addr + cg * 16, pk);
-          continue;
+        if (LR_ATTN_P_HALF && SPLIT == 1 && c == NCH / 2 - 1) {   // keys 0..63 are stored: the MMA thread may issue the first half of P.V
+          if constexpr (PTMEM) tmem_st_wait();
+          else fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_half[x]);
         }
-        uint8_t* base = prow + (cg >> 1) * (kPBytes / 2);
-#if LR_ATTN_KO & 2
-        {  // keep every exponential and pack alive (XOR of all packed words), store (practically) never
-          uint32_t live = 0;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) live ^= pk[i];
-          if (live == 0x12345678u) *reinterpret_cast<uint4*>(base) = make_uint4(pk[0], pk[5], pk[9], live);
-        }
-#else
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int chunk = ((cg & 1) * 4 + t) ^ (r & 7);
-          *reinterpret_cast<uint4*>(base + (chunk << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
-        }
-#endif
       }
 #if !(LR_ATTN_KO & 2) && !(LR_ATTN_KO & 64)
       if constexpr (PTMEM) tmem_st_wait();   // the tcgen05.st of the P row have landed
@@ -792,6 +981,8 @@ static EncodeTiledFn attn_encode_fn() {
   return fn;
 }
 
+static unsigned g_launch_epoch = 0;   // tags the per-SM arrival counters of one launch (LR_ATTN_STAGGER_MODE 2)
+
 template <int HD, bool CAUSAL, int SPLIT, int NT>
 static int launch_attn_tc(const void* base, int total_rows, int ld_qkv, int q_col0, int k_col0, int v_col0, void* o,
                           int ld_o, int n_seq, int rows_per_seq, const int* seq_base, const int* seq_start,
@@ -815,7 +1006,7 @@ static int launch_attn_tc(const void* base, int total_rows, int ld_qkv, int q_co
   // decoder pairs 1.264 -> 1.252 ms; a 4900-token non-causal sequence (39 blocks per tile, fixed cost already
   // amortised, fewer and longer CTAs -> wave quantisation) 1.45 -> 1.60 ms, so long non-causal sequences keep one
   // tile per CTA.
-  if (multi_tile && NT == 1 && Cfg::kStages == 1 && row_lo == nullptr && nt > 1) {
+  if (multi_tile && NT == 1 && !Cfg::kOnePerSm && row_lo == nullptr && nt > 1) {
     if (CAUSAL) {
       tile_mode = 1;                 // pairs {nt-1-x, x}
       gx = (nt + 1) / 2;
@@ -828,7 +1019,7 @@ static int launch_attn_tc(const void* base, int total_rows, int ld_qkv, int q_co
   constexpr int kSmem = Cfg::kSmemBytes + ((SPLIT == 2 && NT == 1) ? 1024 : 0);   // row-max exchange of the experiment
   kern<<<grid, 128 + 128 * NT * SPLIT, kSmem, stream>>>(tm, reinterpret_cast<bf16*>(o), ld_o, rows_per_seq, seq_base,
                                                       seq_start, seq_len, q_col0, k_col0, v_col0, kv_group,
-                                                      scale * 1.4426950408889634f, row_lo, row_hi, tile_mode);
+                                                      scale * 1.4426950408889634f, row_lo, row_hi, tile_mode, ++g_launch_epoch);
   return lr_launch_status();
 }
 

@@ -10,13 +10,15 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "llava-reward_b200", "csrc")
-OUT = os.path.join(ROOT, "llava-reward_b200", "lib", "libllavareward_trace.so")
+EXTRA = [a for a in os.environ.get("LR_TRACE_DEFS", "").split() if a]   # e.g. "-DLR_ATTN_P_HALF=1 -DLR_ATTN_DESC32=1"
+TAG = "".join(c for c in "".join(EXTRA) if c.isalnum())
+OUT = os.path.join(ROOT, "llava-reward_b200", "lib", f"libllavareward_trace{TAG}.so")
 
 
 def build():
     srcs = [os.path.join(CSRC, f) for f in ("attention_tc.cu", "attention.cu")]
     cmd = ["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler",
-           "-fPIC", "--use_fast_math", "-DLR_ATTN_TRACE", "-shared", "-o", OUT, *srcs, "-lcudart"]
+           "-fPIC", "--use_fast_math", "--prec-div=true", "--prec-sqrt=true", "--fmad=true", "-DLR_ATTN_TRACE", *EXTRA, "-shared", "-o", OUT, *srcs, "-lcudart"]
     subprocess.run(cmd, check=True)
 
 
@@ -33,7 +35,10 @@ def main():
     lib.lr_attention_bf16.argtypes = [p, p, p, p, i32, i32, i32, i32, p, p, i32, i32, i32, f32, i32, p]
     lib.lr_attn_trace_set.argtypes = [p]
     bf = torch.bfloat16
-    for name, (nseq, T, heads, hd, causal) in {"dec": (32, 2048, 32, 96, True), "clip": (416, 577, 16, 64, False)}.items():
+    cases = {"dec": (32, 2048, 32, 96, True), "clip": (416, 577, 16, 64, False)}
+    if "--solo" in sys.argv:   # one sequence, one head: every CTA has an SM to itself (no co-resident CTA)
+        cases = {"dec solo": (1, 2048, 1, 96, True), "clip solo": (1, 577, 1, 64, False)}
+    for name, (nseq, T, heads, hd, causal) in cases.items():
         D = heads * hd
         qkv = torch.randn(nseq * T, 3 * D, device="cuda", dtype=bf)
         o = torch.empty(nseq * T, D, device="cuda", dtype=bf)
