@@ -22,6 +22,8 @@
 // multiply V (and is rescaled together with O).
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tmap_cache.cuh"
@@ -183,6 +185,70 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// LR_ATTN_CHUNK_MASK 1: in a block that needs masking (causal diagonal, last partial block) the valid keys of a row are
+// a prefix [0, nvalid) of the block's 128 columns. The warp classifies each 32-column chunk from the min / max of nvalid
+// over its 32 rows (redux.sync): valid for every lane -> no masking instructions; masked for every lane -> no max, no
+// exponentials (P = 0 is stored directly); only the one or two chunks in between pay a per-element compare + select
+// (one ISETP + SEL against nvalid instead of two compares). Bit-identical results: exp2(-inf) is exactly 0 either way.
+#ifndef LR_ATTN_CHUNK_MASK
+#define LR_ATTN_CHUNK_MASK 1   // product: decoder -7 %, CLIP -3 % (profiles/r02_attention_ab_interleaved_6_chunk_mask.txt)
+#endif
+// LR_ATTN_SPIN_WAIT 1: the softmax warps poll s_full / pv_done with mbarrier.test_wait instead of try_wait (which may
+// suspend the warp until the phase completes or a time slice ends).
+#ifndef LR_ATTN_SPIN_WAIT
+#define LR_ATTN_SPIN_WAIT 0
+#endif
+// LR_ATTN_L2_PREFETCH 1: with the single-stage K / V ring the load of block j+1 starts only when the MMAs on block j
+// have retired, so its latency sits between two S MMAs of a tile; the producer therefore asks the L2 for block j+1
+// (cp.async.bulk.prefetch.tensor) while it issues the load of block j.
+#ifndef LR_ATTN_L2_PREFETCH
+#define LR_ATTN_L2_PREFETCH 0
+#endif
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+// LR_ATTN_POLL_SLEEP = N > 0: the two event loops (TMA producer, MMA issuer) sleep N ns (nanosleep) after an iteration
+// in which nothing was ready. Their mbarrier.test_wait polling otherwise issues continuously on schedulers 0 and 1,
+// which the softmax warps of BOTH co-resident CTAs share.
+#ifndef LR_ATTN_POLL_SLEEP
+#define LR_ATTN_POLL_SLEEP 0
+#endif
+__device__ __forceinline__ void poll_idle() {
+#if LR_ATTN_POLL_SLEEP > 0
+  asm volatile("nanosleep.u32 %0;" ::"n"(LR_ATTN_POLL_SLEEP));
+#endif
+}
+// LR_ATTN_EPI_STAGE 1: the O tile leaves through shared memory. A softmax thread owns one output ROW, so its direct
+// 16-byte stores hit 32 different 128-byte lines per warp instruction - the timeline shows 1300 (head_dim 64) to 3800
+// (head_dim 96) cycles per tile in the store loop, LSU-transaction-bound. Staged: every warp writes its 32 rows into
+// a private smem region (its own rows of the retired P buffer, or a dedicated buffer when P lives in TMEM), then
+// reads them back so that consecutive lanes carry consecutive 16-byte pieces of a row (3-6 lines per instruction).
+#ifndef LR_ATTN_EPI_STAGE
+#define LR_ATTN_EPI_STAGE 0
+#endif
+// LR_ATTN_FFMA2 1: the scale-and-subtract in front of the exponentials as packed fma.rn.f32x2 (two elements per
+// instruction: 64 instead of 128 FMA-pipe issues per row and block).
+#ifndef LR_ATTN_FFMA2
+#define LR_ATTN_FFMA2 1   // product: hd64 -2 %, hd96 -2.6 %, hd128 +-0 (profiles/r02_attention_ab_interleaved_7_ffma2.txt)
+#endif
+__device__ __forceinline__ void ffma2(float& d0, float& d1, uint32_t a0, uint32_t a1, float b, float c) {
+  uint64_t a, bb, cc, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c));
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(bb), "l"(cc));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+__device__ __forceinline__ void softmax_wait(uint64_t* bar, uint32_t parity) {
+#if LR_ATTN_SPIN_WAIT
+  while (!mbar_test_wait(bar, parity)) {
+  }
+#else
+  mbar_wait(bar, parity);
+#endif
+}
 #ifndef LR_ATTN_STAGGER
 #define LR_ATTN_STAGGER 0
 #endif
@@ -275,8 +341,13 @@ struct AttnTcCfg {
   static constexpr int kAtoms = HD / 32;
   static constexpr int kTileBytes = kAtoms * kAtomBytes;         // one Q / K tile, and the TMA-loaded part of a V tile
   static constexpr int kVTileBytes = (kAtoms + (kOnes ? 1 : 0)) * kAtomBytes;  // V tile + one atom of ones (row sums via the MMA)
+  // epilogue staging (LR_ATTN_EPI_STAGE): row pitch HD*2 + 16 bytes (conflict-free 16-byte accesses), 256 with an XOR
+  // swizzle for head_dim 128; with P in TMEM there is no retired P buffer to borrow, so 128 rows are added
+  static constexpr int kStagePitch = HD == 128 ? 256 : HD * 2 + 16;
+  static constexpr int kStageBytes = (LR_ATTN_EPI_STAGE && kPTmem) ? 128 * kStagePitch : 0;
   static constexpr int kSmemBytes = NT * kTileBytes /*Q*/ + kStages * kTileBytes /*K*/ + kStages * kVTileBytes /*V*/ +
-                                    (kPTmem ? 0 : NT * kPBytes) + 256 /*barriers*/ + (NT == 2 ? 2048 : 0) /*row-max exchange*/;
+                                    (kPTmem ? 0 : NT * kPBytes) + 256 /*barriers*/ + (NT == 2 ? 2048 : 0) /*row-max exchange*/ +
+                                    kStageBytes;
 };
 
 // SPLIT = threads per query row in the softmax: 1 -> one thread owns the whole 128-column S row (2 warpgroups,
@@ -321,6 +392,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
   uint64_t* p_half = bars + 20;          // [2] per tile  softmax -> MMA : the first 64 keys of P_x(j) are stored (LR_ATTN_P_HALF)
   float* mbuf = reinterpret_cast<float*>(bars + 32);  // [2 tiles][2 halves][128] row-max exchange (SPLIT == 2)
+  [[maybe_unused]] uint8_t* sStage = reinterpret_cast<uint8_t*>(bars) + 256 + (NT == 2 ? 2048 : 0);  // PTMEM only
   constexpr int kThreads = 128 + 128 * NT * SPLIT;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -462,6 +534,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         // K and V rings advance independently (the MMA thread consumes them out of lock-step)
         int kj = 0, vj = 0;
         while (kj < n || vj < n) {
+          [[maybe_unused]] const int kv_before = kj + vj;
           if (kj < n && mbar_test_wait(&k_empty[(g + kj) % NS], (((g + kj) / NS) & 1) ^ 1)) {
             if (kj == 0) {
               // Q of this tile. For a later tile the Q buffer is free once every S MMA of the previous tile - its only
@@ -485,6 +558,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
               for (int a = 0; a < NA; ++a)
                 tma_load_2d(sK + s * TILE + a * kAtomBytes, &tm_qkv, &k_full[s], k_col0 + kv_head * HD + a * 32,
                             slot_row0 + start + kj * 128);
+              if (LR_ATTN_L2_PREFETCH && NS == 1 && kj + 1 < n)
+                for (int a = 0; a < NA; ++a) {
+                  tma_prefetch_l2_2d(&tm_qkv, k_col0 + kv_head * HD + a * 32, slot_row0 + start + (kj + 1) * 128);
+                  tma_prefetch_l2_2d(&tm_qkv, v_col0 + kv_head * HD + a * 32, slot_row0 + start + (kj + 1) * 128);
+                }
             }
             ++kj;
           }
@@ -500,6 +578,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
             }
             ++vj;
           }
+          if (LR_ATTN_POLL_SLEEP > 0 && kj + vj == kv_before) poll_idle();
         }
         g += n;
       }
@@ -623,6 +702,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         int s_next = 1, pv_next = 0;
         [[maybe_unused]] bool half_issued = false;
         while (pv_next < nx) {
+          [[maybe_unused]] const int ev_before = s_next + pv_next + int(half_issued);
           if (s_next < nx && LR_MMA_VOTE(mbar_test_wait(&s_free[x], (g + s_next - 1) & 1) &&
                                          mbar_test_wait(&k_full[(g + s_next) % NS], ((g + s_next) / NS) & 1))) {
             tc_fence_after();
@@ -662,6 +742,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
             ATTN_TRACE(0, x * 4 + 2, pv_next);
             ++pv_next;
           }
+          if (LR_ATTN_POLL_SLEEP > 0 && s_next + pv_next + int(half_issued) == ev_before) poll_idle();
         }
       }
       for (int j = nx; j < n; ++j) {  // K/V blocks only the other tile reads (NT == 2: one tile pair per CTA, g == 0)
@@ -718,7 +799,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     }
     for (int j = 0; j < nx; ++j) {
       if (tr) ATTN_TRACE(1 + x, 0, j);
-      mbar_wait(&s_full[x], (g + j) & 1);
+      softmax_wait(&s_full[x], (g + j) & 1);
       tc_fence_after();
       if (tr) ATTN_TRACE(1 + x, 1, j);
       const int kv0 = start + j * 128;
@@ -728,7 +809,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       float mxc[8];  // 8 independent chains instead of one long dependent FMNMX chain
 #pragma unroll
       for (int c = 0; c < 8; ++c) mxc[c] = -INFINITY;
+      [[maybe_unused]] int nvalid = 128, vmin = 128, vmax = 128;   // leading valid columns: this row / warp min / warp max
+      if (LR_ATTN_CHUNK_MASK && need_mask && !seg) {
+        int lim = kv_end[x] - kv0;
+        if (CAUSAL) lim = min(lim, row_abs + 1 - kv0);
+        nvalid = max(0, min(128, lim));
+        vmin = __reduce_min_sync(0xffffffffu, nvalid);
+        vmax = __reduce_max_sync(0xffffffffu, nvalid);
+      }
+      auto chunk_dead = [&](int c) { return LR_ATTN_CHUNK_MASK != 0 && (h * NCH + c) * 32 >= vmax; };  // warp-uniform
       auto mask_chunk = [&](int c) {
+        if (LR_ATTN_CHUNK_MASK && !seg) {
+          const int base = (h * NCH + c) * 32;
+          // every lane keeps the whole chunk, or no lane keeps anything: a dead chunk is never read again (no max, no
+          // exponentials). Writing -inf into it instead costs 1.2 KB of spills (ptxas), so it is simply left alone.
+          if (base + 32 <= vmin || base >= vmax) return;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sv[c][i] = (base + i < nvalid) ? sv[c][i] : 0xff800000u;
+          return;
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int col = kv0 + (h * NCH + c) * 32 + i;
@@ -756,12 +855,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
           tmem_ld_wait_dep(sv[c]);
           if (c + 1 < NCH) tmem_ld_32x32(tm_S[x] + lane_addr + (c + 1) * 32, sv[c + 1]);
           if (need_mask) mask_chunk(c);
-          if (!(LR_ATTN_KO & 4)) max_chunk(c);
+          if (!(LR_ATTN_KO & 4) && !chunk_dead(c)) max_chunk(c);
         }
         if (tr) ATTN_TRACE(1 + x, 2, j);
       } else {
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) tmem_ld_32x32(tm_S[x] + lane_addr + (h * NCH + c) * 32, sv[c]);
+        for (int c = 0; c < NCH; ++c)
+          tmem_ld_32x32(tm_S[x] + lane_addr + (h * NCH + c) * 32, sv[c]);
         tmem_ld_wait();
         if constexpr (SPLIT == 1 && LR_ATTN_EARLY_SFREE) {
           tc_fence_before();
@@ -771,11 +871,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         if (tr) ATTN_TRACE(1 + x, 2, j);
         if (need_mask) {
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) mask_chunk(c);
-        }
+          for (int c = 0; c < NCH; ++c) {
+            mask_chunk(c);
+            if (!(LR_ATTN_KO & 4) && !chunk_dead(c)) max_chunk(c);
+          }
+        } else {
 #pragma unroll
-        for (int c = 0; c < NCH; ++c)
-          if (!(LR_ATTN_KO & 4)) max_chunk(c);
+          for (int c = 0; c < NCH; ++c)
+            if (!(LR_ATTN_KO & 4)) max_chunk(c);
+        }
       }
       float mx = fmaxf(fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3])), fmaxf(fmaxf(mxc[4], mxc[5]), fmaxf(mxc[6], mxc[7])));
       if constexpr (SPLIT == 2) {
@@ -809,11 +913,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       }
       if (tr) ATTN_TRACE(1 + x, 3, j);
       // P = exp2(S*scale - m_ref) (masked entries: exp2(-inf) = 0) -> bf16, 32 columns (one chunk) at a time
-      auto exp_chunk = [&](int c, uint32_t (&pk)[16]) {
+      // MASKED (compile-time tag): the instantiation for blocks that need masking consults chunk_dead(); the one for
+      // all other blocks stays a single straight-line region (a warp-uniform branch per chunk keeps the scheduler from
+      // interleaving the FFMA / MUFU / F2FP streams of neighbouring chunks: measured +3 % when it sat in the common path)
+      auto exp_chunk = [&](int c, uint32_t (&pk)[16], auto masked_tag) {
+        if (decltype(masked_tag)::value && chunk_dead(c)) {   // masked for every row of this warp: P = 0, no exponentials
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+          return;
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
+#if LR_ATTN_FFMA2
+          float x0, x1;
+          ffma2(x0, x1, sv[c][2 * i], sv[c][2 * i + 1], scale_log2, -msafe);
+          const float p0 = softmax_exp2(x0, 2 * i), p1 = softmax_exp2(x1, 2 * i + 1);
+#else
           const float p0 = softmax_exp2(fmaf(__uint_as_float(sv[c][2 * i]), scale_log2, -msafe), 2 * i);
           const float p1 = softmax_exp2(fmaf(__uint_as_float(sv[c][2 * i + 1]), scale_log2, -msafe), 2 * i + 1);
+#endif
           if constexpr (!ONES) {
             l_reg[(2 * i) & 3] += p0;
             l_reg[(2 * i + 1) & 3] += p1;
@@ -845,11 +963,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         }
 #endif
       };
+      auto p_phase = [&](auto masked_tag) {
       [[maybe_unused]] uint32_t pk_first[16];
-      if constexpr (LR_ATTN_EXP_FIRST != 0) exp_chunk(0, pk_first);   // registers only: runs under the wait below
+      if constexpr (LR_ATTN_EXP_FIRST != 0) exp_chunk(0, pk_first, masked_tag);   // registers only: runs under the wait below
       // P_x buffer and O_x may be touched only after O_x += P_x(j-1) V_(j-1) has retired
       if (j > 0) {
-        mbar_wait(&pv_done[x], (g + j - 1) & 1);
+        softmax_wait(&pv_done[x], (g + j - 1) & 1);
         tc_fence_after();
         if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll 1
@@ -871,7 +990,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
           store_chunk(0, pk_first);
         } else {
           uint32_t pk[16];
-          exp_chunk(c, pk);
+          exp_chunk(c, pk, masked_tag);
           store_chunk(c, pk);
         }
         if (LR_ATTN_P_HALF && SPLIT == 1 && c == NCH / 2 - 1) {   // keys 0..63 are stored: the MMA thread may issue the first half of P.V
@@ -882,6 +1001,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
           if (lane == 0) mbar_arrive(&p_half[x]);
         }
       }
+      };
+      if (LR_ATTN_CHUNK_MASK != 0 && need_mask && !seg) p_phase(std::true_type{});
+      else p_phase(std::false_type{});
 #if !(LR_ATTN_KO & 2) && !(LR_ATTN_KO & 64)
       if constexpr (PTMEM) tmem_st_wait();   // the tcgen05.st of the P row have landed
       else fence_proxy_async_smem();  // P (generic-proxy stores) must be visible to the tensor core's async proxy
@@ -897,11 +1019,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     const bool row_valid = row_abs >= lo[x] && row_abs < hi[x];
     bf16* orow = o + size_t(slot_row0 + row_abs) * ld_o + head * HD;
     if (nx > 0) {
+      if (tr) ATTN_TRACE(1 + x, 7, 0);   // last p_full arrived: the drain of the tile starts
       mbar_wait(&o_final[x], tq & 1);
       // the last block's pv_done phase completed together with o_final (same commit point); observing it here keeps
       // every phase of that barrier waited-on before the next tile arrives on it again (compute-sanitizer synccheck)
       mbar_wait(&pv_done[x], (g + nx - 1) & 1);
       tc_fence_after();
+      if (tr) ATTN_TRACE(1 + x, 7, 1);   // last P.V retired
       float inv;
       if constexpr (!ONES) {
         const float l_sum = (l_reg[0] + l_reg[1]) + (l_reg[2] + l_reg[3]);
@@ -913,6 +1037,47 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         const float l_sum = __uint_as_float(lv[0]);
         inv = l_sum > 0.f ? 1.f / l_sum : 0.f;
       }
+      if constexpr (LR_ATTN_EPI_STAGE && SPLIT == 1) {
+        constexpr int CH = HD / 8;               // 16-byte pieces per output row
+        constexpr int PITCH = Cfg::kStagePitch;
+        auto stage_row = [&](int rr) -> uint8_t* {   // row rr (0..31) of this warp
+          if constexpr (PTMEM) return sStage + (q * 32 + rr) * PITCH;
+          // this warp's own rows of the retired P buffer: 4 KB in each of the two 64-column atoms, 16 rows in each
+          else return sP + x * kPBytes + (rr >> 4) * (kPBytes / 2) + q * 4096 + (rr & 15) * PITCH;
+        };
+        uint8_t* my_row = stage_row(lane);
+#pragma unroll 1
+        for (int c = 0; c < HD / 32; ++c) {
+          uint32_t ov[32];
+          tmem_ld_32x32(tm_O[x] + lane_addr + c * 32, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(ov[8 * t]) * inv, __uint_as_float(ov[8 * t + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(ov[8 * t + 2]) * inv, __uint_as_float(ov[8 * t + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(ov[8 * t + 4]) * inv, __uint_as_float(ov[8 * t + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(ov[8 * t + 6]) * inv, __uint_as_float(ov[8 * t + 7]) * inv);
+            const int piece = c * 4 + t;
+            *reinterpret_cast<uint4*>(my_row + ((HD == 128 ? (piece ^ (lane & 7)) : piece) << 4)) = u;
+          }
+        }
+        __syncwarp();
+        const int row0 = m0 + x * 128 + q * 32;   // first row of this warp
+        const int slot_end = seq_base ? end : rows_per_seq;
+#pragma unroll 1
+        for (int it = 0; it < CH; ++it) {
+          const int idx = it * 32 + lane, rr = idx / CH, piece = idx - rr * CH;
+          const int ra = row0 + rr;
+          if (ra < slot_end) {
+            uint4 u = make_uint4(0, 0, 0, 0);
+            if (ra >= lo[x] && ra < hi[x])
+              u = *reinterpret_cast<const uint4*>(stage_row(rr) + ((HD == 128 ? (piece ^ (rr & 7)) : piece) << 4));
+            *reinterpret_cast<uint4*>(o + size_t(slot_row0 + ra) * ld_o + head * HD + piece * 8) = u;
+          }
+        }
+        __syncwarp();   // the staging rows are this warp's P rows of the next tile
+      } else {
 #pragma unroll 1
       for (int c = h; c < HD / 32; c += SPLIT) {
         uint32_t ov[32];
@@ -932,10 +1097,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
           }
         }
       }
+      }
     } else if (row_in_slot && h == 0) {
 #pragma unroll 1
       for (int c = 0; c < HD / 8; ++c) *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(0, 0, 0, 0);
     }
+    if (tr) ATTN_TRACE(1 + x, 7, 2);     // O written to global memory
     g += n;
     if (n > 0) ++tq;
     // the O accumulator and the P buffer of this tile are free again: the next tile's first P.V is issued only after

@@ -58,7 +58,15 @@ VARIANTS = {
     "mw_d": _v(desc32=1, mma_warp=1),
     "mw_pd": _v(1, 0, 1, 1),
     "mw_epd": _v(1, 1, 1, 1),
-    "mw2_epd": _v(1, 1, 1, 2),                      # = the product at the end of round 2
+    "mw2_epd": _v(1, 1, 1, 2),                      # = the product after the hand-off work
+    "cm": _v(1, 1, 1, 2, LR_ATTN_CHUNK_MASK=1),
+    "cm0": _v(1, 1, 1, 2, LR_ATTN_CHUNK_MASK=0),
+    "ffma2": _v(1, 1, 1, 2, LR_ATTN_CHUNK_MASK=1, LR_ATTN_FFMA2=1),
+    "es": {"LR_ATTN_EPI_STAGE": 1},
+    "es0": {"LR_ATTN_EPI_STAGE": 0},
+    **{f"sleep{d}": {"LR_ATTN_POLL_SLEEP": d} for d in (20, 50, 100, 200)},
+    "l2pf": {"LR_ATTN_L2_PREFETCH": 1},
+    "cm_spin": _v(1, 1, 1, 2, LR_ATTN_CHUNK_MASK=1, LR_ATTN_SPIN_WAIT=1),
     "mw_epd_aux48": _v(1, 1, 1, 1, LR_ATTN_AUX_REGS=48),
     "mw_epd_esfree": _v(1, 1, 1, 1, LR_ATTN_EARLY_SFREE=1),
     # "@nt2": the same object code as the named variant, launched as two query tiles per CTA / one CTA per SM for

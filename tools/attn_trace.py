@@ -26,7 +26,7 @@ IMPL = int(sys.argv[sys.argv.index("--impl") + 1]) if "--impl" in sys.argv else 
 
 
 def main():
-    if not os.path.exists(OUT) or "--build" in sys.argv:
+    if not os.path.exists(OUT) or "--build" in sys.argv or "--build-only" in sys.argv:
         build()
     if "--build-only" in sys.argv:
         return
@@ -72,6 +72,11 @@ def main():
                 v = int(t[0, ev, j])
                 row.append(f"{names[0][ev]}={v - t0 if v else -1}")
             print("  mma      " + " | ".join(row))
+        d = [int(t[1, 7, k]) for k in range(3)]
+        if all(d):
+            last_p = int(t[1, 6, nb - 1])
+            print(f"  tile drain: last p_full -> drain start {d[0] - last_p}, wait last P.V (o_final) {d[1] - d[0]}, "
+                  f"O -> bf16 -> global {d[2] - d[1]} cycles; first event -> first s_full seen {int(t[1, 1, 0]) - t0}")
         # per-iteration deltas for softmax A
         import statistics
         its = [int(t[1, 6, j] - t[1, 6, j - 1]) for j in range(1, nb) if t[1, 6, j] and t[1, 6, j - 1]]
