@@ -66,6 +66,8 @@ VARIANTS = {
     "es0": {"LR_ATTN_EPI_STAGE": 0},
     **{f"sleep{d}": {"LR_ATTN_POLL_SLEEP": d} for d in (20, 50, 100, 200)},
     "l2pf": {"LR_ATTN_L2_PREFETCH": 1},
+    "p_poly1": {"LR_ATTN_POLY_NUM": 1},
+    "p_poly2": {"LR_ATTN_POLY_NUM": 2},
     "cm_spin": _v(1, 1, 1, 2, LR_ATTN_CHUNK_MASK=1, LR_ATTN_SPIN_WAIT=1),
     "mw_epd_aux48": _v(1, 1, 1, 1, LR_ATTN_AUX_REGS=48),
     "mw_epd_esfree": _v(1, 1, 1, 1, LR_ATTN_EARLY_SFREE=1),
