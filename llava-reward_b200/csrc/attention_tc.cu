@@ -766,7 +766,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
     if constexpr (NT == 1 && SPLIT == 2) {
       // experiment (tools/attn_variants.py --split): two threads per row, 384 threads x 80 registers at launch,
       // re-split 128 x 40 + 256 x 96
-      asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+#ifndef LR_ATTN_SPLIT_REGS
+#define LR_ATTN_SPLIT_REGS 96
+#endif
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(LR_ATTN_SPLIT_REGS));
     } else if constexpr (NT == 1) {
       // 2 CTAs/SM: the CTA's 256 x 128 registers are re-split 128 x AUX + 128 x (256 - AUX) (40 + 208 leaves 8 unused)
       asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(LR_ATTN_AUX_REGS <= 48 ? 208 : 256 - LR_ATTN_AUX_REGS));
@@ -1206,7 +1209,10 @@ int attention_tc(const void* q, const void* k, const void* v, void* o, int ld_qk
     if (split == 2) return launch_attn_tc<HD_, CAUSAL_, 2, 2>(LR_ATTN_ARGS);           \
     if (split == 3) return launch_attn_tc<HD_, CAUSAL_, 1, 1>(LR_ATTN_ARGS);           \
     if (split == 4) return launch_attn_tc<HD_, CAUSAL_, 1, 1>(LR_ATTN_ARGS, nullptr, nullptr, true); \
-    if (split == 6) return launch_attn_tc<HD_, CAUSAL_, 2, 1>(LR_ATTN_ARGS, nullptr, nullptr, true); \
+    if (split == 6) {  /* two softmax threads per row, one tile per CTA: not with P in TMEM (row sums per thread) */ \
+      if (AttnTcCfg<HD_, 1>::kPTmem) return LR_ERR_BAD_ARG;                            \
+      return launch_attn_tc<HD_, CAUSAL_, 2, 1>(LR_ATTN_ARGS, nullptr, nullptr, true); \
+    }                                                                                  \
     return launch_attn_tc<HD_, CAUSAL_, 1, 2>(LR_ATTN_ARGS);                           \
   }
   LR_ATTN_CASE(64, false)
