@@ -22,6 +22,7 @@
 // multiply V (and is rescaled together with O).
 #include <cuda.h>
 
+#include <atomic>
 #include <type_traits>
 
 #include "common.cuh"
@@ -255,7 +256,9 @@ __device__ __forceinline__ void softmax_wait(uint64_t* bar, uint32_t parity) {
 #ifndef LR_ATTN_STAGGER_MODE
 #define LR_ATTN_STAGGER_MODE 1
 #endif
+#if LR_ATTN_STAGGER > 0 && LR_ATTN_STAGGER_MODE == 2
 __device__ unsigned long long g_attn_sm_arrivals[1024];   // [%smid] = epoch << 32 | CTAs of that launch seen so far
+#endif
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -485,6 +488,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
       second = lin >= nsm && lin < 2 * nsm;
     } else {
+#if LR_ATTN_STAGGER_MODE == 2
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
       unsigned long long* slot = &g_attn_sm_arrivals[smid & 1023];
@@ -495,6 +499,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         old = atomicCAS(slot, seen, next);
       } while (old != seen);
       second = (seen >> 32) == epoch && (seen & 0xffffffffull) == 1ull;
+#else
+      second = false;
+#endif
     }
     if (second) {
       const long long t0 = clock64();
@@ -1151,7 +1158,7 @@ static EncodeTiledFn attn_encode_fn() {
   return fn;
 }
 
-static unsigned g_launch_epoch = 0;   // tags the per-SM arrival counters of one launch (LR_ATTN_STAGGER_MODE 2)
+static std::atomic<unsigned> g_launch_epoch{0};   // tags the per-SM arrival counters of one launch (LR_ATTN_STAGGER_MODE 2 experiment)
 
 template <int HD, bool CAUSAL, int SPLIT, int NT>
 static int launch_attn_tc(const void* base, int total_rows, int ld_qkv, int q_col0, int k_col0, int v_col0, void* o,
@@ -1189,7 +1196,7 @@ static int launch_attn_tc(const void* base, int total_rows, int ld_qkv, int q_co
   constexpr int kSmem = Cfg::kSmemBytes + ((SPLIT == 2 && NT == 1) ? 1024 : 0);   // row-max exchange of the experiment
   kern<<<grid, 128 + 128 * NT * SPLIT, kSmem, stream>>>(tm, reinterpret_cast<bf16*>(o), ld_o, rows_per_seq, seq_base,
                                                       seq_start, seq_len, q_col0, k_col0, v_col0, kv_group,
-                                                      scale * 1.4426950408889634f, row_lo, row_hi, tile_mode, ++g_launch_epoch);
+                                                      scale * 1.4426950408889634f, row_lo, row_hi, tile_mode, g_launch_epoch.fetch_add(1u, std::memory_order_relaxed) + 1u);
   return lr_launch_status();
 }
 

@@ -1,7 +1,11 @@
 """Compare compile-time variants of the tcgen05 attention kernel (softmax exponentials split between the MUFU and the
 FMA pipe, early release of the S buffer): builds one private .so per variant (here, no GPU needed: --build-only) and,
 on the GPU box, times every variant on the three product shapes and checks it against an fp32 reference.
-usage: python tools/attn_variants.py --build-only ; (GPU box) python tools/attn_variants.py"""
+usage: python tools/attn_variants.py --build-only ; (GPU box) python tools/attn_variants.py
+
+SUPERSEDED by tools/attn_ab.py: this script times one variant after the other, and on a power-capped B200 the first
+variant then always wins (identical object code measured 1.49 ms first and 1.68 ms sixth). Kept because the r01 / early
+r02 logs under profiles/ were produced with it; do not use it for effects below ~15 %."""
 import ctypes as C
 import os
 import subprocess
