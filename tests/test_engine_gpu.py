@@ -639,3 +639,26 @@ def test_device_prefetcher_pinned_memory_is_bounded_for_ragged_batches():
     biggest = max(n * 4 + (n // 7) * 8 for n in sizes)
     assert pf.pinned_bytes <= 2 * (1.25 * biggest + 1024), (pf.pinned_bytes, biggest)
     assert pf.h2d_bytes == sum(n * 4 + (n // 7) * 8 for n in sizes)
+
+
+@pytest.mark.parametrize("case", ["slim_bt", "slim_gpm"])
+def test_all_padding_sample_does_not_disturb_the_batch(case, tmp_path_factory):
+    """Degenerate input: one sample of a ragged batch has an all-zero attention mask (the reference then reads row
+    S - 1 of that sample, rw_model_general_preference.py:420-421; its value depends on the attention implementation -
+    uniform softmax in the eager path, an empty sequence under flash-attention - so only finiteness is asserted for
+    it). The other samples must come out bit-identical to the same batch with a normal middle sample: the slot
+    layout the engine falls back to for such a batch (no rows to pack for that sample) is output-identical."""
+    fx = load_fixture(case)
+    args, model, cfg = build_model(fx, tmp_path_factory)
+    from llava_reward_b200.synth import synth_batch
+    ids, mask, pix, sizes = synth_batch(cfg, 3, (336, 672), None, seed=41, tag="dg", device="cuda",
+                                        image_hw_list=[(336, 672), (672, 336), (336, 672)])
+    r_ok, _ = model.custom_forward(ids, mask, pix, sizes)
+    mask_d = mask.clone()
+    mask_d[1] = 0
+    r_d, _ = model.custom_forward(ids, mask_d, pix, sizes)
+    assert torch.isfinite(r_d.float()).all()
+    assert torch.equal(r_d[0], r_ok[0]) and torch.equal(r_d[2], r_ok[2]), (r_d, r_ok)
+    # and the whole call is repeatable (no state left behind by the degenerate batch)
+    r_d2, _ = model.custom_forward(ids, mask_d, pix, sizes)
+    assert torch.equal(r_d2, r_d)
