@@ -199,6 +199,18 @@ __device__ __forceinline__ bool elect_one() {
 #ifndef LR_ATTN_SPIN_WAIT
 #define LR_ATTN_SPIN_WAIT 0
 #endif
+// LR_ATTN_PRELOAD 1 (one softmax thread per row): software pipelining inside the softmax thread. While the
+// exponentials of block j run, the registers of the chunks already consumed are refilled with S(j+1) - probed with a
+// non-blocking test of s_full once the first / second chunk is done, so nothing stalls if the S MMA is late - and after
+// the p_full arrive of block j only `tcgen05.wait::ld` + the row max of block j+1 are left before s_free(j+1). The wait
+// on s_full and the TMEM read latency (two of the seven links of the per-block chain) leave the critical
+// path; blocks that need masking (the diagonal / last block) and the first block of a tile take the plain path.
+// Measured (profiles/r02_attention_ab_interleaved_12_preload.txt): +10 ... +26 % SLOWER - the probes, the volatile
+// tcgen05.ld between the chunks and the branches cut the exponential phase into basic blocks the scheduler can no
+// longer interleave, and S(j+1) is rarely complete when the first two chunks are done. Off.
+#ifndef LR_ATTN_PRELOAD
+#define LR_ATTN_PRELOAD 0
+#endif
 // LR_ATTN_L2_PREFETCH 1: with the single-stage K / V ring the load of block j+1 starts only when the MMAs on block j
 // have retired, so its latency sits between two S MMAs of a tile; the producer therefore asks the L2 for block j+1
 // (cp.async.bulk.prefetch.tensor) while it issues the load of block j.
@@ -807,15 +819,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       my_lo = row_lo[row_abs];
       my_hi = row_hi[row_abs];
     }
+    uint32_t sv[NCH][32];          // the S row of the current block (LR_ATTN_PRELOAD: refilled with the next block's)
+    [[maybe_unused]] bool have = false;   // sv already holds S(j), its row max is mx_pre and s_free(j) has been signalled
+    [[maybe_unused]] float mx_pre = 0.f;
     for (int j = 0; j < nx; ++j) {
-      if (tr) ATTN_TRACE(1 + x, 0, j);
-      softmax_wait(&s_full[x], (g + j) & 1);
-      tc_fence_after();
-      if (tr) ATTN_TRACE(1 + x, 1, j);
+      const bool preloaded = LR_ATTN_PRELOAD && have;
+      have = false;
+      if (!preloaded) {
+        if (tr) ATTN_TRACE(1 + x, 0, j);
+        softmax_wait(&s_full[x], (g + j) & 1);
+        tc_fence_after();
+        if (tr) ATTN_TRACE(1 + x, 1, j);
+      }
       const int kv0 = start + j * 128;
       const bool need_mask = seg || (kv0 + 128 > kv_end[x]) || (CAUSAL && kv0 + 127 > m0 + x * 128);
       // whole S row -> registers, then give the TMEM buffer back to the MMA warp
-      uint32_t sv[NCH][32];
       float mxc[8];  // 8 independent chains instead of one long dependent FMNMX chain
 #pragma unroll
       for (int c = 0; c < 8; ++c) mxc[c] = -INFINITY;
@@ -857,6 +875,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         for (int i = 0; i < 32; ++i) mxc[(c * 2 + (i >> 4)) & 7] = fmaxf(mxc[(c * 2 + (i >> 4)) & 7], __uint_as_float(sv[c][i]));
 #endif
       };
+      float mx;
+      if (!preloaded) {
       if constexpr (SPLIT == 1 && LR_ATTN_PIPE_LD) {
         // chunk c+1 is in flight while chunk c is masked and reduced
         tmem_ld_32x32(tm_S[x] + lane_addr, sv[0]);
@@ -891,7 +911,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
             if (!(LR_ATTN_KO & 4)) max_chunk(c);
         }
       }
-      float mx = fmaxf(fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3])), fmaxf(fmaxf(mxc[4], mxc[5]), fmaxf(mxc[6], mxc[7])));
+      mx = fmaxf(fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3])), fmaxf(fmaxf(mxc[4], mxc[5]), fmaxf(mxc[6], mxc[7])));
       if constexpr (SPLIT == 2) {
         // The other 64 columns of this row live in a thread of the partner warpgroup: exchange the partial maxima
         // through smem. The S buffer is released only AFTER the exchange, so S_x(j+1) - and with it the next write
@@ -905,6 +925,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[x]);
+      }
+      } else {
+        mx = mx_pre;   // S(j) was read and reduced under the exponentials of block j-1
       }
       mx *= scale_log2;  // scale > 0, so max commutes with the scaling
       // lazy rescale: move the reference max only when it grew by more than the threshold
@@ -973,6 +996,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         }
 #endif
       };
+      // LR_ATTN_PRELOAD: may the next block be pulled in under this block's exponentials?
+      [[maybe_unused]] bool next_ready = false;
+      [[maybe_unused]] const bool next_ok = LR_ATTN_PRELOAD && SPLIT == 1 && !LR_ATTN_PIPE_LD && j + 1 < nx && !seg &&
+                                            !(kv0 + 256 > kv_end[x]) && !(CAUSAL && kv0 + 128 + 127 > m0 + x * 128);
+      auto preload_hook = [&](auto c_tag) {   // chunk c of S(j) has been consumed: its registers can take S(j+1)
+        constexpr int c = decltype(c_tag)::value;
+        if constexpr (LR_ATTN_PRELOAD != 0 && SPLIT == 1) {
+          if (!next_ok) return;
+          if (c <= 1 && !next_ready && mbar_test_wait(&s_full[x], (g + j + 1) & 1)) {
+            next_ready = true;
+            tc_fence_after();
+            if (c == 1) tmem_ld_32x32(tm_S[x] + lane_addr, sv[0]);
+          }
+          if (next_ready) tmem_ld_32x32(tm_S[x] + lane_addr + c * 32, sv[c]);
+        }
+      };
       auto p_phase = [&](auto masked_tag) {
       [[maybe_unused]] uint32_t pk_first[16];
       if constexpr (LR_ATTN_EXP_FIRST != 0) exp_chunk(0, pk_first, masked_tag);   // registers only: runs under the wait below
@@ -1003,6 +1042,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
           exp_chunk(c, pk, masked_tag);
           store_chunk(c, pk);
         }
+        if constexpr (LR_ATTN_PRELOAD != 0 && SPLIT == 1) {
+          if (c == 0) preload_hook(std::integral_constant<int, 0>{});
+          if (c == 1) preload_hook(std::integral_constant<int, 1>{});
+          if (c == 2) preload_hook(std::integral_constant<int, 2>{});
+          if (c == 3) preload_hook(std::integral_constant<int, 3>{});
+        }
         if (LR_ATTN_P_HALF && SPLIT == 1 && c == NCH / 2 - 1) {   // keys 0..63 are stored: the MMA thread may issue the first half of P.V
           if constexpr (PTMEM) tmem_st_wait();
           else fence_proxy_async_smem();
@@ -1023,6 +1068,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[x]);
       if (tr) ATTN_TRACE(1 + x, 6, j);
+      if constexpr (LR_ATTN_PRELOAD != 0 && SPLIT == 1) {
+        if (next_ready) {   // S(j+1) is (arriving) in sv: finish the read, reduce, hand the S buffer back
+          tmem_ld_wait();
+          float m8[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) m8[c] = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m8[(c * 2 + (i >> 4)) & 7] = fmaxf(m8[(c * 2 + (i >> 4)) & 7], __uint_as_float(sv[c][i]));
+          mx_pre = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[x]);
+          have = true;
+        }
+      }
     }
     // epilogue: O / l -> bf16 -> global; rows outside the valid run are zero-filled
     const bool row_in_slot = row_abs < (seq_base ? end : rows_per_seq);  // packed: the next rows are another sequence
