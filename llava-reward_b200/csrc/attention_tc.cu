@@ -196,6 +196,11 @@ __device__ __forceinline__ bool elect_one() {
 #endif
 // LR_ATTN_SPIN_WAIT 1: the softmax warps poll s_full / pv_done with mbarrier.test_wait instead of try_wait (which may
 // suspend the warp until the phase completes or a time slice ends).
+// LR_ATTN_PAD_SMEM = bytes of unused shared memory added to the two-CTAs-per-SM configurations: with 100 KB only ONE
+// CTA fits on an SM - the measurement of what co-residency is worth.
+#ifndef LR_ATTN_PAD_SMEM
+#define LR_ATTN_PAD_SMEM 0
+#endif
 #ifndef LR_ATTN_SPIN_WAIT
 #define LR_ATTN_SPIN_WAIT 0
 #endif
@@ -362,7 +367,7 @@ struct AttnTcCfg {
   static constexpr int kStageBytes = (LR_ATTN_EPI_STAGE && kPTmem) ? 128 * kStagePitch : 0;
   static constexpr int kSmemBytes = NT * kTileBytes /*Q*/ + kStages * kTileBytes /*K*/ + kStages * kVTileBytes /*V*/ +
                                     (kPTmem ? 0 : NT * kPBytes) + 256 /*barriers*/ + (NT == 2 ? 2048 : 0) /*row-max exchange*/ +
-                                    kStageBytes;
+                                    kStageBytes + (kOnePerSm ? 0 : LR_ATTN_PAD_SMEM);
 };
 
 // SPLIT = threads per query row in the softmax: 1 -> one thread owns the whole 128-column S row (2 warpgroups,

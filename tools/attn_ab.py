@@ -73,6 +73,7 @@ VARIANTS = {
     "split104@split2": {"_so": "split104", "_env": {"LR_ATTN_VARIANT": "6"}},
     "preload": {"LR_ATTN_PRELOAD": 1},
     "preload0": {"LR_ATTN_PRELOAD": 0},
+    "one_cta_per_sm": {"LR_ATTN_PAD_SMEM": 102400},
     "cm_spin": _v(1, 1, 1, 2, LR_ATTN_CHUNK_MASK=1, LR_ATTN_SPIN_WAIT=1),
     "mw_epd_aux48": _v(1, 1, 1, 1, LR_ATTN_AUX_REGS=48),
     "mw_epd_esfree": _v(1, 1, 1, 1, LR_ATTN_EARLY_SFREE=1),
