@@ -201,6 +201,11 @@ __device__ __forceinline__ bool elect_one() {
 #ifndef LR_ATTN_PAD_SMEM
 #define LR_ATTN_PAD_SMEM 0
 #endif
+// LR_ATTN_NO_ONES 1: no [V | 1] row-sum columns anywhere - the softmax threads sum the exponentials in registers (as the
+// P-in-TMEM and two-tile hd-128 configurations already do): 4 KB less operand traffic per block, 128 FADD more per row.
+#ifndef LR_ATTN_NO_ONES
+#define LR_ATTN_NO_ONES 0
+#endif
 #ifndef LR_ATTN_SPIN_WAIT
 #define LR_ATTN_SPIN_WAIT 0
 #endif
@@ -355,7 +360,7 @@ struct AttnTcCfg {
   // columns of the ones trick - the softmax threads keep the row sums in registers instead (fp32 sum of the un-rounded
   // exponentials, like flash-attention 2) - and 227 KB of smem allow only a single K/V stage.
   static constexpr bool kPTmem = LR_ATTN_P_TMEM && HD == 64 && NT == 1;
-  static constexpr bool kOnes = !(HD == 128 && NT == 2) && !kPTmem;
+  static constexpr bool kOnes = !(HD == 128 && NT == 2) && !kPTmem && !LR_ATTN_NO_ONES;
   static constexpr int kStages = !kOnePerSm ? ((kPTmem && LR_ATTN_KV2) ? 2 : 1) : (kOnes ? 2 : 1);
   static constexpr int kTmemCols = kOnePerSm ? 512 : 256;
   static constexpr int kAtoms = HD / 32;
