@@ -317,3 +317,29 @@ def test_attention_multitile_is_bit_identical_to_one_tile_per_cta(hd, heads, T, 
         outs.append(o)
     assert not torch.isnan(outs[1].float()).any()
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("hd,causal", [(96, True), (64, False), (128, True), (96, False)])
+@pytest.mark.parametrize("left_pad", [True, False])
+def test_attention_mask_boundaries(hd, causal, left_pad):
+    """Valid lengths on every side of the 32-column chunk and 128-row tile boundaries (the chunk-level masking of the
+    tcgen05 kernel classifies chunks from the warp-wide min / max of the valid prefix): slot layout, left- or
+    right-aligned valid runs, causal and non-causal, against an fp32 reference per sequence."""
+    heads, T = 2, 300
+    lens = [1, 2, 31, 32, 33, 63, 64, 65, 95, 96, 97, 127, 128, 129, 159, 160, 161, 255, 256, 257, 289, 300]
+    nseq = len(lens)
+    D = heads * hd
+    qkv = rnd(nseq * T, 3 * D, seed=11)
+    starts = [T - n if left_pad else 0 for n in lens]
+    ss = torch.tensor(starts, dtype=torch.int32, device=DEV)
+    sl = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    o = torch.full((nseq * T, D), float("nan"), dtype=bf, device=DEV)
+    scale = hd ** -0.5
+    ops.attention(qkv, qkv[:, D:], qkv[:, 2 * D:], o, 3 * D, D, nseq, T, ss, sl, heads, hd, causal, scale, L.ATTN_TCGEN05)
+    torch.cuda.synchronize()
+    f = qkv.float().view(nseq, T, 3, heads, hd)
+    for s in range(nseq):
+        ref = attn_ref(f[s, :, 0], f[s, :, 1], f[s, :, 2], causal, scale, starts[s], lens[s]).reshape(T, D)
+        got = o[s * T:(s + 1) * T]
+        assert not torch.isnan(got.float()).any(), f"len {lens[s]}: rows left unwritten"
+        check_close(got, ref, f"attention len {lens[s]} start {starts[s]}", atol=1e-2, rtol=2e-2)
