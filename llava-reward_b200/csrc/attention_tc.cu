@@ -201,6 +201,14 @@ __device__ __forceinline__ bool elect_one() {
 #ifndef LR_ATTN_PAD_SMEM
 #define LR_ATTN_PAD_SMEM 0
 #endif
+// LR_ATTN_P_HYBRID 1 (head_dim 96, one tile per CTA): the decoder shape is shared-memory-bandwidth bound and
+// TMEM has 256 - 128 (S) - 96 (O) = 32 spare columns once the row sums live in registers: exactly the first 64 keys of
+// the bf16 P row. That half goes through TMEM (tcgen05.st, A operand of the first four P.V MMAs from TMEM), the second
+// half through shared memory as before: 36 KB less shared-memory traffic per block (16 KB of P stores, 16 KB of P
+// operand reads, the 4 KB ones atom of V).
+#ifndef LR_ATTN_P_HYBRID
+#define LR_ATTN_P_HYBRID 0
+#endif
 // LR_ATTN_NO_ONES 1: no [V | 1] row-sum columns anywhere - the softmax threads sum the exponentials in registers (as the
 // P-in-TMEM and two-tile hd-128 configurations already do): 4 KB less operand traffic per block, 128 FADD more per row.
 #ifndef LR_ATTN_NO_ONES
@@ -360,7 +368,8 @@ struct AttnTcCfg {
   // columns of the ones trick - the softmax threads keep the row sums in registers instead (fp32 sum of the un-rounded
   // exponentials, like flash-attention 2) - and 227 KB of smem allow only a single K/V stage.
   static constexpr bool kPTmem = LR_ATTN_P_TMEM && HD == 64 && NT == 1;
-  static constexpr bool kOnes = !(HD == 128 && NT == 2) && !kPTmem && !LR_ATTN_NO_ONES;
+  static constexpr bool kPHybrid = LR_ATTN_P_HYBRID && HD == 96 && NT == 1;
+  static constexpr bool kOnes = !(HD == 128 && NT == 2) && !kPTmem && !kPHybrid && !LR_ATTN_NO_ONES;
   static constexpr int kStages = !kOnePerSm ? ((kPTmem && LR_ATTN_KV2) ? 2 : 1) : (kOnes ? 2 : 1);
   static constexpr int kTmemCols = kOnePerSm ? 512 : 256;
   static constexpr int kAtoms = HD / 32;
@@ -402,6 +411,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
   uint8_t* sV = sK + NS * TILE;          // [NS][VTILE]
   uint8_t* sP = sV + NS * VTILE;         // [NT][kPBytes]
   constexpr bool PTMEM = Cfg::kPTmem;
+  constexpr bool PHYB = Cfg::kPHybrid;   // keys 0..63 of P in TMEM, 64..127 in the second smem atom
   constexpr bool kMmaWarp = LR_ATTN_MMA_WARP == 1 || (LR_ATTN_MMA_WARP == 2 && NT == 2);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (PTMEM ? 0 : NT * kPBytes));
   uint64_t* q_full = bars;               // [1]
@@ -539,7 +549,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
   const uint32_t tmem_base = *tmem_slot;
   // NT = 2: S_A 0, S_B 128, O_A 256, O_B 384;  NT = 1: S 0, O 128
   const uint32_t tm_S[2] = {tmem_base, tmem_base + 128};
-  const uint32_t tm_O[2] = {tmem_base + (NT == 2 ? 256 : (PTMEM ? 192 : 128)), tmem_base + 384};
+  const uint32_t tm_O[2] = {tmem_base + (NT == 2 ? 256 : (PTMEM ? 192 : (PHYB ? 160 : 128))), tmem_base + 384};
   const uint32_t tm_P = tmem_base + 128;   // PTMEM: 64 columns of packed bf16 pairs
 
   // register re-allocation between warpgroups: the softmax threads keep a whole 128-column S row in registers
@@ -696,6 +706,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
 #pragma unroll
         for (int kk = 0; kk < ((LR_ATTN_KO & 16) ? 0 : 8); ++kk) {
           if (kk < kk0 || kk >= kk1) continue;
+          if (PHYB && kk < 4) {   // keys 0..63: A = P from TMEM
+#if LR_ATTN_DESC32
+            umma_bf16_ts(tm_O[x], tm_P + kk * 8, desc_join(v_lo + ((kk * 1024) >> 4), umma_desc_hi(512, kLayoutSW64)),
+                         idesc_o, acc || kk != 0);
+#else
+            umma_bf16_ts(tm_O[x], tm_P + kk * 8, umma_desc(va + kk * 1024, kAtomBytes, 512, kLayoutSW64), idesc_o,
+                         acc || kk != 0);
+#endif
+            continue;
+          }
 #if LR_ATTN_DESC32
           umma_bf16_ss(tm_O[x], desc_join(p_lo + (((kk >> 2) * (kPBytes / 2) + (kk & 3) * 32) >> 4), umma_desc_hi(1024, kLayoutSW128)),
                        desc_join(v_lo + ((kk * 1024) >> 4), umma_desc_hi(512, kLayoutSW64)), idesc_o, acc || kk != 0);
@@ -986,7 +1006,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       // 128 columns = 2 atoms x 8 chunks of 16 B; chunk position XOR (row & 7) = the 128B swizzle.
       auto store_chunk = [&](int c, const uint32_t (&pk)[16]) {
         const int cg = h * NCH + c;  // chunk index inside the 128-column row
-        if constexpr (PTMEM) {   // 32 keys = 16 packed columns of this thread's own TMEM lane
+        if (PTMEM || (PHYB && cg < 2)) {   // 32 keys = 16 packed columns of this thread's own TMEM lane
           tmem_st_32x16(tm_P + lane_addr + cg * 16, pk);
           return;
         }
@@ -1059,7 +1079,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
           if (c == 3) preload_hook(std::integral_constant<int, 3>{});
         }
         if (LR_ATTN_P_HALF && SPLIT == 1 && c == NCH / 2 - 1) {   // keys 0..63 are stored: the MMA thread may issue the first half of P.V
-          if constexpr (PTMEM) tmem_st_wait();
+          if constexpr (PTMEM || PHYB) tmem_st_wait();
           else fence_proxy_async_smem();
           tc_fence_before();
           __syncwarp();
@@ -1070,8 +1090,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       if (LR_ATTN_CHUNK_MASK != 0 && need_mask && !seg) p_phase(std::true_type{});
       else p_phase(std::false_type{});
 #if !(LR_ATTN_KO & 2) && !(LR_ATTN_KO & 64)
-      if constexpr (PTMEM) tmem_st_wait();   // the tcgen05.st of the P row have landed
-      else fence_proxy_async_smem();  // P (generic-proxy stores) must be visible to the tensor core's async proxy
+      if constexpr (PTMEM || PHYB) tmem_st_wait();   // the tcgen05.st of the P row have landed
+      if constexpr (!PTMEM) fence_proxy_async_smem();  // P (generic-proxy stores) must be visible to the tensor core's async proxy
 #endif
       if (tr) ATTN_TRACE(1 + x, 5, j);
       tc_fence_before();
@@ -1289,7 +1309,7 @@ int attention_tc(const void* q, const void* k, const void* v, void* o, int ld_qk
     if (split == 3) return launch_attn_tc<HD_, CAUSAL_, 1, 1>(LR_ATTN_ARGS);           \
     if (split == 4) return launch_attn_tc<HD_, CAUSAL_, 1, 1>(LR_ATTN_ARGS, nullptr, nullptr, true); \
     if (split == 6) {  /* two softmax threads per row, one tile per CTA: not with P in TMEM (row sums per thread) */ \
-      if (AttnTcCfg<HD_, 1>::kPTmem) return LR_ERR_BAD_ARG;                            \
+      if (AttnTcCfg<HD_, 1>::kPTmem || AttnTcCfg<HD_, 1>::kPHybrid) return LR_ERR_BAD_ARG;                            \
       return launch_attn_tc<HD_, CAUSAL_, 2, 1>(LR_ATTN_ARGS, nullptr, nullptr, true); \
     }                                                                                  \
     return launch_attn_tc<HD_, CAUSAL_, 1, 2>(LR_ATTN_ARGS);                           \

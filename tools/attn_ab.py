@@ -75,6 +75,7 @@ VARIANTS = {
     "preload0": {"LR_ATTN_PRELOAD": 0},
     "one_cta_per_sm": {"LR_ATTN_PAD_SMEM": 102400},
     "no_ones": {"LR_ATTN_NO_ONES": 1},
+    "phyb": {"LR_ATTN_P_HYBRID": 1},
     "cm_spin": _v(1, 1, 1, 2, LR_ATTN_CHUNK_MASK=1, LR_ATTN_SPIN_WAIT=1),
     "mw_epd_aux48": _v(1, 1, 1, 1, LR_ATTN_AUX_REGS=48),
     "mw_epd_esfree": _v(1, 1, 1, 1, LR_ATTN_EARLY_SFREE=1),
