@@ -201,6 +201,16 @@ __device__ __forceinline__ bool elect_one() {
 #ifndef LR_ATTN_PAD_SMEM
 #define LR_ATTN_PAD_SMEM 0
 #endif
+// LR_ATTN_SPEC_MAX 1 (one softmax thread per row, blocks after the first of a tile that need no masking): the
+// exponentials start with the OLD reference maximum while the row maximum of this block is reduced in the issue slots
+// the MUFU-paced exponentials leave idle; the first 64 keys of P are held in registers until the maximum is known.
+// If no row of the warp has outgrown the lazy-rescale threshold (the usual case after the first blocks) the values are
+// exactly those of the plain path; otherwise the warp rescales O and recomputes those 64 keys with the new reference -
+// also exactly the plain path's values. The S buffer goes back to the MMA thread right after the TMEM read.
+// Measured: bit-identical output, +6 % slower on every shape (profiles/r02_attention_ab_interleaved_16_speculative_max.txt). Off.
+#ifndef LR_ATTN_SPEC_MAX
+#define LR_ATTN_SPEC_MAX 0
+#endif
 // LR_ATTN_P_HYBRID 1 (head_dim 96, one tile per CTA): the decoder shape is shared-memory-bandwidth bound and
 // TMEM has 256 - 128 (S) - 96 (O) = 32 spare columns once the row sums live in registers: exactly the first 64 keys of
 // the bf16 P row. That half goes through TMEM (tcgen05.st, A operand of the first four P.V MMAs from TMEM), the second
@@ -905,7 +915,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         for (int i = 0; i < 32; ++i) mxc[(c * 2 + (i >> 4)) & 7] = fmaxf(mxc[(c * 2 + (i >> 4)) & 7], __uint_as_float(sv[c][i]));
 #endif
       };
-      float mx;
+      float mx = 0.f;
+      // speculative reference maximum (see LR_ATTN_SPEC_MAX): CTA-uniform
+      const bool spec = LR_ATTN_SPEC_MAX != 0 && SPLIT == 1 && !LR_ATTN_PIPE_LD && !LR_ATTN_PRELOAD && j > 0 && !need_mask;
       if (!preloaded) {
       if constexpr (SPLIT == 1 && LR_ATTN_PIPE_LD) {
         // chunk c+1 is in flight while chunk c is masked and reduced
@@ -935,13 +947,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
             mask_chunk(c);
             if (!(LR_ATTN_KO & 4) && !chunk_dead(c)) max_chunk(c);
           }
-        } else {
+        } else if (!spec) {
 #pragma unroll
           for (int c = 0; c < NCH; ++c)
             if (!(LR_ATTN_KO & 4)) max_chunk(c);
         }
       }
-      mx = fmaxf(fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3])), fmaxf(fmaxf(mxc[4], mxc[5]), fmaxf(mxc[6], mxc[7])));
+      if (!spec) mx = fmaxf(fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3])), fmaxf(fmaxf(mxc[4], mxc[5]), fmaxf(mxc[6], mxc[7])));
       if constexpr (SPLIT == 2) {
         // The other 64 columns of this row live in a thread of the partner warpgroup: exchange the partial maxima
         // through smem. The S buffer is released only AFTER the exchange, so S_x(j+1) - and with it the next write
@@ -959,19 +971,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
       } else {
         mx = mx_pre;   // S(j) was read and reduced under the exponentials of block j-1
       }
-      mx *= scale_log2;  // scale > 0, so max commutes with the scaling
       // lazy rescale: move the reference max only when it grew by more than the threshold
-      float alpha = 1.f;
-      const bool grow = mx > m_ref + kRescaleThreshold || (m_ref == -INFINITY && mx > -INFINITY);
-      if (grow) {
-        alpha = exp2f(m_ref - mx);  // 0 when m_ref = -inf
-        m_ref = mx;
-      }
-      const float msafe = (m_ref == -INFINITY) ? 0.f : m_ref;
-      if constexpr (!ONES) {
+      float alpha = 1.f, msafe = (m_ref == -INFINITY) ? 0.f : m_ref;
+      bool grow = false;
+      auto update_ref = [&](float mxs) {   // mxs = row max x scale (scale > 0, so max commutes with the scaling)
+        grow = mxs > m_ref + kRescaleThreshold || (m_ref == -INFINITY && mxs > -INFINITY);
         if (grow) {
+          alpha = exp2f(m_ref - mxs);  // 0 when m_ref = -inf
+          m_ref = mxs;
+        }
+        msafe = (m_ref == -INFINITY) ? 0.f : m_ref;
+      };
+      if (!spec) {
+        update_ref(mx * scale_log2);
+        if constexpr (!ONES) {
+          if (grow) {
 #pragma unroll
-          for (int t = 0; t < 4; ++t) l_reg[t] *= alpha;
+            for (int t = 0; t < 4; ++t) l_reg[t] *= alpha;
+          }
         }
       }
       if (tr) ATTN_TRACE(1 + x, 3, j);
@@ -1087,7 +1104,58 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o,
         }
       }
       };
+      auto p_phase_spec = [&]() {
+        [[maybe_unused]] float l_save[4] = {l_reg[0], l_reg[1], l_reg[2], l_reg[3]};
+        uint32_t pk0[16], pk1[16];
+        exp_chunk(0, pk0, std::false_type{});          // with the old reference
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)                  // independent of the exponentials: fills their idle issue slots
+          if (!(LR_ATTN_KO & 4)) max_chunk(c);
+        softmax_wait(&pv_done[x], (g + j - 1) & 1);    // spec implies j > 0
+        tc_fence_after();
+        exp_chunk(1, pk1, std::false_type{});
+        const float mxs = fmaxf(fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3])),
+                                fmaxf(fmaxf(mxc[4], mxc[5]), fmaxf(mxc[6], mxc[7]))) * scale_log2;
+        update_ref(mxs);
+        if (__any_sync(0xffffffffu, grow)) {
+          // some row of this warp outgrew the threshold: rescale O and redo the first 64 keys with the new reference
+          // (rows that did not grow have alpha = 1 and the same reference: they reproduce their values)
+          if constexpr (!ONES) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) l_reg[t] = l_save[t] * alpha;
+          }
+#pragma unroll 1
+          for (int c = 0; c < HD / 32 + (ONES ? 1 : 0); ++c) {
+            uint32_t ov[32];
+            tmem_ld_32x32(tm_O[x] + lane_addr + c * 32, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st_32x32(tm_O[x] + lane_addr + c * 32, ov);
+          }
+          tmem_st_wait();
+          exp_chunk(0, pk0, std::false_type{});
+          exp_chunk(1, pk1, std::false_type{});
+        }
+        if (tr) ATTN_TRACE(1 + x, 4, j);
+        store_chunk(0, pk0);
+        store_chunk(1, pk1);
+        if (LR_ATTN_P_HALF) {   // keys 0..63 are stored: the MMA thread may issue the first half of P.V
+          if constexpr (PTMEM || PHYB) tmem_st_wait();
+          else fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_half[x]);
+        }
+#pragma unroll
+        for (int c = 2; c < NCH; ++c) {
+          uint32_t pk[16];
+          exp_chunk(c, pk, std::false_type{});
+          store_chunk(c, pk);
+        }
+      };
       if (LR_ATTN_CHUNK_MASK != 0 && need_mask && !seg) p_phase(std::true_type{});
+      else if (spec) p_phase_spec();
       else p_phase(std::false_type{});
 #if !(LR_ATTN_KO & 2) && !(LR_ATTN_KO & 64)
       if constexpr (PTMEM || PHYB) tmem_st_wait();   // the tcgen05.st of the P row have landed

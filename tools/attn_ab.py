@@ -76,6 +76,7 @@ VARIANTS = {
     "one_cta_per_sm": {"LR_ATTN_PAD_SMEM": 102400},
     "no_ones": {"LR_ATTN_NO_ONES": 1},
     "phyb": {"LR_ATTN_P_HYBRID": 1},
+    "specmax": {"LR_ATTN_SPEC_MAX": 1},
     "cm_spin": _v(1, 1, 1, 2, LR_ATTN_CHUNK_MASK=1, LR_ATTN_SPIN_WAIT=1),
     "mw_epd_aux48": _v(1, 1, 1, 1, LR_ATTN_AUX_REGS=48),
     "mw_epd_esfree": _v(1, 1, 1, 1, LR_ATTN_EARLY_SFREE=1),
@@ -168,6 +169,7 @@ def main():
 
     # correctness of every variant first (also the warm-up of every kernel)
     errs = {}
+    base_out, same = {}, {}
     unsupported = set()
     for vn, lib in libs.items():
         for name in shapes:
@@ -183,6 +185,10 @@ def main():
             e0 = ((o[:T].float() - ref).norm() / ref.norm()).item()
             e1 = ((o[-T:].float() - refl).norm() / refl.norm()).item()
             errs[(vn, name)] = max(e0, e1)
+            if vn == "base":
+                base_out[name] = o.clone()
+            elif name in base_out:
+                same[(vn, name)] = bool(torch.equal(o, base_out[name]))
             if not (errs[(vn, name)] < 5e-3):
                 print(f"!! {vn} | {name}: rel L2 err {e0:.3e} / {e1:.3e}", flush=True)
         ok = all(errs[(vn, name)] < 5e-3 for name in shapes)
@@ -228,7 +234,8 @@ def main():
             med = statistics.median(t)
             print(f"{name:22s} | {vn:24s} | {med:.4f} ms [{min(t):.4f}] = {fl / med / 1e9:5.0f} TF/s | "
                   f"rel {med / base if base else 0:.3f} | sm clock {statistics.median(clocks[(vn, name)]):.0f} MHz | "
-                  f"err {errs[(vn, name)]:.2e}", flush=True)
+                  f"err {errs[(vn, name)]:.2e}" + (f" | bits == base: {same[(vn, name)]}" if (vn, name) in same else ""),
+                  flush=True)
 
 
 if __name__ == "__main__":
