@@ -2,24 +2,21 @@
 // the accumulators in TMEM; K/V/Q tiles arrive by TMA (64B-swizzled atoms of 32 head-dim columns, so head_dim 96
 // needs no padding); softmax runs thread-per-row out of TMEM.
 //
-// Product configuration (NT = 1): one CTA = one 128-row query tile of one head, 256 threads, 112 KB smem and 256 TMEM
-// columns, so TWO CTAs share an SM: their softmax phases de-phase naturally and each CTA's prologue/epilogue hides
-// behind the other's main loop (measured: CLIP 1.70 -> 1.37 ms, decoder 1.35 -> 1.34 ms vs NT = 2).
-// Alternative (NT = 2, kept for comparison) - one CTA = 256 query rows (tiles A and B) sharing K/V, 384 threads:
-//   warp 0    : TMA producer (Q_A, Q_B once; K_j / V_j through two 2-stage rings shared by both tiles)
-//   warp 1    : MMA issuer   (S_X(j) = Q_X K_j^T  [128x128xHD],  O_X += P_X(j) V_j  [128xHDx128], X in {A,B})
-//   warp 2    : TMEM allocator (S_A, S_B: 128 fp32 columns each; O_A, O_B: HD columns each)
-//   warps 4-7 : softmax warpgroup of tile A,   warps 8-11: softmax warpgroup of tile B
-//               (tcgen05.ld the whole 128-column S row into registers and hand the S buffer straight back so
-//                S_X(j+1) is computed while this block's softmax runs -> running max / exp2 / row sum -> bf16 P
-//                row into 128B-swizzled smem -> mbarrier; O is rescaled in TMEM (tcgen05.ld/st) lazily, only when
-//                the row max grew by > 2^8)
-// The softmax warpgroups therefore run back to back; all MMA work hides behind them.
-// Softmax is MUFU-bound on this part (16 ex2/clk/SM, measured with the in-kernel timeline of tools/attn_trace.py;
-// ex2.approx.bf16x2 has the same per-element rate, so it is not used). Everything else is kept off the critical
-// path: the P stores are interleaved with the exponentials, and the row sums come from the tensor core - V carries
-// 16 extra columns of ones, so column HD of O accumulates sum_j P_ij in fp32 from exactly the bf16 values that
-// multiply V (and is rescaled together with O).
+// Product configurations (end of round 2; DESIGN.md 6a-6c has the measurements behind every choice):
+//   head_dim 64 / 96 (NT = 1): one CTA = one 128-row query tile of one head at a time, 256 threads, 256 TMEM columns
+//     and 48 KB (hd 64, P through TMEM) / 112 KB (hd 96, P through 128B-swizzled smem, row sums from 16 ones columns
+//     of V) of shared memory, so TWO CTAs share an SM; a CTA walks several query tiles (causal: the pair {nt-1-x, x}).
+//   head_dim 128 (NT = 2): one CTA per SM, two query tiles (A, B) sharing a 1-stage K/V ring, all 512 TMEM columns,
+//     row sums in registers, the MMA warps converged with an elected issuing lane.
+// Roles:  warp 0 TMA producer | warp 1 (and 3 for tile B) MMA issuer | warp 2 TMEM allocator | warps 4.. softmax:
+//   tcgen05.ld the whole 128-column S row into registers and hand the S buffer straight back, so S(j+1) is computed
+//   while this block's softmax runs -> chunk-level masking (only blocks that need it) -> running max -> packed FFMA2
+//   scale-and-subtract + exp2 -> bf16 P; the first 64 keys are published on their own barrier so that half of the
+//   P.V MMAs are issued under the remaining exponentials; O is rescaled in TMEM lazily, only when the row max grew by
+//   more than 2^8.
+// The LR_ATTN_* switches below are the experiments of rounds 1 and 2. Product defaults: P_TMEM, P_HALF, EXP_FIRST,
+// DESC32, CHUNK_MASK, FFMA2 = 1, MMA_WARP = 2; everything else is 0 = measured neutral or slower (each comment says
+// by how much; tools/attn_ab.py builds any combination and times it interleaved against the product).
 #include <cuda.h>
 
 #include <atomic>
