@@ -31,7 +31,8 @@ def _v(p_half=0, exp_first=0, desc32=0, mma_warp=0, **extra):
 VARIANTS = {
     "base": {},
     "old": None,   # the product object code from before the hand-off experiments were added (kept .so, never rebuilt)
-    "r02a": _v(),                                   # the product of the first half of round 2
+    "r02a": _v(),                                   # the hand-off switches of the first half of round 2 (other defaults)
+    "r02a_full": _v(LR_ATTN_CHUNK_MASK=0, LR_ATTN_FFMA2=0),   # = the product of the first half of round 2, every later switch off
     "hoist40": _v(LR_ATTN_HOIST_DESC=1),
     "aux48": _v(LR_ATTN_AUX_REGS=48),
     "aux56": _v(LR_ATTN_AUX_REGS=56),
