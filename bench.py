@@ -412,9 +412,10 @@ def main():
         flops = 2.0 * (sum(rows) / max(len(rows), 1)) * (2 * cfg.intermediate_size) * K   # mean per launch
         ach = flops / (sum(durs) / len(durs) * 1e-3) / 1e12 if durs else None
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_gate_up_traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as f:
+        tname = next((n for n in ("r02_gate_up_traffic.json", "r01_gate_up_traffic.json")
+                      if os.path.exists(os.path.join(ROOT, "profiles", n))), None)
+        if tname:
+            with open(os.path.join(ROOT, "profiles", tname)) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
         line = {
             "metric": "text-image pairs scored/sec", "value": value, "unit": "pairs/s", "n_gpus": world,
@@ -431,7 +432,7 @@ def main():
                          "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": (ach / peaks["bf16_sustained"]) if ach else None, "traffic": traffic,
                          "traffic_source": "static: one ncu --set full capture of this kernel at this shape "
-                                           "(profiles/r01_gate_up_traffic.json), not measured in this run",
+                                           f"(profiles/{tname}), not measured in this run",
                          "launches_timed": len(durs), "flops_per_launch": flops,
                          "rows_per_launch": (sum(rows) / len(rows)) if rows else None, "peak_source": peaks["source"]},
             "step_roofline": {"tflop_per_pair": TFLOP_PER_PAIR,
