@@ -21,6 +21,8 @@ namespace pair {
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kEpiWarps = 8;
+constexpr int kDefaultL2Hints = 18;  // A evict_last | C evict_first << 4 (see l2_policy()): -5 ... -14 % DRAM reads, -1 % time
+                                     // (profiles/r02_gemm_l2_hints.txt); LR_GEMM_L2_HINTS overrides
 constexpr int kGemmThreads = 128 + kEpiWarps * 32;
 constexpr int kStagingBytes = 32 * 128;  // one [32 rows x 64 bf16] tile per epilogue warp
 
@@ -58,6 +60,28 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tma
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar), "r"(c0), "r"(c1)
       : "memory");
+}
+// L2 eviction-priority hints (kind: 0 normal, 1 evict_first, 2 evict_last). The output tile is written once and never
+// read by this kernel, the A slab of a raster group is re-read by every n-tile of the group, W streams once per group.
+__device__ __forceinline__ uint64_t l2_policy(int kind) {
+  uint64_t p;
+  if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* smem_dst, const void* tmap, uint32_t leader_bar, int c0,
+                                                      int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const void* tmap, const void* smem_src, int c0, int c1, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(policy)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
@@ -114,6 +138,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   // be NULL (table row = output row)
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
+  // bits 16.. of group_m carry the L2 hint kinds of the launch: A (2 bits) | W (2 bits) | C (2 bits)
+  const int l2_hints = group_m >> 16;
+  group_m &= 0xffff;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -164,6 +191,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint64_t pol_a = l2_policy(l2_hints & 3), pol_b = l2_policy((l2_hints >> 2) & 3);
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         int m_blk, n_blk;
         tile_coords(tile, num_m, num_n, group_m, m_blk, n_blk);
@@ -171,8 +199,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);  // bytes of both CTAs
           const uint32_t lbar = map_to_cta(smem_u32(&full_bar[stage]), 0);
-          tma_load_2d_pair(smem_a + stage * Cfg::kStageBytesA, &tma_a, lbar, kb * kBK, m_blk * 2 * kBM + rank * kBM);
-          tma_load_2d_pair(smem_b + stage * Cfg::kStageBytesB, &tma_b, lbar, kb * kBK, n_blk * BN + rank * (BN / 2));
+          tma_load_2d_pair_hint(smem_a + stage * Cfg::kStageBytesA, &tma_a, lbar, kb * kBK,
+                                m_blk * 2 * kBM + rank * kBM, pol_a);
+          tma_load_2d_pair_hint(smem_b + stage * Cfg::kStageBytesB, &tma_b, lbar, kb * kBK,
+                                n_blk * BN + rank * (BN / 2), pol_b);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -227,6 +257,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     static_assert(kChunks >= 1, "tile too narrow for 8 epilogue warps");
     uint8_t* stg = smem_c + ew * kStagingBytes;
     uint8_t* my_row = stg + lane * 128;
+    const uint64_t pol_c = l2_policy((l2_hints >> 4) & 3);
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -357,7 +388,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tma_c, stg, col_g, row0);
+          tma_store_2d_hint(&tma_c, stg, col_g, row0, pol_c);
           tma_store_commit();
         }
       }
@@ -446,6 +477,12 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, void* C, 
     const int g = atoi(e);
     if (g > 0) group_m = g;
   }
+  // L2 eviction hints, 2 bits each for A | W << 2 | C << 4 (0 normal, 1 evict_first, 2 evict_last)
+  static const int l2_hints = [] {
+    const char* e = getenv("LR_GEMM_L2_HINTS");
+    return e ? atoi(e) : kDefaultL2Hints;
+  }();
+  group_m |= (l2_hints & 63) << 16;
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, M, N, K, reinterpret_cast<const bf16*>(bias),
                                                         reinterpret_cast<const bf16*>(R), ldr, group_m, pos, rope_hd,
                                                         reinterpret_cast<const bf16*>(lin_bias));

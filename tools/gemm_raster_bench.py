@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--groups", default="0,2,4,6,8,12,16,24,32,64")
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--warm", type=int, default=2)
+    ap.add_argument("--once", action="store_true", help="one launch per shape, no timing (for ncu --metrics dram__bytes_*)")
     a = ap.parse_args()
     dev = "cuda"
     for name, M, N, K, epi in SHAPES:
@@ -35,6 +36,10 @@ def main():
         C = torch.empty(M, No, device=dev, dtype=torch.bfloat16)
         R = torch.randn(M, No, device=dev, dtype=torch.bfloat16) if epi == L.EPI_RESIDUAL else None
         res = []
+        if a.once:
+            ops.gemm(A, W, C, M, N, K, epi, None, R)
+            torch.cuda.synchronize()
+            continue
         for g in a.groups.split(","):
             os.environ["LR_GEMM_GROUP_M"] = g
             for _ in range(a.warm):
