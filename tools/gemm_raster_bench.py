@@ -1,6 +1,11 @@
 #!/usr/bin/env python
 """Raster experiment for the CTA-pair GEMM: time the large-K decoder shapes for several m-group sizes
-(LR_GEMM_GROUP_M overrides the launch heuristic). python tools/gemm_raster_bench.py"""
+(LR_GEMM_GROUP_M overrides the launch heuristic). python tools/gemm_raster_bench.py
+
+CAVEAT (r02): the group sizes are timed one after the other, so on a power-capped B200 the FIRST entry is favoured by
+up to 10 % ("g0" = the heuristic and the explicit value of the same heuristic differ by that much,
+gpurun_out/r02_gemm_raster_hints.txt). Use it for > 15 % effects only, or interleave as tools/attn_ab.py does.
+--once: one launch per shape for `ncu --metrics dram__bytes_read.sum,...` (tools/gpu_gemm_l2_hints.sh)."""
 import os
 import sys
 
